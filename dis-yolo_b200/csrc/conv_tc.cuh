@@ -1,0 +1,77 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a: interface.
+//
+// Every conv of the network (reference: yolo/yolo3_net_pos.py:109-151, tf.nn.conv2d + BN + leaky
+// [+ residual]) except conv1 (Cin=3) runs through ONE kernel: a persistent, warp-specialised GEMM
+// whose A operand rows are pixels of a P1-layout activation (common.cuh).  The K loop is a list of
+// SEGMENTS; a segment is (A tensor map, constant row shift, first channel, #K-chunks):
+//   1x1 conv            1 segment   shift 0
+//   3x3 stride-1 conv   9 segments  shift (kh-1)*(W+1)+(kw-1)
+//   3x3 stride-2 conv   9 segments over the space-to-depth copy of the input (TF 'SAME' pads 0
+//                       before / 1 after): tap (kh,kw) -> shift (kh>>1)*(Wo+1)+(kw>>1),
+//                       channel block ((kh&1)*2+(kw&1))*Cin
+//   1x1 over concat     2 segments  (skip tensor, upsampled tensor)   [skip, up] order (:291)
+// so A is always a plain 2D TMA tile load with out-of-bounds zero fill -- no im2col buffer.
+#pragma once
+#include "common.cuh"
+
+namespace dy {
+
+constexpr int kBlockM = 128;
+constexpr int kMaxSeg = 9;
+constexpr int kMaxStages = 8;
+
+enum OutMode : int {
+  OUT_NONE = 0,
+  OUT_SAME = 1,         // bf16 P1, same geometry as the GEMM row space
+  OUT_S2D = 2,          // bf16 P1 of the space-to-depth tensor [N, H/2+1, W/2+1, 4*C]
+  OUT_UP2 = 3,          // bf16 P1 of the 2x nearest-neighbour upsampled tensor [N, 2H+1, 2W+1, C]
+  OUT_F32_COMPACT = 4,  // fp32 [N,H,W,cout]          (detection heads)
+  OUT_F32_PLANAR = 5    // fp32 [N,cout,H,W]          (position-sensitive score maps)
+};
+
+struct OutDesc {
+  void* ptr;
+  int mode;
+  int ld;  // destination row pitch in elements
+};
+
+struct ConvSeg {
+  int map;     // 0 -> mapA0, 1 -> mapA1
+  int shift;   // row shift added to the tile's first row
+  int col0;    // first channel (element index along the A tensor's inner dimension)
+  int nchunk;  // number of K chunks in this segment
+};
+
+struct ConvParams {
+  int M;           // GEMM rows = N*(H+1)*(W+1)
+  int H, W;        // valid output extent (row space is (H+1)x(W+1) per image)
+  int cout;        // real output channels
+  int block_n;     // N tile: multiple of 16, <= 256
+  int n_tiles_m, n_tiles_n;
+  int num_seg;
+  ConvSeg seg[kMaxSeg];
+  int num_chunks;  // sum of seg[].nchunk
+  int num_stages;  // smem pipeline depth
+  int tmem_cols;   // power of two >= 2*block_n, >= 32
+  const float* scale;  // [n_tiles_n*block_n] folded BN scale (1 for biased convs)
+  const float* shift;  // [n_tiles_n*block_n] folded BN shift / bias
+  float alpha;
+  int act;                          // 1 -> leaky relu max(alpha*x, x)
+  const __nv_bfloat16* residual;    // P1, same geometry, added AFTER the activation (:148-151)
+  int res_ld;
+  OutDesc out[2];
+};
+
+// Build a 2D bf16 tensor map over a row-major [rows, cols] matrix with a (box_cols x box_rows) box.
+// box_cols*2 bytes must be 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B).
+int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld_elems,
+                 int box_cols, int box_rows);
+
+size_t conv_tc_smem_bytes(int kchunk, int block_n, int stages);
+int conv_tc_pick_stages(int kchunk, int block_n);
+
+// kchunk in {32, 64}
+int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                   const ConvParams& p, int num_sms, cudaStream_t stream);
+
+}  // namespace dy

@@ -1,0 +1,1012 @@
+// libdisyolo_b200: the network object, the layer plan and the C ABI (include/disyolo.h).
+//
+// Reference being replaced: class YOLONet (yolo/yolo3_net_pos.py:12-975) driven through
+// tf.Session.run by train_yolo3_mask.py / calculate_test_map.py.
+#include <map>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+
+#include "../../include/disyolo.h"
+#include "common.cuh"
+#include "conv_misc.cuh"
+#include "conv_tc.cuh"
+#include "postproc.cuh"
+
+namespace dy {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<long long> g_launches{0};
+static inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------------
+// the 82-layer topology (yolo3_net_pos.py:159-412).  src 0 = the input image.
+// ---------------------------------------------------------------------------------------------
+struct LayerDef {
+  int id, src0, src1, res;   // src1: layer whose output is 2x-upsampled and concatenated AFTER src0
+  int cin0, cin1, cout, k, s;
+  bool bn;
+  int H;                     // output spatial size (square)
+};
+
+static std::vector<LayerDef> build_defs(int S) {
+  std::vector<LayerDef> d(83);
+  auto add = [&](int id, int src0, int cin0, int cout, int k, int s, int H, int res = 0, int src1 = 0, int cin1 = 0,
+                 bool bn = true) {
+    d[id] = LayerDef{id, src0, src1, res, cin0, cin1, cout, k, s, bn, H};
+  };
+  add(1, 0, 3, 32, 3, 1, S);                                  // :159-161
+  add(2, 1, 32, 64, 3, 2, S / 2);                             // :165-167
+  add(3, 2, 64, 32, 1, 1, S / 2);                             // :169-172
+  add(4, 3, 32, 64, 3, 1, S / 2, 2);                          // :174-176 (+shortcut)
+  add(5, 4, 64, 128, 3, 2, S / 4);                            // :180-182
+  add(6, 5, 128, 64, 1, 1, S / 4);
+  add(7, 6, 64, 128, 3, 1, S / 4, 5);
+  add(8, 7, 128, 64, 1, 1, S / 4);
+  add(9, 8, 64, 128, 3, 1, S / 4, 7);                         // skip3 :202
+  add(10, 9, 128, 256, 3, 2, S / 8);                          // :204-206
+  for (int i = 0; i < 8; ++i) {                               // :208-218
+    add(11 + 2 * i, 10 + 2 * i, 256, 128, 1, 1, S / 8);
+    add(12 + 2 * i, 11 + 2 * i, 128, 256, 3, 1, S / 8, 10 + 2 * i);
+  }
+  add(27, 26, 256, 512, 3, 2, S / 16);                        // :222-224
+  for (int i = 0; i < 8; ++i) {                               // :226-236
+    add(28 + 2 * i, 27 + 2 * i, 512, 256, 1, 1, S / 16);
+    add(29 + 2 * i, 28 + 2 * i, 256, 512, 3, 1, S / 16, 27 + 2 * i);
+  }
+  add(44, 43, 512, 1024, 3, 2, S / 32);                       // :240-242
+  for (int i = 0; i < 4; ++i) {                               // :244-254
+    add(45 + 2 * i, 44 + 2 * i, 1024, 512, 1, 1, S / 32);
+    add(46 + 2 * i, 45 + 2 * i, 512, 1024, 3, 1, S / 32, 44 + 2 * i);
+  }
+  add(53, 52, 1024, 512, 1, 1, S / 32);                       // :258-272
+  add(54, 53, 512, 1024, 3, 1, S / 32);
+  add(55, 54, 1024, 512, 1, 1, S / 32);
+  add(56, 55, 512, 1024, 3, 1, S / 32);
+  add(57, 56, 1024, 512, 1, 1, S / 32);
+  add(58, 57, 512, 1024, 3, 1, S / 32);                       // :274-276
+  add(59, 58, 1024, 24, 1, 1, S / 32, 0, 0, 0, false);        // :277-279 biased, linear
+  add(60, 57, 512, 256, 1, 1, S / 32);                        // :285-287
+  add(61, 43, 512, 256, 1, 1, S / 16, 0, 60, 256);            // concat[skip5, up] :291-295
+  add(62, 61, 256, 512, 3, 1, S / 16);
+  add(63, 62, 512, 256, 1, 1, S / 16);
+  add(64, 63, 256, 512, 3, 1, S / 16);
+  add(65, 64, 512, 256, 1, 1, S / 16);
+  add(66, 65, 256, 512, 3, 1, S / 16);                        // :309-311
+  add(67, 66, 512, 24, 1, 1, S / 16, 0, 0, 0, false);         // :312-314
+  add(68, 65, 256, 128, 1, 1, S / 16);                        // :320-322
+  add(69, 26, 256, 128, 1, 1, S / 8, 0, 68, 128);             // concat[skip4, up] :326-330
+  add(70, 69, 128, 256, 3, 1, S / 8);
+  add(71, 70, 256, 128, 1, 1, S / 8);
+  add(72, 71, 128, 256, 3, 1, S / 8);
+  add(73, 72, 256, 128, 1, 1, S / 8);
+  add(74, 73, 128, 256, 3, 1, S / 8);                         // :344-346
+  add(75, 74, 256, 24, 1, 1, S / 8, 0, 0, 0, false);          // :347-349
+  add(76, 73, 128, 64, 1, 1, S / 8);                          // :381-383
+  add(77, 9, 128, 64, 1, 1, S / 4, 0, 76, 64);                // concat[skip3, up] :387-391
+  add(78, 77, 64, 128, 3, 1, S / 4);
+  add(79, 78, 128, 32, 1, 1, S / 4);                          // :396-398
+  add(80, 4, 64, 32, 1, 1, S / 2, 0, 79, 32);                 // concat[skip2, up] :402-406
+  add(81, 80, 32, 64, 3, 1, S / 2);
+  add(82, 81, 64, 9, 1, 1, S / 2, 0, 0, 0, false);            // :410-412
+  return d;
+}
+
+static void tf_same_pad(int in, int k, int s, int* before) {
+  const int out = (in + s - 1) / s;
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  *before = total / 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one tensor-core conv: descriptors + launch parameters
+// ---------------------------------------------------------------------------------------------
+struct TcPlan {
+  int kchunk = 64;
+  CUtensorMap a0, a1, b;
+  ConvParams p;
+};
+
+struct TcConvDesc {
+  const __nv_bfloat16* a0 = nullptr;   // src0 operand: P1 SAME (s=1) or S2D (s=2) tensor
+  const __nv_bfloat16* a1 = nullptr;   // UP2 tensor of src1 or null
+  int cin0 = 0, cin1 = 0, cout = 0, k = 1, s = 1;
+  int H = 0, W = 0;                    // output extent
+  int max_batch = 1;
+  const __nv_bfloat16* wpk = nullptr;  // [cout_pad][K] packed weights
+  int cout_pad = 0;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int act = 0;
+  float alpha = 0.1f;
+  const __nv_bfloat16* residual = nullptr;
+  OutDesc out[2];
+};
+
+static int pick_block_n(int cout_pad, long long rows, int num_sms) {
+  static const int cands[] = {256, 128, 64, 32, 16};
+  int best = 16;
+  for (int bn : cands) {
+    if (cout_pad % bn != 0) continue;
+    best = bn;
+    const long long tiles = ((rows + kBlockM - 1) / kBlockM) * (cout_pad / bn);
+    if (tiles >= num_sms || bn <= 64) break;     // enough CTAs, or tiles would get too thin
+    // otherwise try the next smaller tile to spread over more SMs
+  }
+  return best;
+}
+
+static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
+  DY_CHECK(d.k == 1 || d.k == 3, "kernel size must be 1 or 3");
+  DY_CHECK(d.s == 1 || (d.s == 2 && d.k == 3 && d.cin1 == 0), "stride 2 only for 3x3 without concat");
+  DY_CHECK(d.cin0 % 32 == 0 && d.cin1 % 32 == 0, "input channels must be multiples of 32");
+  DY_CHECK(d.cin1 == 0 || d.k == 1, "concat only feeds 1x1 convs");
+  const int kchunk = (d.cin0 % 64 == 0 && d.cin1 % 64 == 0) ? 64 : 32;
+  const int Hp = d.H + 1, Wp = d.W + 1;
+  const long long rows_max = (long long)d.max_batch * Hp * Wp;
+  const int K = d.k * d.k * d.cin0 + d.cin1;
+  ConvParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  plan->kchunk = kchunk;
+  p.H = d.H;
+  p.W = d.W;
+  p.cout = d.cout;
+  p.block_n = pick_block_n(d.cout_pad, rows_max, num_sms);
+  p.n_tiles_n = d.cout_pad / p.block_n;
+  p.num_stages = conv_tc_pick_stages(kchunk, p.block_n);
+  int tc = 32;
+  while (tc < 2 * p.block_n) tc <<= 1;
+  p.tmem_cols = tc;
+  p.scale = d.scale;
+  p.shift = d.shift;
+  p.alpha = d.alpha;
+  p.act = d.act;
+  p.residual = d.residual;
+  p.res_ld = d.cout;
+  p.out[0] = d.out[0];
+  p.out[1] = d.out[1];
+  int ns = 0, nchunks = 0;
+  if (d.k == 1) {
+    p.seg[ns++] = ConvSeg{0, 0, 0, d.cin0 / kchunk};
+    if (d.cin1 > 0) p.seg[ns++] = ConvSeg{1, 0, 0, d.cin1 / kchunk};
+  } else if (d.s == 1) {
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.seg[ns++] = ConvSeg{0, (kh - 1) * Wp + (kw - 1), 0, d.cin0 / kchunk};
+  } else {
+    // TF 'SAME', stride 2, even input: pad 0 before / 1 after -> input pixel (2oy+kh, 2ox+kw)
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        p.seg[ns++] = ConvSeg{0, (kh >> 1) * Wp + (kw >> 1), (((kh & 1) << 1) | (kw & 1)) * d.cin0, d.cin0 / kchunk};
+  }
+  for (int i = 0; i < ns; ++i) nchunks += p.seg[i].nchunk;
+  p.num_seg = ns;
+  p.num_chunks = nchunks;
+  DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
+  const int a0_cols = (d.s == 2) ? 4 * d.cin0 : d.cin0;
+  DY_TRY(make_tmap_2d(&plan->a0, d.a0, rows_max, a0_cols, a0_cols, kchunk, kBlockM));
+  if (d.cin1 > 0) {
+    DY_TRY(make_tmap_2d(&plan->a1, d.a1, rows_max, d.cin1, d.cin1, kchunk, kBlockM));
+  } else {
+    plan->a1 = plan->a0;
+  }
+  DY_TRY(make_tmap_2d(&plan->b, d.wpk, d.cout_pad, K, K, kchunk, p.block_n));
+  return DY_OK;
+}
+
+static int run_tc_plan(TcPlan& plan, int B, int num_sms, cudaStream_t st) {
+  ConvParams& p = plan.p;
+  const long long M = (long long)B * (p.H + 1) * (p.W + 1);
+  DY_CHECK(M < (1ll << 31) - 256, "too many rows");
+  p.M = (int)M;
+  p.n_tiles_m = (int)((M + kBlockM - 1) / kBlockM);
+  note_launch();
+  return launch_conv_tc(plan.kchunk, plan.a0, plan.a1, plan.b, p, num_sms, st);
+}
+
+// pack HWIO fp32 weights -> [cout_pad][K] bf16 (K index = (kh*k+kw)*cin + ci, zero rows beyond cout)
+static void pack_weights_bf16(const float* w_hwio, int K, int cout, int cout_pad, std::vector<__nv_bfloat16>* out) {
+  out->assign((size_t)cout_pad * K, __float2bfloat16(0.f));
+  for (int kk = 0; kk < K; ++kk)
+    for (int co = 0; co < cout; ++co) (*out)[(size_t)co * K + kk] = __float2bfloat16(w_hwio[(size_t)kk * cout + co]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the net
+// ---------------------------------------------------------------------------------------------
+struct LayerState {
+  LayerDef def;
+  std::vector<float> w, gamma, beta, mean, var, bias;   // host copies as loaded
+  int cout_pad = 0, K = 0;
+  float* d_w_f32 = nullptr;
+  __nv_bfloat16* d_wpk = nullptr;
+  float* d_scale = nullptr;
+  float* d_shift = nullptr;
+  // outputs
+  bool need_same = false, need_s2d = false, need_up = false;
+  __nv_bfloat16* same = nullptr;
+  __nv_bfloat16* s2d = nullptr;
+  __nv_bfloat16* up = nullptr;
+  float* f32 = nullptr;     // bf16 mode: heads (compact) / score maps (planar); fp32 mode: every layer, NHWC
+  TcPlan plan;
+  bool planned = false;
+};
+
+}  // namespace dy
+
+using namespace dy;
+
+struct dy_net {
+  dy_config cfg;
+  int S = 0;                       // image size
+  int num_sms = 148;
+  std::vector<LayerState> L;       // 1..82
+  bool finalized = false;
+  std::vector<void*> allocs;
+  // post-processing workspace
+  int n0 = 0, cap = 0;
+  Cand* cand = nullptr;
+  int* cand_count = nullptr;
+  int* sel = nullptr;
+  int* sel_cnt = nullptr;
+  int* edges = nullptr;
+  int* raw_count = nullptr;
+  float* det_raw_ws = nullptr;
+  float* det_box_ws = nullptr;
+  int* det_count_ws = nullptr;
+  float* images_ws = nullptr;      // device staging for dy_forward_host
+  float* windows_ws = nullptr;
+  float* masks_ws = nullptr;
+  cudaStream_t host_stream = nullptr;
+};
+
+namespace dy {
+
+static int dev_alloc(dy_net* net, void** p, size_t bytes, bool zero = true) {
+  if (bytes == 0) bytes = 16;
+  DY_CUDA(cudaMalloc(p, bytes));
+  net->allocs.push_back(*p);
+  if (zero) DY_CUDA(cudaMemset(*p, 0, bytes));
+  return DY_OK;
+}
+
+static size_t p1_elems(int B, int H, int W, int C) { return (size_t)B * (H + 1) * (W + 1) * C; }
+
+static int allocate_buffers(dy_net* net) {
+  const int B = net->cfg.max_batch;
+  auto& L = net->L;
+  const bool bf16 = net->cfg.precision == DY_PRECISION_BF16;
+  for (int n = 1; n <= 82; ++n) {
+    const LayerDef& d = L[n].def;
+    L[n].cout_pad = (d.cout + 15) / 16 * 16;
+    L[n].K = d.k * d.k * d.cin0 + d.cin1;
+  }
+  if (bf16) {
+    for (int n = 1; n <= 82; ++n) {
+      const LayerDef& d = L[n].def;
+      if (d.src0 > 0) {
+        if (d.s == 2) L[d.src0].need_s2d = true; else L[d.src0].need_same = true;
+      }
+      if (d.src1 > 0) L[d.src1].need_up = true;
+      if (d.res > 0) L[d.res].need_same = true;
+    }
+    for (int n = 1; n <= 82; ++n) {
+      const LayerDef& d = L[n].def;
+      LayerState& s = L[n];
+      if (!d.bn) {   // heads + score maps: fp32
+        DY_TRY(dev_alloc(net, (void**)&s.f32, (size_t)B * d.H * d.H * d.cout * 4));
+        continue;
+      }
+      if (s.need_same) DY_TRY(dev_alloc(net, (void**)&s.same, p1_elems(B, d.H, d.H, d.cout) * 2));
+      if (s.need_s2d) DY_TRY(dev_alloc(net, (void**)&s.s2d, p1_elems(B, d.H / 2, d.H / 2, 4 * d.cout) * 2));
+      if (s.need_up) DY_TRY(dev_alloc(net, (void**)&s.up, p1_elems(B, 2 * d.H, 2 * d.H, d.cout) * 2));
+    }
+  } else {
+    for (int n = 1; n <= 82; ++n) {
+      const LayerDef& d = L[n].def;
+      DY_TRY(dev_alloc(net, (void**)&L[n].f32, (size_t)B * d.H * d.H * d.cout * 4));
+    }
+  }
+  // post-processing workspace
+  const int g0 = net->S / 8, g1 = net->S / 16, g2 = net->S / 32;
+  net->n0 = 3 * (g0 * g0 + g1 * g1 + g2 * g2);
+  net->cap = net->n0;
+  const int md = net->cfg.max_detection, C = net->cfg.num_classes;
+  DY_TRY(dev_alloc(net, (void**)&net->cand, (size_t)B * net->cap * sizeof(Cand)));
+  DY_TRY(dev_alloc(net, (void**)&net->cand_count, (size_t)B * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->sel, (size_t)B * C * md * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->sel_cnt, (size_t)B * C * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->edges, (size_t)B * md * 2 * (kMaxK + 1) * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->raw_count, (size_t)B * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->det_raw_ws, (size_t)B * md * 6 * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->det_box_ws, (size_t)B * md * 6 * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->det_count_ws, (size_t)B * 4));
+  return DY_OK;
+}
+
+static int fold_and_upload(dy_net* net, int n) {
+  LayerState& s = net->L[n];
+  const LayerDef& d = s.def;
+  const size_t wn = (size_t)s.K * d.cout;
+  if (s.w.size() != wn) {
+    set_error("missing or mis-shaped weights for convolutional" + std::to_string(n));
+    return DY_ERR_STATE;
+  }
+  std::vector<float> scale(s.cout_pad, 0.f), shift(s.cout_pad, 0.f);
+  if (d.bn) {
+    if ((int)s.gamma.size() != d.cout || (int)s.beta.size() != d.cout || (int)s.mean.size() != d.cout ||
+        (int)s.var.size() != d.cout) {
+      set_error("missing BatchNorm variables for convolutional" + std::to_string(n));
+      return DY_ERR_STATE;
+    }
+    for (int c = 0; c < d.cout; ++c) {
+      // inference-mode BN with moving statistics (yolo3_net_pos.py:81,101), folded
+      const float inv = s.gamma[c] / sqrtf(s.var[c] + net->cfg.bn_eps);
+      scale[c] = inv;
+      shift[c] = s.beta[c] - s.mean[c] * inv;
+    }
+  } else {
+    if ((int)s.bias.size() != d.cout) {
+      set_error("missing biases for convolutional" + std::to_string(n));
+      return DY_ERR_STATE;
+    }
+    for (int c = 0; c < d.cout; ++c) {
+      scale[c] = 1.f;
+      shift[c] = s.bias[c];
+    }
+  }
+  if (!s.d_scale) {
+    DY_TRY(dev_alloc(net, (void**)&s.d_scale, (size_t)s.cout_pad * 4));
+    DY_TRY(dev_alloc(net, (void**)&s.d_shift, (size_t)s.cout_pad * 4));
+  }
+  DY_CUDA(cudaMemcpy(s.d_scale, scale.data(), (size_t)s.cout_pad * 4, cudaMemcpyHostToDevice));
+  DY_CUDA(cudaMemcpy(s.d_shift, shift.data(), (size_t)s.cout_pad * 4, cudaMemcpyHostToDevice));
+  const bool bf16 = net->cfg.precision == DY_PRECISION_BF16;
+  if (!bf16 || n == 1) {
+    if (!s.d_w_f32) DY_TRY(dev_alloc(net, (void**)&s.d_w_f32, wn * 4));
+    DY_CUDA(cudaMemcpy(s.d_w_f32, s.w.data(), wn * 4, cudaMemcpyHostToDevice));
+  }
+  if (bf16 && n > 1) {
+    std::vector<__nv_bfloat16> pk;
+    pack_weights_bf16(s.w.data(), s.K, d.cout, s.cout_pad, &pk);
+    if (!s.d_wpk) DY_TRY(dev_alloc(net, (void**)&s.d_wpk, pk.size() * 2));
+    DY_CUDA(cudaMemcpy(s.d_wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice));
+  }
+  return DY_OK;
+}
+
+static int plan_layer(dy_net* net, int n) {
+  LayerState& s = net->L[n];
+  const LayerDef& d = s.def;
+  TcConvDesc c;
+  c.a0 = (d.s == 2) ? net->L[d.src0].s2d : net->L[d.src0].same;
+  c.a1 = d.src1 > 0 ? net->L[d.src1].up : nullptr;
+  DY_CHECK(c.a0 != nullptr && (d.src1 == 0 || c.a1 != nullptr), "layer input buffer missing");
+  c.cin0 = d.cin0;
+  c.cin1 = d.cin1;
+  c.cout = d.cout;
+  c.k = d.k;
+  c.s = d.s;
+  c.H = d.H;
+  c.W = d.H;
+  c.max_batch = net->cfg.max_batch;
+  c.wpk = s.d_wpk;
+  c.cout_pad = s.cout_pad;
+  c.scale = s.d_scale;
+  c.shift = s.d_shift;
+  c.act = d.bn ? 1 : 0;
+  c.alpha = net->cfg.alpha;
+  c.residual = d.res > 0 ? net->L[d.res].same : nullptr;
+  int no = 0;
+  c.out[0] = OutDesc{nullptr, OUT_NONE, 0};
+  c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
+  if (!d.bn) {
+    c.out[no++] = OutDesc{s.f32, n == 82 ? OUT_F32_PLANAR : OUT_F32_COMPACT, d.cout};
+  } else {
+    if (s.need_same) c.out[no++] = OutDesc{s.same, OUT_SAME, d.cout};
+    if (s.need_s2d) c.out[no++] = OutDesc{s.s2d, OUT_S2D, 4 * d.cout};
+    if (s.need_up) {
+      DY_CHECK(no < 2, "too many output forms");
+      c.out[no++] = OutDesc{s.up, OUT_UP2, d.cout};
+    }
+  }
+  DY_CHECK(no >= 1 && no <= 2, "layer has no consumer");
+  DY_TRY(build_tc_plan(c, net->num_sms, &s.plan));
+  s.planned = true;
+  return DY_OK;
+}
+
+static int run_network_bf16(dy_net* net, const float* images, int B, cudaStream_t st) {
+  auto& L = net->L;
+  note_launch();
+  DY_TRY(launch_conv1(images, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S, L[1].s2d,
+                      L[1].same, st));
+  for (int n = 2; n <= 82; ++n) DY_TRY(run_tc_plan(L[n].plan, B, net->num_sms, st));
+  return DY_OK;
+}
+
+static int run_network_fp32(dy_net* net, const float* images, int B, cudaStream_t st) {
+  auto& L = net->L;
+  for (int n = 1; n <= 82; ++n) {
+    const LayerDef& d = L[n].def;
+    RefConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src0 = d.src0 == 0 ? images : L[d.src0].f32;
+    a.src1 = d.src1 > 0 ? L[d.src1].f32 : nullptr;
+    a.w = L[n].d_w_f32;
+    a.scale = L[n].d_scale;
+    a.shift = L[n].d_shift;
+    a.residual = d.res > 0 ? L[d.res].f32 : nullptr;
+    a.out = L[n].f32;
+    a.Ho = a.Wo = d.H;
+    a.Hi = a.Wi = d.H * d.s;
+    a.c0 = d.cin0;
+    a.c1 = d.cin1;
+    a.cout = d.cout;
+    a.k = d.k;
+    a.s = d.s;
+    tf_same_pad(a.Hi, d.k, d.s, &a.pad_t);
+    a.pad_l = a.pad_t;
+    a.act = d.bn ? 1 : 0;
+    a.alpha = net->cfg.alpha;
+    note_launch();
+    DY_TRY(launch_conv_ref(a, B, st));
+  }
+  return DY_OK;
+}
+
+static int run_network(dy_net* net, const float* images, int B, cudaStream_t st) {
+  DY_CHECK(net->finalized, "dy_finalize_weights has not been called");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
+  if (net->cfg.precision == DY_PRECISION_BF16) return run_network_bf16(net, images, B, st);
+  return run_network_fp32(net, images, B, st);
+}
+
+// decode -> NMS -> top-k (-> masks) on the given head / score maps
+static int run_detect(dy_net* net, const float* y8, const float* y16, const float* y32, int B, const float* windows,
+                      float thresh, float* dense_box, int* dense_cls, float* dense_score, float* det_raw,
+                      float* det_box, int* det_count, cudaStream_t st) {
+  DecodeArgs da;
+  memset(&da, 0, sizeof(da));
+  da.yolo[0] = y8; da.yolo[1] = y16; da.yolo[2] = y32;
+  da.g[0] = net->S / 8; da.g[1] = net->S / 16; da.g[2] = net->S / 32;
+  da.B = B;
+  da.num_class = net->cfg.num_classes;
+  da.net = 32 * da.g[2];
+  memcpy(da.anchors, net->cfg.anchors, sizeof(da.anchors));
+  da.windows = windows;
+  da.thresh = thresh;
+  da.dense_box = dense_box; da.dense_cls = dense_cls; da.dense_score = dense_score;
+  da.cand = net->cand; da.cand_count = net->cand_count; da.cap = net->cap;
+  DY_CUDA(cudaMemsetAsync(net->cand_count, 0, (size_t)B * 4, st));
+  note_launch();
+  DY_TRY(launch_decode(da, st));
+  if (det_box == nullptr && det_raw == nullptr) return DY_OK;
+  NmsArgs na;
+  na.cand = net->cand; na.cand_count = net->cand_count; na.cap = net->cap;
+  na.B = B; na.num_class = net->cfg.num_classes; na.max_det = net->cfg.max_detection;
+  na.iou_thr = net->cfg.iou_threshold;
+  na.sel = net->sel; na.sel_cnt = net->sel_cnt;
+  note_launch();
+  DY_TRY(launch_nms(na, st));
+  FinalizeArgs fa;
+  fa.cand = net->cand; fa.cap = net->cap; fa.B = B; fa.num_class = net->cfg.num_classes;
+  fa.max_det = net->cfg.max_detection; fa.sel = net->sel; fa.sel_cnt = net->sel_cnt;
+  fa.S = net->S / 2; fa.k = net->cfg.k_map;
+  fa.det_raw = det_raw ? det_raw : net->det_raw_ws;
+  fa.raw_count = net->raw_count;
+  fa.det_box = det_box ? det_box : net->det_box_ws;
+  fa.det_count = det_count ? det_count : net->det_count_ws;
+  fa.edges = net->edges;
+  note_launch();
+  DY_TRY(launch_finalize(fa, st));
+  return DY_OK;
+}
+
+static int run_masks(dy_net* net, const float* score, int layout, int B, const int* det_count, float* masks,
+                     cudaStream_t st) {
+  MaskArgs ma;
+  const int Sm = net->S / 2, kk = net->cfg.k_map * net->cfg.k_map;
+  ma.score = score;
+  if (layout == 1) {   // planar [B,kk,S,S]
+    ma.s_img = (long long)kk * Sm * Sm; ma.s_ch = (long long)Sm * Sm; ma.s_row = Sm; ma.s_pix = 1;
+  } else {             // NHWC [B,S,S,kk]
+    ma.s_img = (long long)kk * Sm * Sm; ma.s_ch = 1; ma.s_row = (long long)Sm * kk; ma.s_pix = kk;
+  }
+  ma.det_count = det_count; ma.edges = net->edges;
+  ma.B = B; ma.max_det = net->cfg.max_detection; ma.S = Sm; ma.k = net->cfg.k_map;
+  ma.out = masks;
+  note_launch();
+  return launch_masks(ma, st);
+}
+
+}  // namespace dy
+
+namespace dy {
+__global__ void pack_cands_kernel(const float* box, const int* cls, const float* score, int N, float thresh,
+                                  Cand* cand, int* cand_count, int cap) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float s = score[(long long)b * N + i];
+  if (s > thresh) {
+    const int slot = atomicAdd(cand_count + b, 1);
+    if (slot < cap) {
+      const float4 bx = reinterpret_cast<const float4*>(box)[(long long)b * N + i];
+      Cand c;
+      c.y1 = bx.x; c.x1 = bx.y; c.y2 = bx.z; c.x2 = bx.w;
+      c.score = s; c.idx = i; c.cls = cls[(long long)b * N + i]; c.pad = 0;
+      cand[(long long)b * cap + slot] = c;
+    }
+  }
+}
+__global__ void sel_to_idx_kernel(const Cand* cand, int cap, const float* det_raw, const int* raw_count, int max_det,
+                                  const int* sel, const int* sel_cnt, int num_class, int* sel_idx, int* sel_count) {
+  // recover the candidate index of every output row by matching (score, box) is fragile; instead
+  // re-rank here exactly like finalize_kernel: rows are ordered by (score desc, idx asc).
+  const int b = blockIdx.x;
+  const Cand* cd = cand + (long long)b * cap;
+  if (threadIdx.x != 0) return;
+  int E = 0;
+  for (int c = 0; c < num_class; ++c) E += sel_cnt[b * num_class + c];
+  int written = 0;
+  for (int c = 0; c < num_class; ++c) {
+    const int* s = sel + ((long long)b * num_class + c) * max_det;
+    for (int i = 0; i < sel_cnt[b * num_class + c]; ++i) {
+      const Cand me = cd[s[i]];
+      int r = 0;
+      for (int c2 = 0; c2 < num_class; ++c2) {
+        const int* s2 = sel + ((long long)b * num_class + c2) * max_det;
+        for (int j = 0; j < sel_cnt[b * num_class + c2]; ++j) {
+          const Cand o = cd[s2[j]];
+          if (o.score > me.score || (o.score == me.score && o.idx < me.idx)) ++r;
+        }
+      }
+      if (r < max_det) {
+        sel_idx[b * max_det + r] = me.idx;
+        ++written;
+      }
+    }
+  }
+  for (int r = written; r < max_det; ++r) sel_idx[b * max_det + r] = -1;
+  sel_count[b] = written;
+}
+}  // namespace dy
+
+namespace dy {
+__global__ void edges_from_boxes_kernel(const float* det_box, const int* det_count, int max_det, int S, int k,
+                                        int* edges) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < det_count[b] && d < max_det; d += blockDim.x) {
+    const float* row = det_box + ((long long)b * max_det + d) * 6;
+    const float Sf = (float)S;
+    float pb[4];
+    for (int i = 0; i < 4; ++i) pb[i] = rintf(__fmul_rn(row[i], Sf));
+    const float sub_w = __fdiv_rn(__fsub_rn(pb[3], pb[1]), (float)k);
+    const float sub_h = __fdiv_rn(__fsub_rn(pb[2], pb[0]), (float)k);
+    int* ed = edges + ((long long)b * max_det + d) * (2 * (kMaxK + 1));
+    ed[0] = (int)pb[1];
+    ed[kMaxK + 1] = (int)pb[0];
+    for (int j = 1; j < k; ++j) {
+      ed[j] = (int)rintf(__fadd_rn(pb[1], __fmul_rn((float)j, sub_w)));
+      ed[kMaxK + 1 + j] = (int)rintf(__fadd_rn(pb[0], __fmul_rn((float)j, sub_h)));
+    }
+    ed[k] = (int)pb[3];
+    ed[kMaxK + 1 + k] = (int)pb[2];
+  }
+}
+}  // namespace dy
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* dy_version(void) { return "disyolo_b200 0.1 sm_100a"; }
+const char* dy_last_error(void) { return g_last_error.c_str(); }
+
+int dy_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t dy_launch_count(int32_t reset) {
+  long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+
+int dy_create(const dy_config* cfg, dy_net** out) {
+  DY_CHECK(cfg != nullptr && out != nullptr, "null argument");
+  DY_CHECK(cfg->image_size >= 32 && cfg->image_size % 32 == 0, "image_size must be a positive multiple of 32");
+  DY_CHECK(cfg->num_classes == 3, "the 24-channel heads of convolutional59/67/75 imply 3 classes");
+  DY_CHECK(cfg->k_map == 3, "convolutional82 emits 9 = 3x3 score maps");
+  DY_CHECK(cfg->max_batch >= 1, "max_batch");
+  DY_CHECK(cfg->max_detection >= 1 && cfg->max_detection <= 4096, "max_detection");
+  DY_CHECK(cfg->precision == DY_PRECISION_BF16 || cfg->precision == DY_PRECISION_FP32, "precision");
+  int ndev = dy_device_count();
+  if (ndev <= 0) {
+    set_error("no CUDA device: libdisyolo_b200 has no CPU fallback");
+    return DY_ERR_CUDA;
+  }
+  DY_CHECK(cfg->device >= 0 && cfg->device < ndev, "device ordinal");
+  DY_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  DY_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (cfg->precision == DY_PRECISION_BF16 && prop.major != 10) {
+    set_error(std::string("the bf16 engine needs an sm_100 GPU (tcgen05/TMEM); found ") + prop.name);
+    return DY_ERR_UNSUPPORTED;
+  }
+  dy_net* net = new dy_net();
+  net->cfg = *cfg;
+  net->S = cfg->image_size;
+  net->num_sms = prop.multiProcessorCount;
+  std::vector<LayerDef> defs = build_defs(net->S);
+  net->L.resize(83);
+  for (int n = 1; n <= 82; ++n) net->L[n].def = defs[n];
+  int rc = allocate_buffers(net);
+  if (rc != DY_OK) {
+    dy_destroy(net);
+    return rc;
+  }
+  *out = net;
+  return DY_OK;
+}
+
+int dy_destroy(dy_net* net) {
+  if (!net) return DY_OK;
+  cudaSetDevice(net->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : net->allocs) cudaFree(p);
+  if (net->host_stream) cudaStreamDestroy(net->host_stream);
+  delete net;
+  return DY_OK;
+}
+
+int dy_load_weights(dy_net* net, const char* tf_name, const float* host, const int64_t* shape, int32_t ndim) {
+  DY_CHECK(net && tf_name && host && shape, "null argument");
+  std::string name(tf_name);
+  const std::string prefix = "yolo/convolutional";
+  if (name.compare(0, prefix.size(), prefix) != 0) {
+    set_error("unknown variable " + name);
+    return DY_ERR_NOTFOUND;
+  }
+  size_t p = prefix.size();
+  int n = 0;
+  while (p < name.size() && name[p] >= '0' && name[p] <= '9') n = n * 10 + (name[p++] - '0');
+  if (n < 1 || n > 82 || p >= name.size() || name[p] != '/') {
+    set_error("unknown variable " + name);
+    return DY_ERR_NOTFOUND;
+  }
+  const std::string what = name.substr(p + 1);
+  LayerState& s = net->L[n];
+  const LayerDef& d = s.def;
+  size_t count = 1;
+  for (int i = 0; i < ndim; ++i) count *= (size_t)shape[i];
+  std::vector<float>* dst = nullptr;
+  if (what == "weights") {
+    DY_CHECK(ndim == 4 && shape[0] == d.k && shape[1] == d.k && shape[2] == d.cin0 + d.cin1 && shape[3] == d.cout,
+             "weights must be HWIO [k,k,cin,cout]");
+    dst = &s.w;
+  } else {
+    DY_CHECK(ndim == 1 && shape[0] == d.cout, "per-channel variable must be [cout]");
+    if (what == "biases") dst = &s.bias;
+    else if (what == "BatchNorm/gamma") dst = &s.gamma;
+    else if (what == "BatchNorm/beta") dst = &s.beta;
+    else if (what == "BatchNorm/moving_mean") dst = &s.mean;
+    else if (what == "BatchNorm/moving_variance") dst = &s.var;
+  }
+  if (!dst) {
+    set_error("unknown variable " + name);
+    return DY_ERR_NOTFOUND;
+  }
+  dst->assign(host, host + count);
+  net->finalized = false;
+  return DY_OK;
+}
+
+int dy_finalize_weights(dy_net* net) {
+  DY_CHECK(net, "null net");
+  DY_CUDA(cudaSetDevice(net->cfg.device));
+  for (int n = 1; n <= 82; ++n) DY_TRY(fold_and_upload(net, n));
+  if (net->cfg.precision == DY_PRECISION_BF16)
+    for (int n = 2; n <= 82; ++n) DY_TRY(plan_layer(net, n));
+  DY_CUDA(cudaDeviceSynchronize());
+  net->finalized = true;
+  return DY_OK;
+}
+
+int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream) {
+  DY_CHECK(net && images_dev, "null argument");
+  return run_network(net, images_dev, B, (cudaStream_t)stream);
+}
+
+static void head_ptrs(dy_net* net, const float** y8, const float** y16, const float** y32, const float** mp,
+                      int* layout) {
+  *y8 = net->L[75].f32;
+  *y16 = net->L[67].f32;
+  *y32 = net->L[59].f32;
+  *mp = net->L[82].f32;
+  *layout = net->cfg.precision == DY_PRECISION_BF16 ? 1 : 0;
+}
+
+int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* windows_dev, float det_thresh,
+               float* det_raw_dev, float* det_box_dev, int32_t* det_count_dev, float* masks_dev, void* stream) {
+  DY_CHECK(net && images_dev && windows_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DY_TRY(run_network(net, images_dev, B, st));
+  const float *y8, *y16, *y32, *mp;
+  int layout;
+  head_ptrs(net, &y8, &y16, &y32, &mp, &layout);
+  float* box = det_box_dev ? det_box_dev : net->det_box_ws;
+  int* cnt = det_count_dev ? det_count_dev : net->det_count_ws;
+  DY_TRY(run_detect(net, y8, y16, y32, B, windows_dev, det_thresh, nullptr, nullptr, nullptr, det_raw_dev, box, cnt,
+                    st));
+  if (masks_dev) DY_TRY(run_masks(net, mp, layout, B, cnt, masks_dev, st));
+  return DY_OK;
+}
+
+int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const float* windows_host, float det_thresh,
+                    float* det_raw_host, float* det_box_host, int32_t* det_count_host, float* masks_host) {
+  DY_CHECK(net && images_host && windows_host && det_box_host && det_count_host, "null argument");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
+  DY_CUDA(cudaSetDevice(net->cfg.device));
+  const int S = net->S, Sm = S / 2, md = net->cfg.max_detection;
+  if (!net->host_stream) DY_CUDA(cudaStreamCreateWithFlags(&net->host_stream, cudaStreamNonBlocking));
+  if (!net->images_ws) {
+    DY_TRY(dev_alloc(net, (void**)&net->images_ws, (size_t)net->cfg.max_batch * S * S * 3 * 4, false));
+    DY_TRY(dev_alloc(net, (void**)&net->windows_ws, (size_t)net->cfg.max_batch * 4 * 4, false));
+    DY_TRY(dev_alloc(net, (void**)&net->masks_ws, (size_t)net->cfg.max_batch * md * Sm * Sm * 4, false));
+  }
+  cudaStream_t st = net->host_stream;
+  DY_CUDA(cudaMemcpyAsync(net->images_ws, images_host, (size_t)B * S * S * 3 * 4, cudaMemcpyHostToDevice, st));
+  DY_CUDA(cudaMemcpyAsync(net->windows_ws, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, st));
+  DY_TRY(dy_forward(net, net->images_ws, B, net->windows_ws, det_thresh, net->det_raw_ws, net->det_box_ws,
+                    net->det_count_ws, masks_host ? net->masks_ws : nullptr, st));
+  DY_CUDA(cudaMemcpyAsync(det_count_host, net->det_count_ws, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  DY_CUDA(cudaMemcpyAsync(det_box_host, net->det_box_ws, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
+  if (det_raw_host)
+    DY_CUDA(cudaMemcpyAsync(det_raw_host, net->det_raw_ws, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
+  DY_CUDA(cudaStreamSynchronize(st));
+  if (masks_host) {
+    const size_t per = (size_t)Sm * Sm;
+    for (int b = 0; b < B; ++b) {
+      const int n = det_count_host[b];
+      if (n > 0)
+        DY_CUDA(cudaMemcpyAsync(masks_host + (size_t)b * md * per, net->masks_ws + (size_t)b * md * per,
+                                (size_t)n * per * 4, cudaMemcpyDeviceToHost, st));
+    }
+    DY_CUDA(cudaStreamSynchronize(st));
+  }
+  return DY_OK;
+}
+
+int dy_layer_shape(dy_net* net, int32_t layer, int32_t* h, int32_t* w, int32_t* c) {
+  DY_CHECK(net && layer >= 1 && layer <= 82, "layer must be 1..82");
+  const LayerDef& d = net->L[layer].def;
+  if (h) *h = d.H;
+  if (w) *w = d.H;
+  if (c) *c = d.cout;
+  return DY_OK;
+}
+
+int dy_get_activation(dy_net* net, int32_t layer, int32_t B, float* out_dev, void* stream) {
+  DY_CHECK(net && out_dev && layer >= 1 && layer <= 82, "bad argument");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LayerState& s = net->L[layer];
+  const LayerDef& d = s.def;
+  const size_t n = (size_t)B * d.H * d.H * d.cout;
+  if (net->cfg.precision == DY_PRECISION_FP32) {
+    DY_CUDA(cudaMemcpyAsync(out_dev, s.f32, n * 4, cudaMemcpyDeviceToDevice, st));
+    return DY_OK;
+  }
+  note_launch();
+  if (!d.bn) {
+    if (layer == 82) return launch_planar_to_nhwc(s.f32, out_dev, B, d.H, d.H, d.cout, st);
+    DY_CUDA(cudaMemcpyAsync(out_dev, s.f32, n * 4, cudaMemcpyDeviceToDevice, st));
+    return DY_OK;
+  }
+  if (s.same) return launch_p1_to_nhwc(s.same, out_dev, B, d.H, d.H, d.cout, FORM_SAME, st);
+  if (s.s2d) return launch_p1_to_nhwc(s.s2d, out_dev, B, d.H, d.H, d.cout, FORM_S2D, st);
+  if (s.up) return launch_p1_to_nhwc(s.up, out_dev, B, d.H, d.H, d.cout, FORM_UP2, st);
+  set_error("layer has no buffer");
+  return DY_ERR_STATE;
+}
+
+int dy_get_yolo(dy_net* net, int32_t scale, int32_t B, float* out_dev, void* stream) {
+  DY_CHECK(net && out_dev && scale >= 0 && scale <= 2, "bad argument");
+  static const int layer_of[3] = {75, 67, 59};
+  return dy_get_activation(net, layer_of[scale], B, out_dev, stream);
+}
+
+int dy_get_mask_pos(dy_net* net, int32_t B, float* out_dev, void* stream) {
+  return dy_get_activation(net, 82, B, out_dev, stream);
+}
+
+int dy_decode(dy_net* net, const float* yolo8_dev, const float* yolo16_dev, const float* yolo32_dev, int32_t B,
+              const float* windows_dev, float* box_dev, int32_t* cls_dev, float* score_dev, void* stream) {
+  DY_CHECK(net && yolo8_dev && yolo16_dev && yolo32_dev && windows_dev && box_dev && cls_dev && score_dev,
+           "null argument");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch");
+  return run_detect(net, yolo8_dev, yolo16_dev, yolo32_dev, B, windows_dev, 3.0e38f, box_dev, cls_dev, score_dev,
+                    nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int dy_detect(dy_net* net, const float* yolo8_dev, const float* yolo16_dev, const float* yolo32_dev, int32_t B,
+              const float* windows_dev, float det_thresh, float* det_raw_dev, float* det_box_dev,
+              int32_t* det_count_dev, void* stream) {
+  DY_CHECK(net && yolo8_dev && yolo16_dev && yolo32_dev && windows_dev && det_box_dev && det_count_dev,
+           "null argument");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch");
+  return run_detect(net, yolo8_dev, yolo16_dev, yolo32_dev, B, windows_dev, det_thresh, nullptr, nullptr, nullptr,
+                    det_raw_dev, det_box_dev, det_count_dev, (cudaStream_t)stream);
+}
+
+int dy_nms(dy_net* net, const float* box_dev, const int32_t* cls_dev, const float* score_dev, int32_t B, int32_t N,
+           float det_thresh, int32_t* sel_idx_dev, int32_t* sel_count_dev, float* det_raw_dev, void* stream) {
+  DY_CHECK(net && box_dev && cls_dev && score_dev && sel_idx_dev && sel_count_dev, "null argument");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch");
+  DY_CHECK(N >= 1 && N <= net->cap, "N exceeds the net's candidate capacity");
+  cudaStream_t st = (cudaStream_t)stream;
+  DY_CUDA(cudaMemsetAsync(net->cand_count, 0, (size_t)B * 4, st));
+  dim3 grid((N + 255) / 256, B);
+  note_launch(2);
+  pack_cands_kernel<<<grid, 256, 0, st>>>(box_dev, cls_dev, score_dev, N, det_thresh, net->cand, net->cand_count,
+                                          net->cap);
+  DY_CUDA(cudaGetLastError());
+  NmsArgs na;
+  na.cand = net->cand; na.cand_count = net->cand_count; na.cap = net->cap;
+  na.B = B; na.num_class = net->cfg.num_classes; na.max_det = net->cfg.max_detection;
+  na.iou_thr = net->cfg.iou_threshold;
+  na.sel = net->sel; na.sel_cnt = net->sel_cnt;
+  DY_TRY(launch_nms(na, st));
+  FinalizeArgs fa;
+  fa.cand = net->cand; fa.cap = net->cap; fa.B = B; fa.num_class = net->cfg.num_classes;
+  fa.max_det = net->cfg.max_detection; fa.sel = net->sel; fa.sel_cnt = net->sel_cnt;
+  fa.S = net->S / 2; fa.k = net->cfg.k_map;
+  fa.det_raw = det_raw_dev ? det_raw_dev : net->det_raw_ws;
+  fa.raw_count = net->raw_count;
+  fa.det_box = net->det_box_ws;
+  fa.det_count = net->det_count_ws;
+  fa.edges = net->edges;
+  note_launch(2);
+  DY_TRY(launch_finalize(fa, st));
+  sel_to_idx_kernel<<<B, 32, 0, st>>>(net->cand, net->cap, fa.det_raw, net->raw_count, fa.max_det, net->sel,
+                                      net->sel_cnt, fa.num_class, sel_idx_dev, sel_count_dev);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int dy_assemble_masks(dy_net* net, const float* score_dev, int32_t layout, int32_t B, const float* det_box_dev,
+                      const int32_t* det_count_dev, float* masks_dev, void* stream) {
+  DY_CHECK(net && score_dev && det_box_dev && det_count_dev && masks_dev, "null argument");
+  DY_CHECK(layout == 0 || layout == 1, "layout: 0 = NHWC, 1 = planar");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  note_launch();
+  edges_from_boxes_kernel<<<B, 64, 0, st>>>(det_box_dev, det_count_dev, net->cfg.max_detection, net->S / 2,
+                                            net->cfg.k_map, net->edges);
+  DY_CUDA(cudaGetLastError());
+  return run_masks(net, score_dev, layout, B, det_count_dev, masks_dev, st);
+}
+
+int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
+                  const float* w_host, int32_t k, int32_t stride, int32_t cout, const float* scale_host,
+                  const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,
+                  void* stream) {
+  DY_CHECK(x_dev && w_host && scale_host && shift_host && out_dev, "null argument");
+  DY_CHECK(k == 1 || k == 3, "k");
+  DY_CHECK(stride == 1 || stride == 2, "stride");
+  DY_CHECK(H % stride == 0 && W % stride == 0, "extent must divide the stride");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Ho = H / stride, Wo = W / stride;
+  const int K = k * k * cin;
+  int rc = DY_OK;
+  std::vector<void*> tmp;
+  auto talloc = [&](void** p, size_t bytes) -> int {
+    DY_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    tmp.push_back(*p);
+    DY_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, st));
+    return DY_OK;
+  };
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    for (void* p : tmp) cudaFree(p);
+  };
+  const int cout_pad = (cout + 15) / 16 * 16;
+  std::vector<float> sc(cout_pad, 0.f), sh(cout_pad, 0.f);
+  memcpy(sc.data(), scale_host, (size_t)cout * 4);
+  memcpy(sh.data(), shift_host, (size_t)cout * 4);
+  float *d_sc = nullptr, *d_sh = nullptr;
+  if ((rc = talloc((void**)&d_sc, (size_t)cout_pad * 4)) || (rc = talloc((void**)&d_sh, (size_t)cout_pad * 4))) {
+    cleanup();
+    return rc;
+  }
+  cudaMemcpyAsync(d_sc, sc.data(), (size_t)cout_pad * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_sh, sh.data(), (size_t)cout_pad * 4, cudaMemcpyHostToDevice, st);
+
+  if (precision == DY_PRECISION_FP32) {
+    float* d_w = nullptr;
+    if ((rc = talloc((void**)&d_w, (size_t)K * cout * 4))) { cleanup(); return rc; }
+    cudaMemcpyAsync(d_w, w_host, (size_t)K * cout * 4, cudaMemcpyHostToDevice, st);
+    RefConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src0 = x_dev; a.w = d_w; a.scale = d_sc; a.shift = d_sh; a.residual = residual_dev; a.out = out_dev;
+    a.Hi = H; a.Wi = W; a.Ho = Ho; a.Wo = Wo; a.c0 = cin; a.c1 = 0; a.cout = cout; a.k = k; a.s = stride;
+    tf_same_pad(H, k, stride, &a.pad_t);
+    tf_same_pad(W, k, stride, &a.pad_l);
+    a.act = act; a.alpha = alpha;
+    note_launch();
+    rc = launch_conv_ref(a, B, st);
+    cleanup();
+    return rc;
+  }
+
+  // ---- bf16 tensor-core engine ----
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cin == 3) {
+    if (!(k == 3 && stride == 1 && cout == 32)) {
+      set_error("cin=3 is only supported as convolutional1 (3->32, 3x3, stride 1)");
+      cleanup();
+      return DY_ERR_UNSUPPORTED;
+    }
+    float* d_w = nullptr;
+    __nv_bfloat16* d_out = nullptr;
+    if ((rc = talloc((void**)&d_w, (size_t)K * cout * 4)) ||
+        (rc = talloc((void**)&d_out, p1_elems(B, H, W, cout) * 2))) { cleanup(); return rc; }
+    cudaMemcpyAsync(d_w, w_host, (size_t)K * cout * 4, cudaMemcpyHostToDevice, st);
+    note_launch(2);
+    rc = launch_conv1(x_dev, d_w, d_sc, d_sh, alpha, B, H, W, nullptr, d_out, st);
+    if (rc == DY_OK) rc = launch_p1_to_nhwc(d_out, out_dev, B, H, W, cout, FORM_SAME, st);
+    cleanup();
+    return rc;
+  }
+  if (cin % 32 != 0) {
+    set_error("the bf16 engine needs cin % 32 == 0");
+    cleanup();
+    return DY_ERR_UNSUPPORTED;
+  }
+  __nv_bfloat16 *d_a = nullptr, *d_wpk = nullptr, *d_res = nullptr, *d_out = nullptr;
+  const size_t a_elems = stride == 2 ? p1_elems(B, Ho, Wo, 4 * cin) : p1_elems(B, H, W, cin);
+  std::vector<__nv_bfloat16> pk;
+  pack_weights_bf16(w_host, K, cout, cout_pad, &pk);
+  if ((rc = talloc((void**)&d_a, a_elems * 2)) || (rc = talloc((void**)&d_wpk, pk.size() * 2)) ||
+      (rc = talloc((void**)&d_out, p1_elems(B, Ho, Wo, cout_pad) * 2))) { cleanup(); return rc; }
+  cudaMemcpyAsync(d_wpk, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice, st);
+  note_launch(3);
+  rc = launch_nhwc_to_p1(x_dev, d_a, B, H, W, cin, stride == 2 ? FORM_S2D : FORM_SAME, st);
+  if (rc == DY_OK && residual_dev) {
+    if ((rc = talloc((void**)&d_res, p1_elems(B, Ho, Wo, cout) * 2)) == DY_OK)
+      rc = launch_nhwc_to_p1(residual_dev, d_res, B, Ho, Wo, cout, FORM_SAME, st);
+  }
+  if (rc == DY_OK && cout % 16 != 0) {
+    set_error("dy_conv_layer (bf16) needs cout % 16 == 0");
+    rc = DY_ERR_UNSUPPORTED;
+  }
+  if (rc == DY_OK) {
+    TcConvDesc c;
+    c.a0 = d_a; c.cin0 = cin; c.cout = cout; c.k = k; c.s = stride; c.H = Ho; c.W = Wo; c.max_batch = B;
+    c.wpk = d_wpk; c.cout_pad = cout_pad; c.scale = d_sc; c.shift = d_sh; c.act = act; c.alpha = alpha;
+    c.residual = d_res;
+    c.out[0] = OutDesc{d_out, OUT_SAME, cout};
+    c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
+    TcPlan plan;
+    rc = build_tc_plan(c, num_sms, &plan);
+    if (rc == DY_OK) rc = run_tc_plan(plan, B, num_sms, st);
+    if (rc == DY_OK) rc = launch_p1_to_nhwc(d_out, out_dev, B, Ho, Wo, cout, FORM_SAME, st);
+  }
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

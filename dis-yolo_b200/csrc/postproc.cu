@@ -1,0 +1,412 @@
+// YOLO head decode + threshold, per-class greedy NMS on a warp-ballot alive bitmask, top-k and
+// position-sensitive mask assembly.  Reference: yolo/yolo3_net_pos.py:465-628, :862-952.
+// All arithmetic is fp32 with explicit round-to-nearest intrinsics where the reference (TensorFlow)
+// evaluates separate multiply / add ops, so that no FMA contraction changes a comparison.
+#include "postproc.cuh"
+
+namespace dy {
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// ------------------------------------------------------------------------------------------
+// decode: one thread per candidate (interpret_output :465-514 + filter_detections :523-561)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+  const int b = blockIdx.y;
+  const int n0 = 3 * (a.g[0] * a.g[0] + a.g[1] * a.g[1] + a.g[2] * a.g[2]);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n0) return;
+  const int off1 = 3 * a.g[0] * a.g[0];
+  const int off2 = off1 + 3 * a.g[1] * a.g[1];
+  const int j = idx < off1 ? 0 : (idx < off2 ? 1 : 2);
+  const int local = idx - (j == 0 ? 0 : (j == 1 ? off1 : off2));
+  const int g = a.g[j];
+  const int anchor = local % 3;
+  const int cell = local / 3;
+  const int cy = cell / g, cx = cell % g;
+  const int depth = 5 + a.num_class;
+  const float* p = a.yolo[j] + (((long long)b * g + cy) * g + cx) * (3 * depth) + anchor * depth;
+
+  float t[5 + kMaxClasses];
+  if (depth == 8) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    t[0] = u.x; t[1] = u.y; t[2] = u.z; t[3] = u.w;
+    t[4] = v.x; t[5] = v.y; t[6] = v.z; t[7] = v.w;
+  } else {
+    for (int i = 0; i < depth; ++i) t[i] = __ldg(p + i);
+  }
+  // class-specific confidence = sigmoid(obj) * max softmax(cls)   (:528-548, softmax not sigmoid)
+  float mx = t[5];
+  int cls = 0;
+  for (int c = 1; c < a.num_class; ++c)
+    if (t[5 + c] > mx) { mx = t[5 + c]; cls = c; }     // first maximum, like tf.argmax
+  float sum = 0.f;
+  for (int c = 0; c < a.num_class; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(t[5 + c], mx)));
+  const float pmax = __fdiv_rn(1.f, sum);              // exp(0)/sum
+  const float score = __fmul_rn(sigmoidf_(t[4]), pmax);
+  // box (:487-505): xy = (cell + sigmoid(t_xy)) / grid ; wh = exp(t_wh) * anchor / net
+  const float gf = (float)g, nf = (float)a.net;
+  const float xc = __fdiv_rn(__fadd_rn((float)cx, sigmoidf_(t[0])), gf);
+  const float yc = __fdiv_rn(__fadd_rn((float)cy, sigmoidf_(t[1])), gf);
+  const float w = __fdiv_rn(__fmul_rn(expf(t[2]), a.anchors[(3 * j + anchor) * 2 + 0]), nf);
+  const float h = __fdiv_rn(__fmul_rn(expf(t[3]), a.anchors[(3 * j + anchor) * 2 + 1]), nf);
+  const float hh = __fdiv_rn(h, 2.f), hw = __fdiv_rn(w, 2.f);
+  float y1 = __fsub_rn(yc, hh), x1 = __fsub_rn(xc, hw), y2 = __fadd_rn(yc, hh), x2 = __fadd_rn(xc, hw);
+  // clip_boxes_graph (:940-952)
+  const float wy1 = __ldg(a.windows + b * 4 + 0), wx1 = __ldg(a.windows + b * 4 + 1);
+  const float wy2 = __ldg(a.windows + b * 4 + 2), wx2 = __ldg(a.windows + b * 4 + 3);
+  y1 = fmaxf(fminf(y1, wy2), wy1);
+  x1 = fmaxf(fminf(x1, wx2), wx1);
+  y2 = fmaxf(fminf(y2, wy2), wy1);
+  x2 = fmaxf(fminf(x2, wx2), wx1);
+
+  if (a.dense_box) {
+    reinterpret_cast<float4*>(a.dense_box)[(long long)b * n0 + idx] = make_float4(y1, x1, y2, x2);
+    a.dense_cls[(long long)b * n0 + idx] = cls;
+    a.dense_score[(long long)b * n0 + idx] = score;
+  }
+  if (score > a.thresh) {
+    const int slot = atomicAdd(a.cand_count + b, 1);
+    if (slot < a.cap) {
+      Cand c;
+      c.y1 = y1; c.x1 = x1; c.y2 = y2; c.x2 = x2;
+      c.score = score; c.idx = idx; c.cls = cls; c.pad = 0;
+      a.cand[(long long)b * a.cap + slot] = c;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NMS
+// ------------------------------------------------------------------------------------------
+// ordering key: higher score first, ties -> lower candidate index (our definition; TF1's
+// priority_queue leaves ties unspecified)
+__device__ __forceinline__ unsigned long long cand_key(const Cand& c) {
+  return ((unsigned long long)__float_as_uint(c.score) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)c.idx);
+}
+
+// IoU exactly as tf.image.non_max_suppression evaluates it (fp32, separate mul/add/div)
+__device__ __forceinline__ float iou_tf(const float4 a, const float4 b) {  // (y1,x1,y2,x2) as (x,y,z,w)
+  const float ay1 = fminf(a.x, a.z), ay2 = fmaxf(a.x, a.z), ax1 = fminf(a.y, a.w), ax2 = fmaxf(a.y, a.w);
+  const float by1 = fminf(b.x, b.z), by2 = fmaxf(b.x, b.z), bx1 = fminf(b.y, b.w), bx2 = fmaxf(b.y, b.w);
+  const float aa = __fmul_rn(__fsub_rn(ay2, ay1), __fsub_rn(ax2, ax1));
+  const float ab = __fmul_rn(__fsub_rn(by2, by1), __fsub_rn(bx2, bx1));
+  if (aa <= 0.f || ab <= 0.f) return 0.f;
+  const float iy1 = fmaxf(ay1, by1), ix1 = fmaxf(ax1, bx1), iy2 = fminf(ay2, by2), ix2 = fminf(ax2, bx2);
+  const float inter = __fmul_rn(fmaxf(__fsub_rn(iy2, iy1), 0.f), fmaxf(__fsub_rn(ix2, ix1), 0.f));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+}
+
+struct KeyPos {
+  unsigned long long key;
+  int pos;
+};
+
+__device__ __forceinline__ KeyPos kp_max(KeyPos a, KeyPos b) { return (b.key > a.key) ? b : a; }
+
+__device__ __forceinline__ KeyPos warp_kp_max(KeyPos v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    KeyPos t;
+    t.key = __shfl_xor_sync(0xffffffffu, v.key, o);
+    t.pos = __shfl_xor_sync(0xffffffffu, v.pos, o);
+    v = kp_max(v, t);
+  }
+  return v;
+}
+
+// One CTA per (class, image).  The class's survivors live as an "alive" bitmask in shared memory,
+// one 32-bit word per 32 candidates, rebuilt with warp ballots.  Each round: block-wide arg-max of
+// the ordering key over alive candidates = next box TF's greedy loop would select; one pass then
+// clears every alive candidate whose IoU with it exceeds the threshold (strict >) while gathering
+// the next round's arg-max.  At most max_det rounds (max_output_size, :566-573).
+__global__ void __launch_bounds__(256) nms_kernel(NmsArgs a) {
+  extern __shared__ uint32_t alive[];
+  __shared__ unsigned long long red_key[8];
+  __shared__ int red_pos[8];
+  __shared__ unsigned long long best_key_s;
+  __shared__ int best_pos_s;
+
+  const int c = blockIdx.x, b = blockIdx.y;
+  int n = a.cand_count[b];
+  if (n > a.cap) n = a.cap;
+  const Cand* cd = a.cand + (long long)b * a.cap;
+  const int nwords = (n + 31) >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  int* sel = a.sel + ((long long)b * a.num_class + c) * a.max_det;
+
+  KeyPos best;
+  best.key = 0ull;
+  best.pos = -1;
+  for (int w = warp; w < nwords; w += nwarps) {
+    const int i = w * 32 + lane;
+    bool al = false;
+    if (i < n) {
+      const Cand ci = cd[i];
+      al = (ci.cls == c);
+      if (al) {
+        KeyPos t;
+        t.key = cand_key(ci);
+        t.pos = i;
+        best = kp_max(best, t);
+      }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, al);
+    if (lane == 0) alive[w] = m;
+  }
+  int nsel = 0;
+  while (true) {
+    best = warp_kp_max(best);
+    if (lane == 0) {
+      red_key[warp] = best.key;
+      red_pos[warp] = best.pos;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      KeyPos v;
+      v.key = lane < nwarps ? red_key[lane] : 0ull;
+      v.pos = lane < nwarps ? red_pos[lane] : -1;
+      v = warp_kp_max(v);
+      if (lane == 0) {
+        best_key_s = v.key;
+        best_pos_s = v.pos;
+      }
+    }
+    __syncthreads();
+    const unsigned long long bk = best_key_s;
+    const int bp = best_pos_s;
+    if (bk == 0ull) break;
+    if (threadIdx.x == 0) sel[nsel] = bp;
+    ++nsel;
+    if (nsel >= a.max_det) break;
+    const Cand sc = cd[bp];
+    const float4 sb = make_float4(sc.y1, sc.x1, sc.y2, sc.x2);
+    best.key = 0ull;
+    best.pos = -1;
+    for (int w = warp; w < nwords; w += nwarps) {
+      const uint32_t word = alive[w];
+      if (word == 0u) continue;                   // warp-uniform
+      const int i = w * 32 + lane;
+      bool al = (word >> lane) & 1u;
+      if (al) {
+        if (i == bp) {
+          al = false;
+        } else {
+          const Cand ci = cd[i];
+          if (iou_tf(make_float4(ci.y1, ci.x1, ci.y2, ci.x2), sb) > a.iou_thr) {
+            al = false;
+          } else {
+            KeyPos t;
+            t.key = cand_key(ci);
+            t.pos = i;
+            best = kp_max(best, t);
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, al);
+      if (lane == 0) alive[w] = m;
+    }
+  }
+  if (threadIdx.x == 0) a.sel_cnt[b * a.num_class + c] = nsel;
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: union of per-class keep sets -> top-k by score (ties: lower index) -> zero padded
+// [max_det,6] rows (:590-628); then val_test's rounding / positive-size filter and the integer
+// bin edges of assemble_kmask_from_box (:876-897).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void box_edges(const Cand& c, int S, int k, float (&pb)[4], int* gx, int* gy) {
+  const float Sf = (float)S;
+  pb[0] = rintf(__fmul_rn(c.y1, Sf));    // tf.round = half-to-even
+  pb[1] = rintf(__fmul_rn(c.x1, Sf));
+  pb[2] = rintf(__fmul_rn(c.y2, Sf));
+  pb[3] = rintf(__fmul_rn(c.x2, Sf));
+  const float sub_w = __fdiv_rn(__fsub_rn(pb[3], pb[1]), (float)k);
+  const float sub_h = __fdiv_rn(__fsub_rn(pb[2], pb[0]), (float)k);
+  gx[0] = (int)pb[1];
+  gy[0] = (int)pb[0];
+  for (int j = 1; j < k; ++j) {
+    gx[j] = (int)rintf(__fadd_rn(pb[1], __fmul_rn((float)j, sub_w)));
+    gy[j] = (int)rintf(__fadd_rn(pb[0], __fmul_rn((float)j, sub_h)));
+  }
+  gx[k] = (int)pb[3];
+  gy[k] = (int)pb[2];
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
+  extern __shared__ unsigned long long fin_smem[];
+  const int Emax = a.num_class * a.max_det;
+  unsigned long long* keys = fin_smem;                       // [Emax]
+  int* pos = reinterpret_cast<int*>(keys + Emax);            // [Emax]
+  int* rank_pos = pos + Emax;                                // [max_det] cand position by rank
+  int* offs = rank_pos + a.max_det;                          // [max_det] output slot or -1
+  __shared__ int E_s, nvalid_s;
+
+  const int b = blockIdx.x;
+  const Cand* cd = a.cand + (long long)b * a.cap;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    for (int c = 0; c < a.num_class; ++c) {
+      const int cnt = a.sel_cnt[b * a.num_class + c];
+      const int* s = a.sel + ((long long)b * a.num_class + c) * a.max_det;
+      for (int i = 0; i < cnt; ++i) pos[e++] = s[i];
+    }
+    E_s = e;
+  }
+  __syncthreads();
+  const int E = E_s;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) keys[e] = cand_key(cd[pos[e]]);
+  __syncthreads();
+  const int nraw = E < a.max_det ? E : a.max_det;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const unsigned long long k = keys[e];
+    int r = 0;
+    for (int j = 0; j < E; ++j) r += (keys[j] > k) ? 1 : 0;
+    if (r < a.max_det) rank_pos[r] = pos[e];
+  }
+  __syncthreads();
+  // raw rows + keep flags
+  for (int r = threadIdx.x; r < a.max_det; r += blockDim.x) {
+    float* row = a.det_raw + ((long long)b * a.max_det + r) * 6;
+    if (r < nraw) {
+      const Cand c = cd[rank_pos[r]];
+      row[0] = c.y1; row[1] = c.x1; row[2] = c.y2; row[3] = c.x2;
+      row[4] = (float)c.cls; row[5] = c.score;
+      float pb[4];
+      int gx[kMaxK + 1], gy[kMaxK + 1];
+      box_edges(c, a.S, a.k, pb, gx, gy);
+      offs[r] = (__fsub_rn(pb[2], pb[0]) > 0.f && __fsub_rn(pb[3], pb[1]) > 0.f) ? 1 : 0;
+    } else {
+      for (int i = 0; i < 6; ++i) row[i] = 0.f;
+      offs[r] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nv = 0;
+    for (int r = 0; r < nraw; ++r) {
+      const int keep = offs[r];
+      offs[r] = keep ? nv : -1;
+      nv += keep;
+    }
+    for (int r = nraw; r < a.max_det; ++r) offs[r] = -1;
+    nvalid_s = nv;
+    a.raw_count[b] = nraw;
+    a.det_count[b] = nv;
+  }
+  __syncthreads();
+  const int nv = nvalid_s;
+  for (int r = threadIdx.x; r < a.max_det; r += blockDim.x) {
+    if (r < nraw && offs[r] >= 0) {
+      const int o = offs[r];
+      const Cand c = cd[rank_pos[r]];
+      float* row = a.det_box + ((long long)b * a.max_det + o) * 6;
+      row[0] = c.y1; row[1] = c.x1; row[2] = c.y2; row[3] = c.x2;
+      row[4] = (float)c.cls; row[5] = c.score;
+      float pb[4];
+      int gx[kMaxK + 1], gy[kMaxK + 1];
+      box_edges(c, a.S, a.k, pb, gx, gy);
+      int* ed = a.edges + ((long long)b * a.max_det + o) * (2 * (kMaxK + 1));
+      for (int j = 0; j <= a.k; ++j) {
+        ed[j] = gx[j];
+        ed[kMaxK + 1 + j] = gy[j];
+      }
+    }
+    if (r >= nv) {
+      float* row = a.det_box + ((long long)b * a.max_det + r) * 6;
+      for (int i = 0; i < 6; ++i) row[i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// position-sensitive mask assembly (:862-933): out[d,y,x] = sigmoid(score[y,x, by*k+bx]) inside
+// bin (by,bx) of box d, sigmoid(0)=0.5 outside the box.  One thread = 4 consecutive x (float4
+// store); planar score maps make the gather a coalesced row read.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_kernel(MaskArgs a) {
+  const int d = blockIdx.y, b = blockIdx.z;
+  if (d >= a.det_count[b]) return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int quads_per_row = a.S >> 2;
+  if (q >= a.S * quads_per_row) return;
+  const int y = q / quads_per_row;
+  const int x0 = (q % quads_per_row) << 2;
+  const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
+  int gx[kMaxK + 1], gy[kMaxK + 1];
+#pragma unroll
+  for (int j = 0; j <= kMaxK; ++j) {
+    gx[j] = (j <= a.k) ? __ldg(ed + j) : 0;
+    gy[j] = (j <= a.k) ? __ldg(ed + kMaxK + 1 + j) : 0;
+  }
+  int by = -1;
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j)
+    if (j < a.k && y >= gy[j] && y < gy[j + 1]) by = j;
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x0 + i;
+    int bx = -1;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j)
+      if (j < a.k && x >= gx[j] && x < gx[j + 1]) bx = j;
+    float val = 0.5f;
+    if (by >= 0 && bx >= 0) {
+      const float s = __ldg(a.score + b * a.s_img + (long long)(by * a.k + bx) * a.s_ch + y * a.s_row + x * a.s_pix);
+      val = sigmoidf_(s);
+    }
+    v[i] = val;
+  }
+  float4* o = reinterpret_cast<float4*>(a.out + (((long long)b * a.max_det + d) * a.S + y) * a.S + x0);
+  *o = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+}  // namespace
+
+int launch_decode(const DecodeArgs& a, cudaStream_t st) {
+  DY_CHECK(a.num_class >= 1 && a.num_class <= kMaxClasses, "num_class");
+  const int n0 = 3 * (a.g[0] * a.g[0] + a.g[1] * a.g[1] + a.g[2] * a.g[2]);
+  dim3 grid((n0 + 255) / 256, a.B);
+  decode_kernel<<<grid, 256, 0, st>>>(a);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_nms(const NmsArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)((a.cap + 31) / 32) * 4;
+  DY_CHECK(smem <= 48 * 1024, "candidate capacity too large for the alive bitmask");
+  dim3 grid(a.num_class, a.B);
+  nms_kernel<<<grid, 256, smem, st>>>(a);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
+  DY_CHECK(a.k >= 1 && a.k <= kMaxK, "k_map");
+  const int Emax = a.num_class * a.max_det;
+  const size_t smem = (size_t)Emax * 12 + (size_t)a.max_det * 8 + 16;
+  DY_CHECK(smem <= 96 * 1024, "max_detection too large");
+  static bool attr = false;
+  if (!attr) {
+    DY_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  finalize_kernel<<<a.B, 256, smem, st>>>(a);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_masks(const MaskArgs& a, cudaStream_t st) {
+  DY_CHECK(a.S % 4 == 0, "score map size must be a multiple of 4");
+  DY_CHECK(a.max_det <= 65535 && a.B <= 65535, "grid limits");
+  dim3 grid((a.S * (a.S / 4) + 255) / 256, a.max_det, a.B);
+  mask_kernel<<<grid, 256, 0, st>>>(a);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+}  // namespace dy

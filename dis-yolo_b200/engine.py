@@ -1,0 +1,292 @@
+"""Thin object wrapper over the C ABI (include/disyolo.h).  PyTorch tensors are used only as
+device / pinned-host buffers; every compute call goes through libdisyolo_b200.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_TABLE = None
+
+
+def layer_table():
+    """[{id, cin, cout, k, s, bn, res, size_div}] for convolutional1..82 -- the shapes of the
+    reference's builder calls (yolo3_net_pos.py:159-412); ``cin`` includes concatenated channels."""
+    global _TABLE
+    if _TABLE is not None:
+        return _TABLE
+    t = []
+
+    def add(n, cin, cout, k, s=1, bn=True, res=False, div=1):
+        t.append(dict(id=n, cin=cin, cout=cout, k=k, s=s, bn=bn, res=res, size_div=div))
+
+    add(1, 3, 32, 3, div=1)
+    add(2, 32, 64, 3, 2, div=2)
+    add(3, 64, 32, 1, div=2); add(4, 32, 64, 3, res=True, div=2)
+    add(5, 64, 128, 3, 2, div=4)
+    for n in (6, 8):
+        add(n, 128, 64, 1, div=4); add(n + 1, 64, 128, 3, res=True, div=4)
+    add(10, 128, 256, 3, 2, div=8)
+    for i in range(8):
+        add(11 + 2 * i, 256, 128, 1, div=8); add(12 + 2 * i, 128, 256, 3, res=True, div=8)
+    add(27, 256, 512, 3, 2, div=16)
+    for i in range(8):
+        add(28 + 2 * i, 512, 256, 1, div=16); add(29 + 2 * i, 256, 512, 3, res=True, div=16)
+    add(44, 512, 1024, 3, 2, div=32)
+    for i in range(4):
+        add(45 + 2 * i, 1024, 512, 1, div=32); add(46 + 2 * i, 512, 1024, 3, res=True, div=32)
+    for n, (ci, co, k) in zip(range(53, 59), [(1024, 512, 1), (512, 1024, 3)] * 3):
+        add(n, ci, co, k, div=32)
+    add(59, 1024, 24, 1, bn=False, div=32)
+    add(60, 512, 256, 1, div=32)
+    add(61, 768, 256, 1, div=16)
+    for n, (ci, co, k) in zip(range(62, 67), [(256, 512, 3), (512, 256, 1)] * 3):
+        add(n, ci, co, k, div=16)
+    add(67, 512, 24, 1, bn=False, div=16)
+    add(68, 256, 128, 1, div=16)
+    add(69, 384, 128, 1, div=8)
+    for n, (ci, co, k) in zip(range(70, 75), [(128, 256, 3), (256, 128, 1)] * 3):
+        add(n, ci, co, k, div=8)
+    add(75, 256, 24, 1, bn=False, div=8)
+    add(76, 128, 64, 1, div=8)
+    add(77, 192, 64, 1, div=4); add(78, 64, 128, 3, div=4); add(79, 128, 32, 1, div=4)
+    add(80, 96, 32, 1, div=2); add(81, 32, 64, 3, div=2); add(82, 64, 9, 1, bn=False, div=2)
+    _TABLE = t
+    return t
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine(object):
+    """One network on one GPU."""
+
+    def __init__(self, image_size=576, max_batch=1, precision='bf16', device=0, anchors=None,
+                 num_classes=3, k_map=3, alpha=0.1, bn_eps=1e-5, iou_threshold=0.3,
+                 max_detection=30, lock=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.lib()
+        _lib.require_gpu()
+        cfg = _lib.DyConfig()
+        cfg.num_classes = num_classes
+        a = np.asarray(anchors if anchors is not None else
+                       [[31, 23], [62, 58], [143, 91], [213, 186], [61, 337], [194, 432],
+                        [474, 248], [551, 93], [478, 454]], np.float32).reshape(-1)
+        if a.size != 18:
+            raise ValueError('anchors must be 9 x (w,h)')
+        for i in range(18):
+            cfg.anchors[i] = float(a[i])
+        cfg.image_size = int(image_size)
+        cfg.k_map = int(k_map)
+        cfg.alpha = float(alpha)
+        cfg.bn_eps = float(bn_eps)
+        cfg.iou_threshold = float(iou_threshold)
+        cfg.max_detection = int(max_detection)
+        cfg.max_batch = int(max_batch)
+        cfg.precision = {'bf16': _lib.PRECISION_BF16, 'fp32': _lib.PRECISION_FP32}[precision]
+        cfg.device = int(device)
+        lk = lock if lock is not None else [1] * 52 + [0] * 30
+        for i in range(82):
+            cfg.lock[i] = int(bool(lk[i]))
+        self.cfg = cfg
+        self.image_size, self.max_batch, self.max_detection = int(image_size), int(max_batch), int(max_detection)
+        self.precision, self.k_map, self.num_classes = precision, int(k_map), int(num_classes)
+        self.device = torch.device('cuda', int(device))
+        h = C.c_void_p()
+        _lib.check(self.lib.dy_create(C.byref(cfg), C.byref(h)), 'dy_create')
+        self.h = h
+        self._pinned = {}
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.dy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights --------------------------------------------------------------------------
+    def load_weights(self, weights):
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            _lib.check(self.lib.dy_load_weights(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim),
+                       'dy_load_weights(%s)' % name)
+        _lib.check(self.lib.dy_finalize_weights(self.h), 'dy_finalize_weights')
+
+    # ---- helpers ----------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype=None):
+        t = self.torch
+        if not isinstance(x, t.Tensor):
+            x = t.from_numpy(np.ascontiguousarray(x))
+        if dtype is not None and x.dtype != dtype:
+            x = x.to(dtype)
+        return x.to(self.device).contiguous()
+
+    @property
+    def mask_size(self):
+        return self.image_size // 2
+
+    @property
+    def num_candidates(self):
+        s = self.image_size
+        return 3 * ((s // 8) ** 2 + (s // 16) ** 2 + (s // 32) ** 2)
+
+    # ---- device-resident forward ------------------------------------------------------------
+    def forward(self, images, windows, det_thresh, want_masks=True, out=None):
+        """images [B,S,S,3] fp32 cuda, windows [B,4] fp32 cuda -> dict of cuda tensors."""
+        t = self.torch
+        images = self._dev(images, t.float32)
+        windows = self._dev(windows, t.float32)
+        B = images.shape[0]
+        md, sm = self.max_detection, self.mask_size
+        if out is None:
+            out = dict(det_raw=t.empty((B, md, 6), dtype=t.float32, device=self.device),
+                       det_box=t.empty((B, md, 6), dtype=t.float32, device=self.device),
+                       det_count=t.empty((B,), dtype=t.int32, device=self.device),
+                       masks=t.empty((B, md, sm, sm), dtype=t.float32, device=self.device) if want_masks else None)
+        _lib.check(self.lib.dy_forward(self.h, _ptr(images), B, _ptr(windows), float(det_thresh),
+                                       _ptr(out['det_raw']), _ptr(out['det_box']), _ptr(out['det_count']),
+                                       _ptr(out.get('masks')), self._stream()), 'dy_forward')
+        return out
+
+    def forward_network(self, images):
+        images = self._dev(images, self.torch.float32)
+        _lib.check(self.lib.dy_forward_network(self.h, _ptr(images), images.shape[0], self._stream()),
+                   'dy_forward_network')
+
+    # ---- host-buffer forward (the reference-facing call) ------------------------------------
+    def pinned(self, key, shape, dtype):
+        t = self.torch
+        buf = self._pinned.get(key)
+        n = int(np.prod(shape))
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = t.empty((n,), dtype=dtype).pin_memory()
+            self._pinned[key] = buf
+        return buf[:n].view(*shape)
+
+    def forward_host(self, images, windows, det_thresh, want_masks=True):
+        """images / windows: numpy or pinned torch CPU tensors.  Returns pinned CPU tensors
+        (det_raw, det_box, det_count, masks); masks rows beyond det_count[b] are unspecified."""
+        t = self.torch
+        B = int(images.shape[0])
+        S, md, sm = self.image_size, self.max_detection, self.mask_size
+
+        def stage(key, x, shape):
+            if isinstance(x, t.Tensor) and x.is_pinned() and x.dtype == t.float32 and x.is_contiguous():
+                return x
+            buf = self.pinned(key, shape, t.float32)
+            buf.copy_(x if isinstance(x, t.Tensor) else t.from_numpy(np.ascontiguousarray(x, np.float32)))
+            return buf
+        img = stage('img', images, (B, S, S, 3))
+        win = stage('win', windows, (B, 4))
+        raw = self.pinned('raw', (B, md, 6), t.float32)
+        box = self.pinned('box', (B, md, 6), t.float32)
+        cnt = self.pinned('cnt', (B,), t.int32)
+        msk = self.pinned('msk', (B, md, sm, sm), t.float32) if want_masks else None
+        _lib.check(self.lib.dy_forward_host(self.h, _ptr(img), B, _ptr(win), float(det_thresh), _ptr(raw), _ptr(box),
+                                            _ptr(cnt), _ptr(msk)), 'dy_forward_host')
+        return raw, box, cnt, msk
+
+    # ---- parity taps ------------------------------------------------------------------------
+    def layer_shape(self, layer):
+        h, w, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self.lib.dy_layer_shape(self.h, layer, C.byref(h), C.byref(w), C.byref(c)), 'dy_layer_shape')
+        return h.value, w.value, c.value
+
+    def activation(self, layer, B):
+        h, w, c = self.layer_shape(layer)
+        out = self.torch.empty((B, h, w, c), dtype=self.torch.float32, device=self.device)
+        _lib.check(self.lib.dy_get_activation(self.h, layer, B, _ptr(out), self._stream()), 'dy_get_activation')
+        return out
+
+    def yolo(self, scale, B):
+        g = self.image_size // (8, 16, 32)[scale]
+        out = self.torch.empty((B, g, g, 3, 5 + self.num_classes), dtype=self.torch.float32, device=self.device)
+        _lib.check(self.lib.dy_get_yolo(self.h, scale, B, _ptr(out), self._stream()), 'dy_get_yolo')
+        return out
+
+    def mask_pos(self, B):
+        sm = self.mask_size
+        out = self.torch.empty((B, sm, sm, self.k_map ** 2), dtype=self.torch.float32, device=self.device)
+        _lib.check(self.lib.dy_get_mask_pos(self.h, B, _ptr(out), self._stream()), 'dy_get_mask_pos')
+        return out
+
+    # ---- stand-alone stages -----------------------------------------------------------------
+    def decode(self, yolos, windows):
+        t = self.torch
+        y = [self._dev(v, t.float32) for v in yolos]
+        windows = self._dev(windows, t.float32)
+        B, n0 = y[0].shape[0], self.num_candidates
+        box = t.empty((B, n0, 4), dtype=t.float32, device=self.device)
+        cls = t.empty((B, n0), dtype=t.int32, device=self.device)
+        score = t.empty((B, n0), dtype=t.float32, device=self.device)
+        _lib.check(self.lib.dy_decode(self.h, _ptr(y[0]), _ptr(y[1]), _ptr(y[2]), B, _ptr(windows), _ptr(box),
+                                      _ptr(cls), _ptr(score), self._stream()), 'dy_decode')
+        return box, cls, score
+
+    def detect(self, yolos, windows, det_thresh):
+        t = self.torch
+        y = [self._dev(v, t.float32) for v in yolos]
+        windows = self._dev(windows, t.float32)
+        B, md = y[0].shape[0], self.max_detection
+        raw = t.empty((B, md, 6), dtype=t.float32, device=self.device)
+        box = t.empty((B, md, 6), dtype=t.float32, device=self.device)
+        cnt = t.empty((B,), dtype=t.int32, device=self.device)
+        _lib.check(self.lib.dy_detect(self.h, _ptr(y[0]), _ptr(y[1]), _ptr(y[2]), B, _ptr(windows), float(det_thresh),
+                                      _ptr(raw), _ptr(box), _ptr(cnt), self._stream()), 'dy_detect')
+        return raw, box, cnt
+
+    def nms(self, box, cls, score, det_thresh):
+        t = self.torch
+        box, cls, score = self._dev(box, t.float32), self._dev(cls, t.int32), self._dev(score, t.float32)
+        B, N, md = box.shape[0], box.shape[1], self.max_detection
+        idx = t.empty((B, md), dtype=t.int32, device=self.device)
+        cnt = t.empty((B,), dtype=t.int32, device=self.device)
+        raw = t.empty((B, md, 6), dtype=t.float32, device=self.device)
+        _lib.check(self.lib.dy_nms(self.h, _ptr(box), _ptr(cls), _ptr(score), B, N, float(det_thresh), _ptr(idx),
+                                   _ptr(cnt), _ptr(raw), self._stream()), 'dy_nms')
+        return idx, cnt, raw
+
+    def assemble_masks(self, score_maps, det_box, det_count, layout='nhwc'):
+        t = self.torch
+        score_maps = self._dev(score_maps, t.float32)
+        det_box, det_count = self._dev(det_box, t.float32), self._dev(det_count, t.int32)
+        B, md, sm = det_box.shape[0], self.max_detection, self.mask_size
+        out = t.empty((B, md, sm, sm), dtype=t.float32, device=self.device)
+        _lib.check(self.lib.dy_assemble_masks(self.h, _ptr(score_maps), 0 if layout == 'nhwc' else 1, B,
+                                              _ptr(det_box), _ptr(det_count), _ptr(out), self._stream()),
+                   'dy_assemble_masks')
+        return out
+
+
+def conv_layer(x, w, stride, scale, shift, act, alpha=0.1, residual=None, precision='bf16'):
+    """One conv / conv_bn / res_conv_bn of the reference through the library (dy_conv_layer).
+    x [B,H,W,cin] cuda fp32, w HWIO numpy, scale/shift numpy [cout]."""
+    import torch
+    lib = _lib.lib()
+    _lib.require_gpu()
+    x = x.contiguous().float()
+    B, H, W, cin = x.shape
+    w = np.ascontiguousarray(w, np.float32)
+    k, cout = w.shape[0], w.shape[3]
+    scale = np.ascontiguousarray(scale, np.float32)
+    shift = np.ascontiguousarray(shift, np.float32)
+    out = torch.empty((B, H // stride, W // stride, cout), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        residual = residual.contiguous().float()
+    with torch.cuda.device(x.device):
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.dy_conv_layer({'bf16': 0, 'fp32': 1}[precision], _ptr(x), B, H, W, cin,
+                                     w.ctypes.data_as(C.c_void_p), k, stride, cout,
+                                     scale.ctypes.data_as(C.c_void_p), shift.ctypes.data_as(C.c_void_p),
+                                     int(bool(act)), float(alpha), _ptr(residual), _ptr(out), st), 'dy_conv_layer')
+    return out

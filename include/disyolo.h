@@ -1,0 +1,153 @@
+/* disyolo.h -- C ABI of libdisyolo_b200.so: the DIS-YOLO hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (ZHANGKEON/DIS-YOLO) has no FFI: its hot path is a Python class that builds a
+ * TensorFlow-1.x graph (yolo/yolo3_net_pos.py) driven through tf.Session.run.  This header is the
+ * boundary a maintainer binds with ctypes instead; each entry point cites the
+ * reference interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative dy_status otherwise; dy_last_error() returns
+ *     a thread-local human readable message.  Nothing aborts, nothing throws across this ABI.
+ *   - "dev" pointers are CUDA device pointers on the net's device, "host" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all work is enqueued on
+ *     it asynchronously; the caller owns inputs/outputs, the library owns weights and workspaces.
+ *   - one dy_net per GPU; calls on one net must be serialised by the caller.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DISYOLO_H_
+#define DISYOLO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dy_net dy_net;
+
+enum dy_status {
+  DY_STATUS_OK = 0,
+  DY_STATUS_INVALID = -1,
+  DY_STATUS_CUDA = -2,
+  DY_STATUS_STATE = -3,
+  DY_STATUS_NOTFOUND = -4,
+  DY_STATUS_UNSUPPORTED = -5
+};
+
+enum dy_precision {
+  DY_PRECISION_BF16 = 0, /* tcgen05 bf16 x bf16 -> fp32 accumulate, bf16 activations        */
+  DY_PRECISION_FP32 = 1  /* verification mode: fp32 CUDA-core convolutions, fp32 activations */
+};
+
+/* Constructor arguments = the constants YOLONet.__init__ reads from yolo/config.py
+ * (yolo3_net_pos.py:13-37; config.py:21-22,38,41-46,60-72) plus the per-layer lock flags that are
+ * literals inside build_network (yolo3_net_pos.py:155-156). */
+typedef struct dy_config {
+  int32_t num_classes;     /* len(cfg.CLASSES) = 3                                  */
+  float anchors[18];       /* cfg.ANCHORS, 9 x (w,h) in pixels, smallest first      */
+  int32_t image_size;      /* cfg.IMAGE_SIZE / TEST_SIZE, multiple of 32            */
+  int32_t k_map;           /* cfg.K_MAP (3, 5 or 7)                                 */
+  float alpha;             /* cfg.ALPHA leaky slope                                 */
+  float bn_eps;            /* 1e-5  (yolo3_net_pos.py:75)                           */
+  float iou_threshold;     /* cfg.IOU_THRESHOLD                                     */
+  int32_t max_detection;   /* cfg.MAX_DETECTION                                     */
+  int32_t max_batch;       /* cfg.BATCH_SIZE upper bound; buffers are sized for it  */
+  int32_t precision;       /* enum dy_precision                                     */
+  int32_t device;          /* CUDA device ordinal                                   */
+  uint8_t lock[82];        /* lock flag of convolutional1..82 (1 = frozen)          */
+  uint8_t reserved[2];
+} dy_config;
+
+/* Library / build information: "disyolo_b200 <version> sm_100a". */
+const char* dy_version(void);
+/* Message of the last failing call on this thread. */
+const char* dy_last_error(void);
+/* Number of CUDA devices visible (0 when there is no driver / GPU). */
+int dy_device_count(void);
+
+/* Replaces: YOLONet(training) graph construction (yolo3_net_pos.py:13-65, 153-463).
+ * Allocates every activation buffer / workspace for max_batch images. */
+int dy_create(const dy_config* cfg, dy_net** out);
+int dy_destroy(dy_net* net);
+
+/* Replaces: tf.train.Saver.restore / slim.assign_from_checkpoint_fn by variable name
+ * (train_yolo3_mask.py:85-107, calculate_test_map.py:184-185).  `tf_name` is the reference's
+ * variable name, e.g. "yolo/convolutional7/weights" (HWIO fp32), ".../BatchNorm/gamma|beta|
+ * moving_mean|moving_variance", ".../biases".  `host` holds prod(shape) floats. */
+int dy_load_weights(dy_net* net, const char* tf_name, const float* host, const int64_t* shape, int32_t ndim);
+/* Folds BN, packs bf16 operands, builds TMA descriptors.  Must follow the last dy_load_weights and
+ * precede dy_forward. */
+int dy_finalize_weights(dy_net* net);
+
+/* Replaces: sess.run(net.evaluation, {images, clip_window, det_thresh, is_training: False})
+ * (calculate_test_map.py:214-218, train_yolo3_mask.py:171-174; graph: yolo3_net_pos.py:153-463,
+ * 465-628, 862-938).
+ *   images_dev   [B,S,S,3] fp32 NHWC RGB/255          windows_dev [B,4] fp32 (y1,x1,y2,x2)
+ *   det_raw_dev  [B,max_det,6] fp32  filter_detections output, zero padded (may be NULL)
+ *   det_box_dev  [B,max_det,6] fp32  rows kept by val_test's w>0,h>0 filter, zero padded
+ *   det_count_dev[B] int32           number of valid rows of det_box
+ *   masks_dev    [B,max_det,S/2,S/2] fp32; only the first det_count[b] maps of image b are written
+ */
+int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* windows_dev, float det_thresh,
+               float* det_raw_dev, float* det_box_dev, int32_t* det_count_dev, float* masks_dev, void* stream);
+
+/* The same call with HOST buffers: pinned staging, H2D of images/windows, the forward, D2H of the
+ * boxes, the counts and exactly det_count[b] masks per image; synchronises before returning.
+ * This is the call the Python facade's Session.run makes. */
+int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const float* windows_host, float det_thresh,
+                    float* det_raw_host, float* det_box_host, int32_t* det_count_host, float* masks_host);
+
+/* Network only (conv1..82), no decode / NMS / masks: fills the head and score-map buffers. */
+int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream);
+
+/* Parity taps (replace sess.run on intermediate tensors of build_network).
+ * dy_get_activation: output of convolutional<layer> (after BN/leaky/residual) as fp32 NHWC
+ *   [B,h,w,c]; dims are reported by dy_layer_shape.
+ * dy_get_yolo: scale 0/1/2 = stride 8/16/32 map [B,g,g,3*(5+C)] fp32 (yolo3_net_pos.py:353).
+ * dy_get_mask_pos: [B,S/2,S/2,k*k] fp32 NHWC (yolo3_net_pos.py:410-412). */
+int dy_layer_shape(dy_net* net, int32_t layer, int32_t* h, int32_t* w, int32_t* c);
+int dy_get_activation(dy_net* net, int32_t layer, int32_t B, float* out_dev, void* stream);
+int dy_get_yolo(dy_net* net, int32_t scale, int32_t B, float* out_dev, void* stream);
+int dy_get_mask_pos(dy_net* net, int32_t B, float* out_dev, void* stream);
+
+/* Stand-alone stages, fed identical inputs in the parity tests.
+ * dy_decode   replaces interpret_output + the candidate part of filter_detections
+ *             (yolo3_net_pos.py:465-514, 523-561).  yolo8/16/32_dev: [B,g,g,3*(5+C)] fp32.
+ *             Outputs (dense, candidate order of :527-542): box [B,N0,4] (y1,x1,y2,x2 clipped),
+ *             cls [B,N0] int32, score [B,N0] fp32.
+ * dy_detect   replaces filter_detections + val_test's box filter (:517-628, 876-880) from head
+ *             maps: decode -> threshold -> per-class NMS -> top-k.
+ * dy_nms      the same selection from caller-supplied boxes/classes/scores [B,N,...] (identical
+ *             decoded boxes in -> keep set must be bit-exact); sel_idx [B,max_det] int32 receives
+ *             the selected candidate indices in output order (-1 padded), sel_count [B].
+ * dy_assemble_masks replaces val_test's mask assembly (:881-933).  score maps either NHWC
+ *             [B,S,S,k*k] (layout=0, the reference's) or planar [B,k*k,S,S] (layout=1);
+ *             det_box [B,max_det,6] / det_count [B] as produced by dy_forward. */
+int dy_decode(dy_net* net, const float* yolo8_dev, const float* yolo16_dev, const float* yolo32_dev, int32_t B,
+              const float* windows_dev, float* box_dev, int32_t* cls_dev, float* score_dev, void* stream);
+int dy_detect(dy_net* net, const float* yolo8_dev, const float* yolo16_dev, const float* yolo32_dev, int32_t B,
+              const float* windows_dev, float det_thresh, float* det_raw_dev, float* det_box_dev,
+              int32_t* det_count_dev, void* stream);
+int dy_nms(dy_net* net, const float* box_dev, const int32_t* cls_dev, const float* score_dev, int32_t B, int32_t N,
+           float det_thresh, int32_t* sel_idx_dev, int32_t* sel_count_dev, float* det_raw_dev, void* stream);
+int dy_assemble_masks(dy_net* net, const float* score_dev, int32_t layout, int32_t B, const float* det_box_dev,
+                      const int32_t* det_count_dev, float* masks_dev, void* stream);
+
+/* One convolution of the reference's builders through the same engine the network uses
+ * (conv / conv_bn / res_conv_bn, yolo3_net_pos.py:109-151): x [B,H,W,cin] fp32 NHWC (device),
+ * w HWIO [k,k,cin,cout] fp32 (host), per-channel scale/shift (host; folded BN or 1/bias),
+ * act = leaky flag, residual [B,Ho,Wo,cout] fp32 NHWC (device) or NULL, out [B,Ho,Wo,cout] fp32.
+ * stride in {1,2} with TensorFlow 'SAME' padding.  precision selects the tcgen05 bf16 engine or
+ * the fp32 verification kernel.  Used by the per-layer parity tests. */
+int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
+                  const float* w_host, int32_t k, int32_t stride, int32_t cout, const float* scale_host,
+                  const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,
+                  void* stream);
+
+/* Kernel launches issued by this library since the last call (bench.py's gpu_launches). */
+int64_t dy_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISYOLO_H_ */

@@ -1,0 +1,111 @@
+"""GPU: every conv flavour of the reference's builders (conv / conv_bn / res_conv_bn,
+yolo3_net_pos.py:109-151) through dy_conv_layer, against the oracle on the same seeded inputs.
+
+bf16 engine (tcgen05): inputs and weights are rounded to bf16 on both sides, so the remaining
+difference is fp32 accumulation order + the bf16 rounding of the stored output: tolerance 1e-2
+relative (north_star: per-layer activations within 1e-2 in bf16).
+fp32 verification kernel: tolerance 1e-4 relative (north_star), measured ~1e-6."""
+import numpy as np
+import pytest
+
+from oracle import dis_oracle as O
+from tests.util import bf16_round, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, cin, cout, k, s, act, residual)
+CASES = [
+    (2, 18, 18, 1024, 512, 1, 1, True, False),     # bottleneck 1x1 (conv45..)
+    (2, 36, 36, 64, 32, 1, 1, True, False),        # cout=32 tile (conv3)
+    (3, 20, 12, 96, 32, 1, 1, True, False),        # 96 = 64+32 channels -> 32-wide K chunks (conv80)
+    (2, 18, 18, 512, 1024, 3, 1, True, True),      # res_conv_bn (conv46..)
+    (2, 24, 24, 32, 64, 3, 1, True, True),         # Cin=32 3x3 (conv4, conv81)
+    (1, 16, 20, 64, 128, 3, 1, True, False),       # non-square
+    (2, 32, 32, 32, 64, 3, 2, True, False),        # stride 2, Cin=32 (conv2)
+    (2, 36, 36, 64, 128, 3, 2, True, False),       # stride 2 (conv5)
+    (1, 36, 36, 256, 512, 3, 2, True, False),      # stride 2 (conv27)
+    (2, 18, 18, 1024, 32, 1, 1, False, False),     # linear biased head shape (conv59, padded cout)
+    (5, 9, 9, 128, 256, 3, 1, True, False),        # many tiny images: tiles straddle image borders
+]
+
+
+def _make(case, seed):
+    B, H, W, cin, cout, k, s, act, res = case
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, H, W, cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = (rng.standard_normal(cout) * 0.3).astype(np.float32)
+    r = rng.standard_normal((B, H // s, W // s, cout)).astype(np.float32) if res else None
+    return x, w, scale, shift, r
+
+
+def _oracle(x, w, s, scale, shift, act, r):
+    y = O.conv2d_same(x, w, s) * scale + shift
+    if act:
+        y = O.leaky_relu(y)
+    if r is not None:
+        y = y + r
+    return y
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: 'B%d_%dx%d_%d-%d_k%ds%d%s%s' % (
+    c[0], c[1], c[2], c[3], c[4], c[5], c[6], '_act' if c[7] else '', '_res' if c[8] else ''))
+def test_conv_bf16_tcgen05(case):
+    import torch
+    from disyolo_b200.engine import conv_layer
+    x, w, scale, shift, r = _make(case, 11)
+    xb, wb = bf16_round(x), bf16_round(w)
+    rb = bf16_round(r) if r is not None else None
+    want = _oracle(xb, wb, case[6], scale, shift, case[7], rb)
+    got = conv_layer(torch.from_numpy(x).cuda(), w, case[6], scale, shift, case[7], 0.1,
+                     torch.from_numpy(r).cuda() if r is not None else None, 'bf16').cpu().numpy()
+    assert got.shape == want.shape
+    e = rel_err(got, want)
+    worst = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 0.25)))
+    print('bf16 conv %s: rel %.3g worst %.3g' % (str(case), e, worst))
+    assert e < 5e-3 and worst < 1e-2
+
+
+@pytest.mark.parametrize('case', CASES[:9], ids=lambda c: 'B%d_%dx%d_%d-%d_k%ds%d' % c[:7])
+def test_conv_fp32_verify(case):
+    import torch
+    from disyolo_b200.engine import conv_layer
+    x, w, scale, shift, r = _make(case, 12)
+    want = _oracle(x, w, case[6], scale, shift, case[7], r)
+    got = conv_layer(torch.from_numpy(x).cuda(), w, case[6], scale, shift, case[7], 0.1,
+                     torch.from_numpy(r).cuda() if r is not None else None, 'fp32').cpu().numpy()
+    e = rel_err(got, want)
+    print('fp32 conv %s: rel %.3g' % (str(case), e))
+    assert e < 1e-5
+    assert float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0))) < 1e-4
+
+
+def test_conv1_stem():
+    import torch
+    from disyolo_b200.engine import conv_layer
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 64, 48, 3), dtype=np.float32)
+    w = (rng.standard_normal((3, 3, 3, 32)) * 0.3).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, 32).astype(np.float32)
+    shift = (rng.standard_normal(32) * 0.3).astype(np.float32)
+    want = _oracle(x, w, 1, scale, shift, True, None)
+    got = conv_layer(torch.from_numpy(x).cuda(), w, 1, scale, shift, True, 0.1, None, 'bf16').cpu().numpy()
+    assert rel_err(got, want) < 4e-3          # fp32 math, bf16 store
+    got32 = conv_layer(torch.from_numpy(x).cuda(), w, 1, scale, shift, True, 0.1, None, 'fp32').cpu().numpy()
+    assert rel_err(got32, want) < 1e-5
+
+
+def test_conv_linearity_property():
+    """conv(a*x) == a*conv(x) for the linear (no activation, zero shift) conv: a size-independent
+    property checked at a full-size layer shape (conv54 at batch 4: 18x18x512 -> 1024)."""
+    import torch
+    from disyolo_b200.engine import conv_layer
+    rng = np.random.default_rng(6)
+    x = bf16_round(rng.standard_normal((4, 18, 18, 512)).astype(np.float32))
+    w = (rng.standard_normal((3, 3, 512, 1024)) / 68.0).astype(np.float32)
+    one, zero = np.ones(1024, np.float32), np.zeros(1024, np.float32)
+    xc = torch.from_numpy(x).cuda()
+    y1 = conv_layer(xc, w, 1, one, zero, False, 0.1, None, 'bf16').cpu().numpy()
+    y2 = conv_layer(xc * 2.0, w, 1, one, zero, False, 0.1, None, 'bf16').cpu().numpy()
+    assert np.array_equal(y2, 2.0 * y1)       # power-of-two scaling is exact in bf16/fp32
