@@ -28,6 +28,7 @@ void set_error(const std::string& msg);
   do {                                                                                          \
     cudaError_t _e = (call);                                                                    \
     if (_e != cudaSuccess) {                                                                    \
+      (void)cudaGetLastError(); /* do not leave a stale error for the next call */              \
       ::dy::set_error(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " at " +      \
                       __FILE__ + ":" + std::to_string(__LINE__));                               \
       return ::dy::DY_ERR_CUDA;                                                                 \

@@ -311,6 +311,9 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
   return DY_OK;
 }
 
+// dynamic smem ceiling: 227 KB per CTA minus the kernel's static shared memory, rounded down
+static constexpr int kConvTcMaxSmem = 224 * 1024;
+
 size_t conv_tc_smem_bytes(int kchunk, int block_n, int stages) {
   return (size_t)stages * (size_t)(kBlockM + block_n) * kchunk * 2 + 1024;
 }
@@ -331,19 +334,20 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
   DY_CHECK(p.tmem_cols >= 2 * p.block_n && p.tmem_cols <= 512, "tmem_cols");
   const size_t smem = conv_tc_smem_bytes(kchunk, p.block_n, p.num_stages);
+  DY_CHECK(smem <= (size_t)kConvTcMaxSmem, "pipeline does not fit in shared memory");
   const int tiles = p.n_tiles_m * p.n_tiles_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
   if (kchunk == 64) {
     static bool attr64 = false;
     if (!attr64) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr64 = true;
     }
     conv_tc_kernel<64><<<grid, 256, smem, stream>>>(a0, a1, b, p);
   } else {
     static bool attr32 = false;
     if (!attr32) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32 = true;
     }
     conv_tc_kernel<32><<<grid, 256, smem, stream>>>(a0, a1, b, p);
