@@ -48,6 +48,7 @@ SIGNATURES = {
     'dy_forward': (C.c_int, [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P]),
     'dy_forward_host': (C.c_int, [_P, _P, _I, _P, _F, _P, _P, _P, _P]),
     'dy_forward_network': (C.c_int, [_P, _P, _I, _P]),
+    'dy_forward_profile': (C.c_int, [_P, _P, _I, _P, _P]),
     'dy_layer_shape': (C.c_int, [_P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     'dy_get_activation': (C.c_int, [_P, _I, _I, _P, _P]),
     'dy_get_yolo': (C.c_int, [_P, _I, _I, _P, _P]),

@@ -723,6 +723,37 @@ int dy_finalize_weights(dy_net* net) {
   return DY_OK;
 }
 
+int dy_forward_profile(dy_net* net, const float* images_dev, int32_t B, float* layer_ms_host, void* stream) {
+  DY_CHECK(net && images_dev && layer_ms_host, "null argument");
+  DY_CHECK(net->finalized, "dy_finalize_weights has not been called");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
+  DY_CHECK(net->cfg.precision == DY_PRECISION_BF16, "per-layer profile is for the bf16 engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(83);
+  for (auto& e : ev) DY_CUDA(cudaEventCreate(&e));
+  auto& L = net->L;
+  int rc = DY_OK;
+  cudaEventRecord(ev[0], st);
+  note_launch();
+  rc = launch_conv1(images_dev, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S,
+                    L[1].s2d, L[1].same, st);
+  cudaEventRecord(ev[1], st);
+  for (int n = 2; n <= 82 && rc == DY_OK; ++n) {
+    rc = run_tc_plan(L[n].plan, B, net->num_sms, st);
+    cudaEventRecord(ev[n], st);
+  }
+  if (rc == DY_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("stream synchronize failed in dy_forward_profile");
+    rc = DY_ERR_CUDA;
+  }
+  if (rc == DY_OK) {
+    layer_ms_host[0] = 0.f;
+    for (int n = 1; n <= 82; ++n) cudaEventElapsedTime(&layer_ms_host[n], ev[n - 1], ev[n]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
 int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream) {
   DY_CHECK(net && images_dev, "null argument");
   return run_network(net, images_dev, B, (cudaStream_t)stream);

@@ -163,6 +163,14 @@ class Engine(object):
         _lib.check(self.lib.dy_forward_network(self.h, _ptr(images), images.shape[0], self._stream()),
                    'dy_forward_network')
 
+    def profile_layers(self, images):
+        """Per-layer device milliseconds of one network pass (index 1..82)."""
+        images = self._dev(images, self.torch.float32)
+        ms = np.zeros(83, np.float32)
+        _lib.check(self.lib.dy_forward_profile(self.h, _ptr(images), images.shape[0],
+                                               ms.ctypes.data_as(C.c_void_p), self._stream()), 'dy_forward_profile')
+        return ms
+
     # ---- host-buffer forward (the reference-facing call) ------------------------------------
     def pinned(self, key, shape, dtype):
         t = self.torch

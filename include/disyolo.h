@@ -100,6 +100,11 @@ int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const floa
 /* Network only (conv1..82), no decode / NMS / masks: fills the head and score-map buffers. */
 int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream);
 
+/* Measurement aid for bench.py: the same launches as dy_forward_network with a CUDA event between
+ * consecutive layers; layer_ms_host[1..82] receives each layer's device time in milliseconds
+ * ([0] = 0).  Synchronises the stream.  bf16 engine only. */
+int dy_forward_profile(dy_net* net, const float* images_dev, int32_t B, float* layer_ms_host, void* stream);
+
 /* Parity taps (replace sess.run on intermediate tensors of build_network).
  * dy_get_activation: output of convolutional<layer> (after BN/leaky/residual) as fp32 NHWC
  *   [B,h,w,c]; dims are reported by dy_layer_shape.
