@@ -261,7 +261,7 @@ def run_ours(args):
     box_dev = out['det_box']
     pe0.record()
     for _ in range(5):
-        eng.assemble_masks(mp, box_dev, cnt_dev, 'nhwc')
+        eng.assemble_masks(mp, box_dev, cnt_dev, 'nhwc', out=out['masks'])
     pe1.record()
     torch.cuda.synchronize()
     mask_ms = pe0.elapsed_time(pe1) / 5

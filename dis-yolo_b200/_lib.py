@@ -58,6 +58,7 @@ SIGNATURES = {
     'dy_nms': (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),
     'dy_assemble_masks': (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     'dy_conv_layer': (C.c_int, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P]),
+    'dy_set_option': (C.c_int, [C.c_char_p, _I]),
     'dy_launch_count': (C.c_int64, [_I]),
 }
 

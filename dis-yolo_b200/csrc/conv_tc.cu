@@ -83,34 +83,156 @@ __device__ __forceinline__ void write_out16(const ConvParams& p, const OutDesc& 
   }
 }
 
+constexpr int kNumThreads = 384;     // 12 warps: producer, MMA, TMEM-alloc, spare, 2 x 4 epilogue warps
+
+// folded BN scale/shift (+ leaky) on one 16-column accumulator chunk
+__device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r)[16], const float* s_scale,
+                                         const float* s_shift, int c0, float (&v)[16]) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * j4);   // smem broadcast
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * j4);
+    v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), sc.x, sh.x);
+    v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), sc.y, sh.y);
+    v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), sc.z, sh.z);
+    v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), sc.w, sh.w);
+  }
+  if (p.act) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(p.alpha * v[j], v[j]);
+  }
+}
+
+// residual of this chunk (16 bf16 = 2 x 16B) -> registers; issued one chunk ahead of use
+__device__ __forceinline__ void load_res16(const __nv_bfloat16* rp, uint4& a, uint4& b) {
+  const uint4* q = reinterpret_cast<const uint4*>(rp);
+  a = __ldg(q);
+  b = __ldg(q + 1);
+}
+
+// direct path: the row's owner thread adds its residual and writes its own pixels
+__device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const PixelInfo& px, long long m,
+                                                      int gcol, const uint32_t (&r)[16], const float* s_scale,
+                                                      const float* s_shift, int c0, bool has_res, const uint4& ra,
+                                                      const uint4& rb) {
+  float v[16];
+  bn_act16(p, r, s_scale, s_shift, c0, v);
+  if (has_res) {
+    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+      const float2 f = __bfloat1622float2(h);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+  write_out16(p, p.out[0], px, m, gcol, v);
+  if (p.out[1].mode != OUT_NONE) write_out16(p, p.out[1], px, m, gcol, v);
+}
+
+// staged path, phase 1: (+ residual already sitting in the staging row) -> bf16 -> staging row
+__device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&r)[16],
+                                                      const float* s_scale, const float* s_shift, int c0,
+                                                      bool has_res, uint8_t* srow /* row base + 2*col */) {
+  float v[16];
+  bn_act16(p, r, s_scale, s_shift, c0, v);
+  uint4* q = reinterpret_cast<uint4*>(srow);
+  if (has_res) {
+    const uint4 ra = q[0], rb = q[1];
+    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+      const float2 f = __bfloat1622float2(h);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+  uint4 a, b;
+  a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
+  a.z = pack_bf16(v[4], v[5]);   a.w = pack_bf16(v[6], v[7]);
+  b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
+  b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+  q[0] = a;
+  q[1] = b;
+}
+
+// destination element offset of a pixel's row in an output form (without the channel), or -1
+__device__ __forceinline__ long long dest_offset(const ConvParams& p, const OutDesc& o, const PixelInfo& px,
+                                                 long long m) {
+  if (!px.valid) return -1;
+  switch (o.mode) {
+    case OUT_SAME:
+      return m * o.ld;
+    case OUT_S2D: {
+      const int Hq = p.H / 2 + 1, Wq = p.W / 2 + 1;
+      const long long r = ((long long)px.n * Hq + (px.y >> 1)) * Wq + (px.x >> 1);
+      return r * o.ld + (((px.y & 1) << 1) | (px.x & 1)) * p.cout;
+    }
+    case OUT_UP2: {
+      const int Hu = 2 * p.H + 1, Wu = 2 * p.W + 1;
+      return (((long long)px.n * Hu + 2 * px.y) * Wu + 2 * px.x) * o.ld;
+    }
+    default:
+      return -1;
+  }
+}
+
+// staged path, phase 2: one 16-byte vector (8 channels) of one row -> every destination form
+__device__ __forceinline__ void store_vec(const ConvParams& p, const OutDesc& o, long long off, int gcol,
+                                          const uint4& v) {
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(o.ptr) + off + gcol;
+  *reinterpret_cast<uint4*>(d) = v;
+  if (o.mode == OUT_UP2) {
+    const long long Wu = 2 * p.W + 1;
+    *reinterpret_cast<uint4*>(d + o.ld) = v;
+    *reinterpret_cast<uint4*>(d + Wu * o.ld) = v;
+    *reinterpret_cast<uint4*>(d + (Wu + 1) * o.ld) = v;
+  }
+}
+
 template <int KCHUNK>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
+               const __grid_constant__ ConvParams p) {
   static_assert(KCHUNK == 64 || KCHUNK == 32, "K chunk is one 128B or 64B swizzle row");
   constexpr uint32_t kLayout = (KCHUNK == 64) ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
   constexpr uint32_t kSBO = (KCHUNK == 64) ? 1024u : 512u;        // 8 rows of the swizzle atom
-  constexpr uint32_t kABytes = kBlockM * KCHUNK * 2;
 
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_scale[2][256];                 // per epilogue warpgroup
+  __shared__ __align__(16) float s_shift[2][256];
+  __shared__ long long s_dst[2][2][kBlockM];                      // [warpgroup][output][row] element offset / -1
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t b_bytes = (uint32_t)p.block_n * KCHUNK * 2;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t b_bytes = (uint32_t)p.block_n * KCHUNK * 2;            // one weight K chunk
+  const uint32_t a_tx = (uint32_t)p.a_rows * KCHUNK * 2;                // bytes one A box delivers
+  const uint32_t a_bytes = (a_tx + 1023u) & ~1023u;
+  const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : (uint32_t)p.max_ntap * b_bytes);
+  const uint32_t bres_bytes = p.b_resident ? (uint32_t)p.num_chunks * b_bytes : 0u;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // swizzle atoms need 1024B alignment
-  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));     // [resident weights][stages...]
+  const uint32_t stages_off = bres_bytes;
+  constexpr uint32_t kRowBytes = KCHUNK * 2;
+  const uint32_t epi_pitch = (uint32_t)p.slab * 2 + 16;                 // staging row pitch (bank-conflict pad)
+  const uint32_t epi_off = stages_off + (uint32_t)p.num_stages * stage_bytes;
   const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+  const bool has_res = p.residual != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
+    if (has_res) tma_prefetch_desc(&mapR);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
@@ -119,8 +241,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp of the owning warpgroup
     }
+    mbar_init(&bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -135,21 +258,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
+      if (p.b_resident) {
+        // this CTA only ever sees one N tile (grid is a multiple of n_tiles_n): park its weights
+        const int n0c = (int)(blockIdx.x % p.n_tiles_n) * p.block_n;
+        mbar_expect_tx(&bres_bar, bres_bytes);
+        for (int kb = 0; kb < p.num_chunks; ++kb)
+          tma_load_2d(smem_gen + (size_t)kb * b_bytes, &mapB, &bres_bar, kb * KCHUNK, n0c);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / p.n_tiles_n) * kBlockM;
         const int n0 = (tile % p.n_tiles_n) * p.block_n;
-        int kb = 0;
+        if (has_res) {
+          // pull the residual tile towards L2 now; the epilogue reads it a few microseconds later
+          for (int c = 0; c < p.block_n; c += 64) tma_prefetch_2d(&mapR, n0 + c, m0);
+        }
         for (int s = 0; s < p.num_seg; ++s) {
-          const ConvSeg sg = p.seg[s];
+          const ConvSeg& sg = p.seg[s];   // stays in constant param space (dynamic tap index)
           const CUtensorMap* am = sg.map ? &mapA1 : &mapA0;
-          for (int c = 0; c < sg.nchunk; ++c, ++kb) {
+          const uint32_t tx = a_tx + (p.b_resident ? 0u : (uint32_t)sg.ntap * b_bytes);
+          for (int c = 0; c < sg.nchunk; ++c) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            uint8_t* sa = smem_gen + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full_bar[stage], tx);
+            uint8_t* sa = smem_gen + stages_off + (size_t)stage * stage_bytes;
             tma_load_2d(sa, am, &full_bar[stage], sg.col0 + c * KCHUNK, m0 + sg.shift);
-            tma_load_2d(sa + kABytes, &mapB, &full_bar[stage], kb * KCHUNK, n0);
+            if (!p.b_resident) {
+              for (int t = 0; t < sg.ntap; ++t)
+                tma_load_2d(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[stage],
+                            (sg.tap_b0[t] + c) * KCHUNK, n0);
+            }
             if (++stage == p.num_stages) {
               stage = 0;
               phase ^= 1u;
@@ -165,28 +303,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (p.b_resident) {
+        mbar_wait(&bres_bar, 0);                        // resident weights have landed
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);    // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        for (int kb = 0; kb < p.num_chunks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);           // TMA bytes have landed
-          tc_fence_after();
-          const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-          const uint64_t adesc = umma_desc(sa, kSBO, kLayout);
-          const uint64_t bdesc = umma_desc(sa + kABytes, kSBO, kLayout);
+        uint32_t first = 1u;
+        for (int s = 0; s < p.num_seg; ++s) {
+          const ConvSeg& sg = p.seg[s];   // stays in constant param space (dynamic tap index)
+          for (int c = 0; c < sg.nchunk; ++c) {
+            mbar_wait(&full_bar[stage], phase);         // TMA bytes have landed
+            tc_fence_after();
+            const uint32_t sa = smem_base + stages_off + (uint32_t)stage * stage_bytes;
+            for (int t = 0; t < sg.ntap; ++t) {
+              // same box, start address advanced by whole rows: tap t of the shared halo'd segment
+              const uint64_t adesc = umma_desc(sa + (uint32_t)sg.tap_row[t] * kRowBytes, kSBO, kLayout);
+              const uint32_t sb = p.b_resident ? smem_base + (uint32_t)(sg.tap_b0[t] + c) * b_bytes
+                                               : sa + a_bytes + (uint32_t)t * b_bytes;
+              const uint64_t bdesc = umma_desc(sb, kSBO, kLayout);
 #pragma unroll
-          for (int k = 0; k < KCHUNK / 16; ++k) {
-            // +32 bytes (16 bf16) along K inside the swizzle row: +2 in the (addr>>4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      (uint32_t)((kb | k) != 0));
-          }
-          umma_commit(&empty_bar[stage]);               // frees the smem slot when the MMAs retire
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1u;
+              for (int k = 0; k < KCHUNK / 16; ++k) {
+                // +32 bytes (16 bf16) along K inside the swizzle row: +2 in the (addr>>4) field
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ^ 1u);
+                first = 0u;
+              }
+            }
+            umma_commit(&empty_bar[stage]);             // frees the smem slot when the MMAs retire
+            if (++stage == p.num_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
         umma_commit(&tfull_bar[acc]);                   // accumulator complete -> epilogue
@@ -194,11 +345,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ================================ epilogue ================================
-    const int q = warp - 4;                             // TMEM lane quarter == warp % 4
+    // Two warpgroups; warpgroup g drains accumulator stage g, i.e. every other tile of this CTA.
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;                             // TMEM lane quarter == warp % 4
+    const int wg_tid = (warp - 4 - 4 * wg) * 32 + lane; // 0..127 inside the warpgroup
     const int Hp = p.H + 1, Wp = p.W + 1;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
+    float* my_scale = s_scale[wg];
+    float* my_shift = s_shift[wg];
+    int cached_n0 = -1;
+    int it = wg;
+    for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = wg;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int m0 = (tile / p.n_tiles_n) * kBlockM;
       const int n0 = (tile % p.n_tiles_n) * p.block_n;
@@ -212,45 +369,115 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         px.n = (int)(t / Hp);
         px.valid = (m < p.M) && (x < p.W) && (px.y < p.H);
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      if (n0 != cached_n0) {
+        // (re)stage this N tile's folded BN scale/shift; 128 threads of the warpgroup only
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        for (int i = wg_tid; i < p.block_n; i += 128) {
+          my_scale[i] = __ldg(p.scale + n0 + i);
+          my_shift[i] = __ldg(p.shift + n0 + i);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        cached_n0 = n0;
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (px.valid) {
-          const int gcol = n0 + c0;
-          float v[16];
-          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + gcol);
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + gcol);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 sc = __ldg(sc4 + j4);
-            const float4 sh = __ldg(sh4 + j4);
-            v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), sc.x, sh.x);
-            v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), sc.y, sh.y);
-            v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), sc.z, sh.z);
-            v[4 * j4 + 3] = fmaf(__uint_as_float(r[4 * j4 + 3]), sc.w, sh.w);
+      uint32_t r0[16], r1[16];
+      if (p.slab == 0) {
+        // ---------------- direct path: the row's owner thread reads/writes global memory ----------------
+        const __nv_bfloat16* res_row = has_res ? p.residual + m * p.res_ld + n0 : nullptr;
+        const bool do_res = has_res && px.valid;
+        uint4 ra0 = make_uint4(0, 0, 0, 0), rb0 = ra0, ra1 = ra0, rb1 = ra0;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        tmem_ld16(taddr, r0);
+        if (do_res) load_res16(res_row, ra0, rb0);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          tmem_ld_wait();
+          const bool more1 = c0 + 16 < p.block_n;
+          if (more1) {
+            tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
+            if (do_res) load_res16(res_row + c0 + 16, ra1, rb1);
           }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(p.alpha * v[j], v[j]);
+          if (px.valid) epilogue_chunk_direct(p, px, m, n0 + c0, r0, my_scale, my_shift, c0, has_res, ra0, rb0);
+          if (more1) {
+            tmem_ld_wait();
+            if (c0 + 32 < p.block_n) {
+              tmem_ld16(taddr + (uint32_t)(c0 + 32), r0);
+              if (do_res) load_res16(res_row + c0 + 32, ra0, rb0);
+            }
+            if (px.valid)
+              epilogue_chunk_direct(p, px, m, n0 + c0 + 16, r1, my_scale, my_shift, c0 + 16, has_res, ra1, rb1);
           }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.res_ld + gcol);
-            const uint4 ra = __ldg(rp), rb = __ldg(rp + 1);
-            const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        }
+      } else {
+        // ---------------- staged path: coalesced residual reads and output stores ----------------
+        // Phase 1 works thread-per-row (that is how TMEM is read); global memory is touched only in
+        // the cooperative phases 0/2 where consecutive lanes cover consecutive 16-byte vectors of a
+        // row, so one instruction touches 4-8 cache lines instead of 32.
+        uint8_t* stg = smem_gen + epi_off + (size_t)wg * kBlockM * epi_pitch;
+        const int row = q * 32 + lane;
+        const int vpr = p.slab >> 3;                      // 16-byte vectors per staged row (4 or 8)
+        const int vsh = (p.slab == 64) ? 3 : 2;           // log2(vpr)
+        const int nvec = kBlockM * vpr;                   // vectors per slab, nvec / 128 per thread
+        s_dst[wg][0][row] = dest_offset(p, p.out[0], px, m);
+        s_dst[wg][1][row] = (p.out[1].mode != OUT_NONE) ? dest_offset(p, p.out[1], px, m) : -1;
+        uint4 rres[8];
+        auto fetch_res = [&](int slab0) {                 // coalesced residual slab -> registers
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-              const float2 f = __bfloat1622float2(h);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * 128 + wg_tid;
+            if (i < vpr) {
+              const int rr = idx >> vsh, cj = idx & (vpr - 1);
+              const long long mm = (long long)m0 + rr;
+              rres[i] = (mm < p.M) ? __ldg(reinterpret_cast<const uint4*>(p.residual + mm * p.res_ld + n0 + slab0 +
+                                                                          cj * 8))
+                                   : make_uint4(0, 0, 0, 0);
             }
           }
-          write_out16(p, p.out[0], px, m, gcol, v);
-          if (p.out[1].mode != OUT_NONE) write_out16(p, p.out[1], px, m, gcol, v);
+        };
+        if (has_res) fetch_res(0);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        for (int slab0 = 0; slab0 < p.block_n; slab0 += p.slab) {
+          if (has_res) {
+            // phase 0: park this slab's residual in the staging rows, start fetching the next slab's
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int idx = i * 128 + wg_tid;
+              if (i < vpr) {
+                const int rr = idx >> vsh, cj = idx & (vpr - 1);
+                *reinterpret_cast<uint4*>(stg + (size_t)rr * epi_pitch + cj * 16) = rres[i];
+              }
+            }
+            if (slab0 + p.slab < p.block_n) fetch_res(slab0 + p.slab);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          // phase 1: accumulator -> BN/leaky (+ residual) -> bf16, thread per row
+          uint8_t* srow = stg + (size_t)row * epi_pitch;
+          tmem_ld16(taddr + (uint32_t)slab0, r0);
+          for (int c0 = 0; c0 < p.slab; c0 += 32) {
+            tmem_ld_wait();
+            const bool more1 = c0 + 16 < p.slab;
+            if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
+            epilogue_chunk_staged(p, r0, my_scale, my_shift, slab0 + c0, has_res, srow + c0 * 2);
+            if (more1) {
+              tmem_ld_wait();
+              if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
+              epilogue_chunk_staged(p, r1, my_scale, my_shift, slab0 + c0 + 16, has_res, srow + (c0 + 16) * 2);
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          // phase 2: cooperative, coalesced stores to every destination form
+          for (int idx = wg_tid; idx < nvec; idx += 128) {
+            const int rr = idx >> vsh, cj = idx & (vpr - 1);
+            const long long d0 = s_dst[wg][0][rr];
+            if (d0 < 0) continue;                         // pad pixel / beyond M: never written
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + cj * 16);
+            const int gcol = n0 + slab0 + cj * 8;
+            store_vec(p, p.out[0], d0, gcol, v);
+            const long long d1 = s_dst[wg][1][rr];
+            if (d1 >= 0) store_vec(p, p.out[1], d1, gcol, v);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         }
       }
       tc_fence_before();
@@ -312,45 +539,68 @@ int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long c
 }
 
 // dynamic smem ceiling: 227 KB per CTA minus the kernel's static shared memory, rounded down
-static constexpr int kConvTcMaxSmem = 224 * 1024;
+static constexpr int kConvTcMaxSmem = 216 * 1024;
 
-size_t conv_tc_smem_bytes(int kchunk, int block_n, int stages) {
-  return (size_t)stages * (size_t)(kBlockM + block_n) * kchunk * 2 + 1024;
+static size_t a_stage_bytes(int kchunk, const ConvParams& p) {
+  return ((size_t)p.a_rows * kchunk * 2 + 1023) & ~(size_t)1023;
+}
+static size_t stage_bytes_of(int kchunk, const ConvParams& p) {
+  return a_stage_bytes(kchunk, p) + (p.b_resident ? 0 : (size_t)p.max_ntap * p.block_n * kchunk * 2);
+}
+static size_t resident_bytes_of(int kchunk, const ConvParams& p) {
+  return p.b_resident ? (size_t)p.num_chunks * p.block_n * kchunk * 2 : 0;
 }
 
-int conv_tc_pick_stages(int kchunk, int block_n) {
-  const size_t budget = 200 * 1024;
-  size_t per = (size_t)(kBlockM + block_n) * kchunk * 2;
-  int s = (int)(budget / per);
+static size_t epilogue_bytes_of(const ConvParams& p) {
+  return p.slab ? 2 * (size_t)kBlockM * ((size_t)p.slab * 2 + 16) : 0;
+}
+
+size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p) {
+  return resident_bytes_of(kchunk, p) + (size_t)p.num_stages * stage_bytes_of(kchunk, p) + epilogue_bytes_of(p) +
+         1024;
+}
+
+int conv_tc_pick_stages(int kchunk, const ConvParams& p) {
+  const size_t budget = 214 * 1024 - epilogue_bytes_of(p);
+  const size_t res = resident_bytes_of(kchunk, p);
+  if (res + 2 * stage_bytes_of(kchunk, p) > budget) return 0;
+  int s = (int)((budget - res) / stage_bytes_of(kchunk, p));
   if (s > kMaxStages) s = kMaxStages;
-  if (s < 2) s = 2;
   return s;
 }
 
 int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                   const ConvParams& p, int num_sms, cudaStream_t stream) {
+                   const CUtensorMap& r, const ConvParams& p, int num_sms, cudaStream_t stream) {
   DY_CHECK(kchunk == 64 || kchunk == 32, "kchunk");
   DY_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n");
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
   DY_CHECK(p.tmem_cols >= 2 * p.block_n && p.tmem_cols <= 512, "tmem_cols");
-  const size_t smem = conv_tc_smem_bytes(kchunk, p.block_n, p.num_stages);
+  DY_CHECK(p.a_rows == kBlockM || p.a_rows == kHaloRows, "a_rows");
+  DY_CHECK(p.max_ntap >= 1 && p.max_ntap <= 3, "max_ntap");
+  DY_CHECK(p.slab == 0 || ((p.slab == 32 || p.slab == 64) && p.block_n % p.slab == 0), "slab");
+  const size_t smem = conv_tc_smem_bytes(kchunk, p);
   DY_CHECK(smem <= (size_t)kConvTcMaxSmem, "pipeline does not fit in shared memory");
   const int tiles = p.n_tiles_m * p.n_tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (p.b_resident) {
+    // every CTA must keep seeing the same N tile: tile = blockIdx.x + i*grid, n = tile % n_tiles_n
+    grid = grid / p.n_tiles_n * p.n_tiles_n;
+    DY_CHECK(grid >= p.n_tiles_n, "grid too small for resident weights");
+  }
   if (kchunk == 64) {
     static bool attr64 = false;
     if (!attr64) {
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr64 = true;
     }
-    conv_tc_kernel<64><<<grid, 256, smem, stream>>>(a0, a1, b, p);
+    conv_tc_kernel<64><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, p);
   } else {
     static bool attr32 = false;
     if (!attr32) {
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32 = true;
     }
-    conv_tc_kernel<32><<<grid, 256, smem, stream>>>(a0, a1, b, p);
+    conv_tc_kernel<32><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, p);
   }
   DY_CUDA(cudaGetLastError());
   return DY_OK;

@@ -35,11 +35,22 @@ struct OutDesc {
   int ld;  // destination row pitch in elements
 };
 
+constexpr int kHaloRows = 136;   // 128 + 2 halo rows, rounded up to the 8-row swizzle atom
+
+// One A-operand segment of the K loop.  Every K chunk of the segment is ONE TMA box of a_rows rows
+// that feeds `ntap` MMA groups: group t reads the box starting tap_row[t] rows in (the UMMA
+// descriptor start address is simply advanced by whole rows -- the hardware swizzle is a pure
+// function of the shared-memory address, verified on B200 by scripts/experiments/umma_shift_test.cu)
+// against weight chunk tap_b0[t] + c.  A 3x3 stride-1 conv is therefore 3 segments (one per kernel
+// row) of 3 taps each instead of 9 separate loads.
 struct ConvSeg {
-  int map;     // 0 -> mapA0, 1 -> mapA1
-  int shift;   // row shift added to the tile's first row
-  int col0;    // first channel (element index along the A tensor's inner dimension)
-  int nchunk;  // number of K chunks in this segment
+  int map;         // 0 -> mapA0, 1 -> mapA1
+  int shift;       // row shift added to the tile's first row
+  int col0;        // first channel (element index along the A tensor's inner dimension)
+  int nchunk;      // number of K chunks in this segment
+  int ntap;        // 1..3 MMA groups per chunk
+  int tap_row[3];  // row offset of each group inside the loaded box
+  int tap_b0[3];   // weight K-chunk index of each group for c = 0
 };
 
 struct ConvParams {
@@ -50,8 +61,12 @@ struct ConvParams {
   int n_tiles_m, n_tiles_n;
   int num_seg;
   ConvSeg seg[kMaxSeg];
-  int num_chunks;  // sum of seg[].nchunk
+  int num_chunks;  // number of weight K chunks = sum of seg[].nchunk * seg[].ntap
   int num_stages;  // smem pipeline depth
+  int a_rows;      // rows per A box: 128, or kHaloRows when taps share a halo'd box
+  int max_ntap;    // max seg[].ntap (sizes the per-stage weight slots when weights are streamed)
+  int b_resident;  // 1: the CTA's whole [block_n x K] weight slab is loaded to smem once
+  int slab;        // epilogue staging width in columns (64 or 32); 0 = direct per-thread stores (fp32 heads)
   int tmem_cols;   // power of two >= 2*block_n, >= 32
   const float* scale;  // [n_tiles_n*block_n] folded BN scale (1 for biased convs)
   const float* shift;  // [n_tiles_n*block_n] folded BN shift / bias
@@ -67,11 +82,11 @@ struct ConvParams {
 int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld_elems,
                  int box_cols, int box_rows);
 
-size_t conv_tc_smem_bytes(int kchunk, int block_n, int stages);
-int conv_tc_pick_stages(int kchunk, int block_n);
+size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p);
+int conv_tc_pick_stages(int kchunk, const ConvParams& p);
 
 // kchunk in {32, 64}
 int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                   const ConvParams& p, int num_sms, cudaStream_t stream);
+                   const CUtensorMap& r, const ConvParams& p, int num_sms, cudaStream_t stream);
 
 }  // namespace dy

@@ -107,7 +107,7 @@ static void tf_same_pad(int in, int k, int s, int* before) {
 // ---------------------------------------------------------------------------------------------
 struct TcPlan {
   int kchunk = 64;
-  CUtensorMap a0, a1, b;
+  CUtensorMap a0, a1, b, r;
   ConvParams p;
 };
 
@@ -127,6 +127,11 @@ struct TcConvDesc {
   OutDesc out[2];
 };
 
+// tuning overrides (dy_set_option): -1 = automatic
+static int g_opt_resident = -1;     // 0: never keep weights resident, 1: whenever the slab fits
+static int g_opt_halo = -1;         // 0: never share a halo'd A box between taps, 1: whenever legal
+static int g_opt_staged = -1;       // 0: per-thread row stores, 1: smem-staged cooperative stores
+
 static int pick_block_n(int cout_pad, long long rows, int num_sms) {
   static const int cands[] = {256, 128, 64, 32, 16};
   int best = 16;
@@ -140,6 +145,8 @@ static int pick_block_n(int cout_pad, long long rows, int num_sms) {
   return best;
 }
 
+static const size_t kResidentSlabMax = 80 * 1024;
+
 static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   DY_CHECK(d.k == 1 || d.k == 3, "kernel size must be 1 or 3");
   DY_CHECK(d.s == 1 || (d.s == 2 && d.k == 3 && d.cin1 == 0), "stride 2 only for 3x3 without concat");
@@ -148,6 +155,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   const int kchunk = (d.cin0 % 64 == 0 && d.cin1 % 64 == 0) ? 64 : 32;
   const int Hp = d.H + 1, Wp = d.W + 1;
   const long long rows_max = (long long)d.max_batch * Hp * Wp;
+  const long long m_tiles = (rows_max + kBlockM - 1) / kBlockM;
   const int K = d.k * d.k * d.cin0 + d.cin1;
   ConvParams& p = plan->p;
   memset(&p, 0, sizeof(p));
@@ -155,9 +163,56 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   p.H = d.H;
   p.W = d.W;
   p.cout = d.cout;
-  p.block_n = pick_block_n(d.cout_pad, rows_max, num_sms);
+
+  // ---- planning mode.  Rules distilled from a per-layer A/B of every mode at batch 64 on B200
+  // (scripts/ab_layers.py, profiles/r1_ab_layers.txt):
+  //   resident : the CTA's whole weight slab lives in smem (only when all of N fits: <= 80 KB)
+  //   halo     : 3x3 -- one 136-row activation box per kernel row feeds the 3 horizontal taps
+  //   staged   : epilogue goes through smem for coalesced residual reads / output stores
+  bool resident = false, halo = false, staged = false;
+  int block_n = pick_block_n(d.cout_pad, rows_max, num_sms);
+  const bool enough_work = m_tiles >= num_sms;
+  const bool fits = d.cout_pad <= 256 && (size_t)d.cout_pad * K * 2 <= kResidentSlabMax;
+  const bool has_res = d.residual != nullptr;
+  const bool dual = d.out[1].mode != OUT_NONE;
+  const bool up2 = d.out[0].mode == OUT_UP2 || d.out[1].mode == OUT_UP2;
+  if (enough_work) {
+    if (d.k == 1) {
+      resident = fits;
+      staged = up2;
+    } else if (d.s == 1) {
+      if (fits) {
+        resident = halo = true;
+        staged = has_res || dual;
+      } else if (d.cout_pad <= 128) {
+        halo = true;
+        staged = has_res || dual;
+      } else if (d.cout_pad == 256) {
+        halo = staged = has_res;
+      } else {
+        staged = true;
+      }
+    } else {
+      if (fits) resident = halo = true;
+      else if (d.cout_pad <= 128) halo = true;
+    }
+  } else {
+    staged = up2;
+  }
+  if (g_opt_resident == 0) resident = false;
+  if (g_opt_resident == 1 && fits) resident = true;
+  if (g_opt_halo == 0) halo = false;
+  if (g_opt_halo == 1 && d.k == 3) halo = true;
+  if (g_opt_staged >= 0) staged = g_opt_staged != 0;
+  if (resident) block_n = d.cout_pad;
+  if (halo && !resident) {
+    // three streamed weight chunks per stage: keep a stage <= ~64 KB so that >= 3 stages fit
+    while (block_n > 64 && 3 * (size_t)block_n * kchunk * 2 > 48 * 1024) block_n /= 2;
+  }
+  p.block_n = block_n;
   p.n_tiles_n = d.cout_pad / p.block_n;
-  p.num_stages = conv_tc_pick_stages(kchunk, p.block_n);
+  p.b_resident = resident ? 1 : 0;
+  p.a_rows = halo ? kHaloRows : kBlockM;
   int tc = 32;
   while (tc < 2 * p.block_n) tc <<= 1;
   p.tmem_cols = tc;
@@ -169,31 +224,81 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   p.res_ld = d.cout;
   p.out[0] = d.out[0];
   p.out[1] = d.out[1];
-  int ns = 0, nchunks = 0;
+
+  // ---- K loop segments.  Weight K-chunk index of tap (kh,kw), chunk c: ((kh*3+kw)*cpt + c).
+  const int cpt = d.cin0 / kchunk;
+  int ns = 0;
+  auto seg1 = [&](int map, int shift, int col0, int nchunk, int b0) {
+    ConvSeg g;
+    memset(&g, 0, sizeof(g));
+    g.map = map; g.shift = shift; g.col0 = col0; g.nchunk = nchunk; g.ntap = 1;
+    g.tap_row[0] = 0; g.tap_b0[0] = b0;
+    p.seg[ns++] = g;
+  };
   if (d.k == 1) {
-    p.seg[ns++] = ConvSeg{0, 0, 0, d.cin0 / kchunk};
-    if (d.cin1 > 0) p.seg[ns++] = ConvSeg{1, 0, 0, d.cin1 / kchunk};
+    seg1(0, 0, 0, cpt, 0);
+    if (d.cin1 > 0) seg1(1, 0, 0, d.cin1 / kchunk, cpt);
   } else if (d.s == 1) {
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw) p.seg[ns++] = ConvSeg{0, (kh - 1) * Wp + (kw - 1), 0, d.cin0 / kchunk};
+    if (halo) {
+      for (int kh = 0; kh < 3; ++kh) {      // one box per kernel row, three row-shifted taps
+        ConvSeg g;
+        memset(&g, 0, sizeof(g));
+        g.map = 0; g.shift = (kh - 1) * Wp - 1; g.col0 = 0; g.nchunk = cpt; g.ntap = 3;
+        for (int kw = 0; kw < 3; ++kw) { g.tap_row[kw] = kw; g.tap_b0[kw] = (kh * 3 + kw) * cpt; }
+        p.seg[ns++] = g;
+      }
+    } else {
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) seg1(0, (kh - 1) * Wp + (kw - 1), 0, cpt, (kh * 3 + kw) * cpt);
+    }
   } else {
-    // TF 'SAME', stride 2, even input: pad 0 before / 1 after -> input pixel (2oy+kh, 2ox+kw)
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw)
-        p.seg[ns++] = ConvSeg{0, (kh >> 1) * Wp + (kw >> 1), (((kh & 1) << 1) | (kw & 1)) * d.cin0, d.cin0 / kchunk};
+    // TF 'SAME', stride 2, even input: pad 0 before / 1 after -> input pixel (2oy+kh, 2ox+kw) =
+    // space-to-depth pixel (oy+(kh>>1), ox+(kw>>1)), channel block ((kh&1)*2 + (kw&1))
+    if (halo) {
+      for (int kh = 0; kh < 3; ++kh) {
+        ConvSeg g;                           // column parity 0: taps kw=0 (row 0) and kw=2 (row 1)
+        memset(&g, 0, sizeof(g));
+        g.map = 0; g.shift = (kh >> 1) * Wp; g.col0 = ((kh & 1) << 1) * d.cin0; g.nchunk = cpt; g.ntap = 2;
+        g.tap_row[0] = 0; g.tap_b0[0] = (kh * 3 + 0) * cpt;
+        g.tap_row[1] = 1; g.tap_b0[1] = (kh * 3 + 2) * cpt;
+        p.seg[ns++] = g;
+        seg1(0, (kh >> 1) * Wp, (((kh & 1) << 1) | 1) * d.cin0, cpt, (kh * 3 + 1) * cpt);   // parity 1: kw=1
+      }
+    } else {
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          seg1(0, (kh >> 1) * Wp + (kw >> 1), (((kh & 1) << 1) | (kw & 1)) * d.cin0, cpt, (kh * 3 + kw) * cpt);
+    }
   }
-  for (int i = 0; i < ns; ++i) nchunks += p.seg[i].nchunk;
+  int nchunks = 0, max_ntap = 1;
+  for (int i = 0; i < ns; ++i) {
+    nchunks += p.seg[i].nchunk * p.seg[i].ntap;
+    if (p.seg[i].ntap > max_ntap) max_ntap = p.seg[i].ntap;
+  }
   p.num_seg = ns;
   p.num_chunks = nchunks;
+  p.max_ntap = max_ntap;
+  // epilogue staging: bf16 outputs go through shared memory for coalesced stores
+  const bool bf16_out = d.out[0].mode == OUT_SAME || d.out[0].mode == OUT_S2D || d.out[0].mode == OUT_UP2;
+  if (!bf16_out || p.block_n % 32 != 0) staged = false;
+  p.slab = !staged ? 0 : (p.block_n % 64 == 0 && p.block_n <= 128 ? 64 : 32);
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
+  p.num_stages = conv_tc_pick_stages(kchunk, p);
+  DY_CHECK(p.num_stages >= 2, "no room for a shared-memory pipeline");
   const int a0_cols = (d.s == 2) ? 4 * d.cin0 : d.cin0;
-  DY_TRY(make_tmap_2d(&plan->a0, d.a0, rows_max, a0_cols, a0_cols, kchunk, kBlockM));
+  DY_TRY(make_tmap_2d(&plan->a0, d.a0, rows_max, a0_cols, a0_cols, kchunk, p.a_rows));
   if (d.cin1 > 0) {
-    DY_TRY(make_tmap_2d(&plan->a1, d.a1, rows_max, d.cin1, d.cin1, kchunk, kBlockM));
+    DY_TRY(make_tmap_2d(&plan->a1, d.a1, rows_max, d.cin1, d.cin1, kchunk, p.a_rows));
   } else {
     plan->a1 = plan->a0;
   }
   DY_TRY(make_tmap_2d(&plan->b, d.wpk, d.cout_pad, K, K, kchunk, p.block_n));
+  if (d.residual != nullptr) {
+    DY_CHECK(d.cout % 64 == 0 && p.block_n % 64 == 0, "residual layers need cout % 64 == 0");
+    DY_TRY(make_tmap_2d(&plan->r, d.residual, rows_max, d.cout, d.cout, 64, kBlockM));   // L2 prefetch only
+  } else {
+    plan->r = plan->a0;
+  }
   return DY_OK;
 }
 
@@ -204,7 +309,7 @@ static int run_tc_plan(TcPlan& plan, int B, int num_sms, cudaStream_t st) {
   p.M = (int)M;
   p.n_tiles_m = (int)((M + kBlockM - 1) / kBlockM);
   note_launch();
-  return launch_conv_tc(plan.kchunk, plan.a0, plan.a1, plan.b, p, num_sms, st);
+  return launch_conv_tc(plan.kchunk, plan.a0, plan.a1, plan.b, plan.r, p, num_sms, st);
 }
 
 // pack HWIO fp32 weights -> [cout_pad][K] bf16 (K index = (kh*k+kw)*cin + ci, zero rows beyond cout)
@@ -615,6 +720,19 @@ int dy_device_count(void) {
     return 0;
   }
   return n;
+}
+
+int dy_set_option(const char* name, int32_t value) {
+  DY_CHECK(name != nullptr, "null option name");
+  const std::string n(name);
+  if (n == "tc_resident") g_opt_resident = value;
+  else if (n == "tc_halo") g_opt_halo = value;
+  else if (n == "tc_staged") g_opt_staged = value;
+  else {
+    set_error("unknown option " + n);
+    return DY_ERR_NOTFOUND;
+  }
+  return DY_OK;
 }
 
 int64_t dy_launch_count(int32_t reset) {

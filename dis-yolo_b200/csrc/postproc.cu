@@ -327,42 +327,56 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
 // bin (by,bx) of box d, sigmoid(0)=0.5 outside the box.  One thread = 4 consecutive x (float4
 // store); planar score maps make the gather a coalesced row read.
 // ------------------------------------------------------------------------------------------
+constexpr int kMaskRowSplit = 4;   // CTAs per (detection, image)
+
 __global__ void __launch_bounds__(256) mask_kernel(MaskArgs a) {
   const int d = blockIdx.y, b = blockIdx.z;
   if (d >= a.det_count[b]) return;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  const int quads_per_row = a.S >> 2;
-  if (q >= a.S * quads_per_row) return;
-  const int y = q / quads_per_row;
-  const int x0 = (q % quads_per_row) << 2;
-  const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
+  __shared__ int s_gx[kMaxK + 1], s_gy[kMaxK + 1];
+  if (threadIdx.x <= kMaxK) {
+    const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
+    s_gx[threadIdx.x] = threadIdx.x <= a.k ? ed[threadIdx.x] : 0x7fffffff;
+    s_gy[threadIdx.x] = threadIdx.x <= a.k ? ed[kMaxK + 1 + threadIdx.x] : 0x7fffffff;
+  }
+  __syncthreads();
   int gx[kMaxK + 1], gy[kMaxK + 1];
 #pragma unroll
   for (int j = 0; j <= kMaxK; ++j) {
-    gx[j] = (j <= a.k) ? __ldg(ed + j) : 0;
-    gy[j] = (j <= a.k) ? __ldg(ed + kMaxK + 1 + j) : 0;
+    gx[j] = s_gx[j];
+    gy[j] = s_gy[j];
   }
-  int by = -1;
-#pragma unroll
-  for (int j = 0; j < kMaxK; ++j)
-    if (j < a.k && y >= gy[j] && y < gy[j + 1]) by = j;
-  float v[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = x0 + i;
-    int bx = -1;
+  const int quads_per_row = a.S >> 2;
+  const int rows_per_cta = (a.S + kMaskRowSplit - 1) / kMaskRowSplit;
+  const int y_begin = blockIdx.x * rows_per_cta;
+  const int y_end = min(a.S, y_begin + rows_per_cta);
+  const int nq = (y_end - y_begin) * quads_per_row;
+  const float* sbase = a.score + b * a.s_img;
+  float* obase = a.out + ((long long)b * a.max_det + d) * a.S * a.S;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const int y = y_begin + q / quads_per_row;
+    const int x0 = (q % quads_per_row) << 2;
+    int by = -1;
 #pragma unroll
     for (int j = 0; j < kMaxK; ++j)
-      if (j < a.k && x >= gx[j] && x < gx[j + 1]) bx = j;
-    float val = 0.5f;
-    if (by >= 0 && bx >= 0) {
-      const float s = __ldg(a.score + b * a.s_img + (long long)(by * a.k + bx) * a.s_ch + y * a.s_row + x * a.s_pix);
-      val = sigmoidf_(s);
+      if (j < a.k && y >= gy[j] && y < gy[j + 1]) by = j;
+    float4 o = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+    if (by >= 0 && x0 + 3 >= gx[0] && x0 < gx[a.k]) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x0 + i;
+        int bx = -1;
+#pragma unroll
+        for (int j = 0; j < kMaxK; ++j)
+          if (j < a.k && x >= gx[j] && x < gx[j + 1]) bx = j;
+        float val = 0.5f;
+        if (bx >= 0) val = sigmoidf_(__ldg(sbase + (long long)(by * a.k + bx) * a.s_ch + y * a.s_row + x * a.s_pix));
+        v[i] = val;
+      }
+      o = make_float4(v[0], v[1], v[2], v[3]);
     }
-    v[i] = val;
+    __stcs(reinterpret_cast<float4*>(obase + (long long)y * a.S + x0), o);   // streaming store
   }
-  float4* o = reinterpret_cast<float4*>(a.out + (((long long)b * a.max_det + d) * a.S + y) * a.S + x0);
-  *o = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 }  // namespace
@@ -403,7 +417,7 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
 int launch_masks(const MaskArgs& a, cudaStream_t st) {
   DY_CHECK(a.S % 4 == 0, "score map size must be a multiple of 4");
   DY_CHECK(a.max_det <= 65535 && a.B <= 65535, "grid limits");
-  dim3 grid((a.S * (a.S / 4) + 255) / 256, a.max_det, a.B);
+  dim3 grid(kMaskRowSplit, a.max_det, a.B);
   mask_kernel<<<grid, 256, 0, st>>>(a);
   DY_CUDA(cudaGetLastError());
   return DY_OK;

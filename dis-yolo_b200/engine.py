@@ -264,16 +264,22 @@ class Engine(object):
                                    _ptr(cnt), _ptr(raw), self._stream()), 'dy_nms')
         return idx, cnt, raw
 
-    def assemble_masks(self, score_maps, det_box, det_count, layout='nhwc'):
+    def assemble_masks(self, score_maps, det_box, det_count, layout='nhwc', out=None):
         t = self.torch
         score_maps = self._dev(score_maps, t.float32)
         det_box, det_count = self._dev(det_box, t.float32), self._dev(det_count, t.int32)
         B, md, sm = det_box.shape[0], self.max_detection, self.mask_size
-        out = t.empty((B, md, sm, sm), dtype=t.float32, device=self.device)
+        if out is None:
+            out = t.empty((B, md, sm, sm), dtype=t.float32, device=self.device)
         _lib.check(self.lib.dy_assemble_masks(self.h, _ptr(score_maps), 0 if layout == 'nhwc' else 1, B,
                                               _ptr(det_box), _ptr(det_count), _ptr(out), self._stream()),
                    'dy_assemble_masks')
         return out
+
+
+def set_option(name, value):
+    """dy_set_option: planning overrides of the conv engine ('tc_resident', 'tc_halo'; -1 = auto)."""
+    _lib.check(_lib.lib().dy_set_option(name.encode(), int(value)), 'dy_set_option')
 
 
 def conv_layer(x, w, stride, scale, shift, act, alpha=0.1, residual=None, precision='bf16'):

@@ -149,6 +149,12 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
                   const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,
                   void* stream);
 
+/* Tuning / test overrides of the conv engine's planning heuristics; value -1 = automatic.
+ *   "tc_resident": 0 never / 1 whenever it fits -- keep a CTA's weight slab resident in smem
+ *   "tc_halo":     0 never / 1 whenever legal   -- one halo'd activation box feeds all 3 horizontal taps
+ * Affects plans built afterwards (dy_finalize_weights, dy_conv_layer). */
+int dy_set_option(const char* name, int32_t value);
+
 /* Kernel launches issued by this library since the last call (bench.py's gpu_launches). */
 int64_t dy_launch_count(int32_t reset);
 

@@ -109,3 +109,32 @@ def test_conv_linearity_property():
     y1 = conv_layer(xc, w, 1, one, zero, False, 0.1, None, 'bf16').cpu().numpy()
     y2 = conv_layer(xc * 2.0, w, 1, one, zero, False, 0.1, None, 'bf16').cpu().numpy()
     assert np.array_equal(y2, 2.0 * y1)       # power-of-two scaling is exact in bf16/fp32
+
+
+@pytest.mark.parametrize('resident,halo,staged', [(1, 1, 1), (0, 1, 0), (1, 0, 0), (0, 0, 1), (0, 1, 1)])
+@pytest.mark.parametrize('case', [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], CASES[6], CASES[7],
+                                  CASES[8], CASES[10]],
+                         ids=lambda c: 'B%d_%dx%d_%d-%d_k%ds%d' % c[:7])
+def test_conv_bf16_forced_modes(case, resident, halo, staged):
+    """Every planning mode of the tensor-core engine (weights resident in smem or streamed; one
+    halo'd activation box shared by the three horizontal taps or one box per tap) must give the
+    same result as the default plan -- bit for bit, since the MMA order along K is unchanged."""
+    import torch
+    from disyolo_b200.engine import conv_layer, set_option
+    x, w, scale, shift, r = _make(case, 13)
+    xc = torch.from_numpy(x).cuda()
+    rc = torch.from_numpy(r).cuda() if r is not None else None
+    want = _oracle(bf16_round(x), bf16_round(w), case[6], scale, shift, case[7],
+                   bf16_round(r) if r is not None else None)
+    try:
+        set_option('tc_resident', resident)
+        set_option('tc_halo', halo)
+        set_option('tc_staged', staged)
+        got = conv_layer(xc, w, case[6], scale, shift, case[7], 0.1, rc, 'bf16').cpu().numpy()
+    finally:
+        set_option('tc_resident', -1)
+        set_option('tc_halo', -1)
+        set_option('tc_staged', -1)
+    e = rel_err(got, want)
+    assert e < 5e-3, 'resident=%d halo=%d staged=%d rel err %.3g' % (resident, halo, staged, e)
+    assert float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 0.25))) < 1e-2
