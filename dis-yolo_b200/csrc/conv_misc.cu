@@ -88,6 +88,214 @@ conv1_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio, co
 }
 
 // ------------------------------------------------------------------------------------------
+// conv1 on the tensor cores.  K = 3*3*3 = 27 is padded to 32 (one 64-byte SWIZZLE_64B row); the A
+// operand does not exist in memory: producer warps build it on the fly (im2col in shared memory).
+//   warps 0..3   producers: each warp owns one 32-pixel segment of the 128-pixel tile; coalesced
+//                loads of its 3 x 34 x 3 fp32 patch into a warp-private smem patch (next tile's
+//                patch is prefetched into registers), then each lane packs its pixel's 27 taps to
+//                bf16 and writes its swizzled 64-byte row; fence.proxy.async + mbarrier arrive
+//   warp  4      MMA issuer: 2 x tcgen05.mma (M=128, N=32, K=16) per tile into 1 of 4 TMEM stages
+//   warp  5      TMEM allocator
+//   warps 8..11  epilogue: tcgen05.ld -> folded BN -> leaky -> bf16 -> space-to-depth (and/or P1) store
+// Tiles are 128 consecutive pixels in (n,y,x) raster order; W % 32 == 0 keeps a segment in one row.
+// ------------------------------------------------------------------------------------------
+constexpr int kC1Threads = 384;
+constexpr int kC1Stages = 4;
+
+__global__ void __launch_bounds__(kC1Threads, 1)
+conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio, const float* __restrict__ scale,
+                const float* __restrict__ shift, float alpha, int B, int H, int W,
+                __nv_bfloat16* __restrict__ out_s2d, __nv_bfloat16* __restrict__ out_same) {
+  __shared__ __align__(1024) uint8_t sA[kC1Stages][128 * 64];     // A tiles, SWIZZLE_64B rows of 64 B
+  __shared__ __align__(1024) uint8_t sB[32 * 64];                 // weights [32 cout][32 k], same layout
+  __shared__ __align__(16) float patch[4][3][104];                // warp-private input patches
+  __shared__ __align__(16) float ssc[32], ssh[32];
+  __shared__ __align__(8) uint64_t full_bar[kC1Stages], empty_bar[kC1Stages], tfull_bar[4], tempty_bar[4];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)B * H * W;
+  const int num_tiles = (int)((total + 127) / 128);
+
+  // weights -> sB (bf16, K padded with zeros), scale/shift -> smem
+  for (int i = threadIdx.x; i < 32 * 4; i += blockDim.x) {
+    const int n = i >> 2, j = i & 3;                              // row n, 16-byte chunk j (k = 8j..8j+7)
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k0 = 8 * j + 2 * e, k1 = k0 + 1;
+      const float a = k0 < 27 ? w_hwio[k0 * 32 + n] : 0.f;
+      const float b = k1 < 27 ? w_hwio[k1 * 32 + n] : 0.f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      pk[e] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(sB + n * 64 + ((j ^ ((n >> 1) & 3)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (threadIdx.x < 32) {
+    ssc[threadIdx.x] = scale[threadIdx.x];
+    ssh[threadIdx.x] = shift[threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kC1Stages; ++i) {
+      mbar_init(&full_bar[i], 4);      // one arrive per producer warp
+      mbar_init(&empty_bar[i], 1);     // tcgen05.commit
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);    // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(&tmem_base_smem, 128);
+    tmem_relinquish();
+  }
+  // generic-proxy writes of sB must be visible to the tensor core (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    // ================================ im2col producers ================================
+    float* mypatch = &patch[warp][0][0];
+    float pre[12];                                                  // next tile's patch, in flight
+    auto issue_loads = [&](int tile) {
+      const long long p0 = (long long)tile * 128 + warp * 32;       // first pixel of this warp's segment
+      const bool seg_ok = p0 < total;
+      const int x0 = (int)(p0 % W);
+      const long long t = p0 / W;
+      const int y = (int)(t % H), n = (int)(t / H);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int yy = y + r - 1;
+        const bool row_ok = seg_ok && yy >= 0 && yy < H;
+        const float* rowp = img + (((long long)n * H + yy) * W + x0 - 1) * 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = lane + 32 * i;                              // element of the 34-pixel x 3-channel row
+          const int xx = x0 - 1 + e / 3;
+          pre[r * 4 + i] = (row_ok && e < 102 && xx >= 0 && xx < W) ? __ldg(rowp + e) : 0.f;
+        }
+      }
+    };
+    int it = 0;
+    if ((int)blockIdx.x < num_tiles) issue_loads(blockIdx.x);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int stage = it % kC1Stages;
+      const uint32_t ph = (uint32_t)(it / kC1Stages) & 1u;
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (lane + 32 * i < 104) mypatch[r * 104 + lane + 32 * i] = pre[r * 4 + i];
+      __syncwarp();
+      if (tile + (int)gridDim.x < num_tiles) issue_loads(tile + gridDim.x);
+      // this lane's pixel: taps (kh,kw,c) = patch[kh][(lane+kw)*3 + c], k = (kh*3+kw)*3 + c
+      uint32_t pk[16];
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = 2 * kk + h;
+          v[h] = (k < 27) ? mypatch[(k / 9) * 104 + lane * 3 + (k % 9)] : 0.f;
+        }
+        __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+        pk[kk] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      if (lane == 0) mbar_wait(&empty_bar[stage], ph ^ 1u);          // MMA has released this stage
+      __syncwarp();
+      const int row = warp * 32 + lane;
+      uint8_t* rp = &sA[stage][row * 64];
+      const int sw = (row >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(rp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp == 4) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(32);
+      const uint64_t bdesc = umma_desc(smem_u32(sB), 512, 4);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % kC1Stages, acc = it & 3;
+        mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> 2) & 1u) ^ 1u);
+        mbar_wait(&full_bar[stage], (uint32_t)(it / kC1Stages) & 1u);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc(smem_u32(&sA[stage][0]), 512, 4);
+        umma_bf16(tmem_base + acc * 32, adesc, bdesc, idesc, 0u);
+        umma_bf16(tmem_base + acc * 32, adesc + 2, bdesc + 2, idesc, 1u);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ================================ epilogue ================================
+    const int q = warp & 3;
+    const int Hq = H / 2 + 1, Wq = W / 2 + 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 3;
+      const long long pix = (long long)tile * 128 + q * 32 + lane;
+      const bool ok = pix < total;
+      const int x = (int)(pix % W);
+      const long long t = pix / W;
+      const int y = (int)(t % H), n = (int)(t / H);
+      mbar_wait(&tfull_bar[acc], (uint32_t)(it >> 2) & 1u);
+      tc_fence_after();
+      uint32_t r0[16], r1[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 32);
+      tmem_ld16(taddr, r0);
+      tmem_ld16(taddr + 16, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);                  // accumulator is in registers now
+      if (ok) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const uint32_t a = c < 16 ? r0[c] : r1[c - 16], b = c < 16 ? r0[c + 1] : r1[c - 15];
+          float v0 = fmaf(__uint_as_float(a), ssc[c], ssh[c]);
+          float v1 = fmaf(__uint_as_float(b), ssc[c + 1], ssh[c + 1]);
+          v0 = fmaxf(alpha * v0, v0);
+          v1 = fmaxf(alpha * v1, v1);
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (out_s2d != nullptr) {
+          const long long r = ((long long)n * Hq + (y >> 1)) * Wq + (x >> 1);
+          uint4* d = reinterpret_cast<uint4*>(out_s2d + r * 128 + (((y & 1) << 1) | (x & 1)) * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            d[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+        if (out_same != nullptr) {
+          const long long r = ((long long)n * (H + 1) + y) * (W + 1) + x;
+          uint4* d = reinterpret_cast<uint4*>(out_same + r * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            d[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // layout converters (one thread per element; test / parity-tap paths, not the hot path)
 // ------------------------------------------------------------------------------------------
 __global__ void nhwc_to_p1_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int H,
@@ -223,9 +431,16 @@ conv_ref_kernel(RefConvArgs a) {
 }  // namespace
 
 int launch_conv1(const float* img, const float* w_hwio, const float* scale, const float* shift, float alpha,
-                 int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_same, cudaStream_t st) {
-  dim3 grid((W + 127) / 128, H, B);
-  conv1_kernel<<<grid, 128, 0, st>>>(img, w_hwio, scale, shift, alpha, B, H, W, out_s2d, out_same);
+                 int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_same, int use_tc, int num_sms,
+                 cudaStream_t st) {
+  if (use_tc && W % 32 == 0) {
+    const long long tiles = ((long long)B * H * W + 127) / 128;
+    const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+    conv1_tc_kernel<<<grid, kC1Threads, 0, st>>>(img, w_hwio, scale, shift, alpha, B, H, W, out_s2d, out_same);
+  } else {
+    dim3 grid((W + 127) / 128, H, B);
+    conv1_kernel<<<grid, 128, 0, st>>>(img, w_hwio, scale, shift, alpha, B, H, W, out_s2d, out_same);
+  }
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

@@ -19,7 +19,8 @@ struct RefConvArgs {
 };
 
 int launch_conv1(const float* img, const float* w_hwio, const float* scale, const float* shift, float alpha,
-                 int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_same, cudaStream_t st);
+                 int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_same, int use_tc, int num_sms,
+                 cudaStream_t st);
 int launch_nhwc_to_p1(const float* src, __nv_bfloat16* dst, int N, int H, int W, int C, int form, cudaStream_t st);
 int launch_p1_to_nhwc(const __nv_bfloat16* src, float* dst, int N, int H, int W, int C, int form, cudaStream_t st);
 int launch_planar_to_nhwc(const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st);

@@ -131,6 +131,7 @@ struct TcConvDesc {
 static int g_opt_resident = -1;     // 0: never keep weights resident, 1: whenever the slab fits
 static int g_opt_halo = -1;         // 0: never share a halo'd A box between taps, 1: whenever legal
 static int g_opt_staged = -1;       // 0: per-thread row stores, 1: smem-staged cooperative stores
+static int g_opt_conv1_tc = -1;     // 0: conv1 on CUDA cores, otherwise the tcgen05 im2col stem kernel
 
 static int pick_block_n(int cout_pad, long long rows, int num_sms) {
   static const int cands[] = {256, 128, 64, 32, 16};
@@ -528,7 +529,7 @@ static int run_network_bf16(dy_net* net, const float* images, int B, cudaStream_
   auto& L = net->L;
   note_launch();
   DY_TRY(launch_conv1(images, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S, L[1].s2d,
-                      L[1].same, st));
+                      L[1].same, g_opt_conv1_tc != 0, net->num_sms, st));
   for (int n = 2; n <= 82; ++n) DY_TRY(run_tc_plan(L[n].plan, B, net->num_sms, st));
   return DY_OK;
 }
@@ -728,6 +729,7 @@ int dy_set_option(const char* name, int32_t value) {
   if (n == "tc_resident") g_opt_resident = value;
   else if (n == "tc_halo") g_opt_halo = value;
   else if (n == "tc_staged") g_opt_staged = value;
+  else if (n == "conv1_tc") g_opt_conv1_tc = value;
   else {
     set_error("unknown option " + n);
     return DY_ERR_NOTFOUND;
@@ -854,7 +856,7 @@ int dy_forward_profile(dy_net* net, const float* images_dev, int32_t B, float* l
   cudaEventRecord(ev[0], st);
   note_launch();
   rc = launch_conv1(images_dev, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S,
-                    L[1].s2d, L[1].same, st);
+                    L[1].s2d, L[1].same, g_opt_conv1_tc != 0, net->num_sms, st);
   cudaEventRecord(ev[1], st);
   for (int n = 2; n <= 82 && rc == DY_OK; ++n) {
     rc = run_tc_plan(L[n].plan, B, net->num_sms, st);
@@ -1115,7 +1117,7 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
         (rc = talloc((void**)&d_out, p1_elems(B, H, W, cout) * 2))) { cleanup(); return rc; }
     cudaMemcpyAsync(d_w, w_host, (size_t)K * cout * 4, cudaMemcpyHostToDevice, st);
     note_launch(2);
-    rc = launch_conv1(x_dev, d_w, d_sc, d_sh, alpha, B, H, W, nullptr, d_out, st);
+    rc = launch_conv1(x_dev, d_w, d_sc, d_sh, alpha, B, H, W, nullptr, d_out, g_opt_conv1_tc != 0, num_sms, st);
     if (rc == DY_OK) rc = launch_p1_to_nhwc(d_out, out_dev, B, H, W, cout, FORM_SAME, st);
     cleanup();
     return rc;
