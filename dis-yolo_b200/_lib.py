@@ -58,6 +58,14 @@ SIGNATURES = {
     'dy_nms': (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),
     'dy_assemble_masks': (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     'dy_conv_layer': (C.c_int, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P]),
+    'dy_train_init': (C.c_int, [_P]),
+    'dy_train_param_count': (C.c_int64, [_P]),
+    'dy_train_layer_span': (C.c_int, [_P, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    'dy_train_forward': (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P]),
+    'dy_train_backward': (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    'dy_train_apply': (C.c_int, [_P, _P, _F, _F, _P]),
+    'dy_train_get_tensor': (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    'dy_get_weights': (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
     'dy_set_option': (C.c_int, [C.c_char_p, _I]),
     'dy_launch_count': (C.c_int64, [_I]),
 }

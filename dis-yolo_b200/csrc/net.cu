@@ -14,6 +14,7 @@
 #include "conv_misc.cuh"
 #include "conv_tc.cuh"
 #include "postproc.cuh"
+#include "train.cuh"
 
 namespace dy {
 
@@ -339,6 +340,15 @@ struct LayerState {
   float* f32 = nullptr;     // bf16 mode: heads (compact) / score maps (planar); fp32 mode: every layer, NHWC
   TcPlan plan;
   bool planned = false;
+  // ---- training state (fp32 engine) ----
+  bool unlocked = false, in_bwd = false, need_in_grad = false;
+  float *d_gamma = nullptr, *d_beta = nullptr, *d_mean = nullptr, *d_var = nullptr, *d_bias = nullptr;
+  float* z = nullptr;          // pre-BN conv output of this step
+  float* dy = nullptr;         // gradient w.r.t. this layer's output
+  float* wt = nullptr;         // [k*k][cout][cin] weights for dgrad
+  float *bn_a = nullptr, *bn_b = nullptr, *bmean = nullptr, *bvar = nullptr, *binvstd = nullptr;
+  double* stat = nullptr;      // [4*cout]: sum, sumsq | s1, s2
+  long long off_w = -1, off_g = -1, off_b = -1;   // offsets into the flat trainable vector
 };
 
 }  // namespace dy
@@ -367,6 +377,21 @@ struct dy_net {
   float* windows_ws = nullptr;
   float* masks_ws = nullptr;
   cudaStream_t host_stream = nullptr;
+  // ---- training ----
+  bool train_ready = false;
+  long long n_train = 0;           // number of trainable scalars
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  float* dz_scratch = nullptr;     // largest dz
+  float* dx_scratch = nullptr;     // largest concat dgrad result
+  double* loss_acc = nullptr;      // [8] obj, noobj, cls, xy, wh, mask, l2, (unused)
+  float* mask_rois = nullptr;
+  int* mask_assign = nullptr;
+  int* mask_npos = nullptr;
+  float* train_windows = nullptr;
+  float* ones_dev = nullptr;       // [1024] identity scale for "conv only" passes
+  float* zeros_dev = nullptr;
+  long long adam_step = 0;
 };
 
 namespace dy {
@@ -1158,6 +1183,368 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
   }
   cleanup();
   return rc;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Training step (fp32 engine).  Reference: sess.run([total_loss, optimizer]) --
+// train_yolo3_mask.py:146-149,216; graph yolo3_net_pos.py:52-61 (placeholders, losses), :71-107 (BN),
+// :631-860 (loss_yolo, loss_mask), :38/:61 (L2 + total), train_yolo3_mask.py:55 (Adam).
+// =============================================================================================
+namespace dy {
+
+static const float kBnDecay = 0.997f;      // yolo3_net_pos.py:74
+static const float kL2 = 1e-4f;            // yolo3_net_pos.py:38
+static const float kAdamB1 = 0.9f, kAdamB2 = 0.999f, kAdamEps = 1e-8f;
+
+static size_t out_elems(const LayerDef& d, int B) { return (size_t)B * d.H * d.H * d.cout; }
+
+static int train_init(dy_net* net) {
+  if (net->train_ready) return DY_OK;
+  DY_CHECK(net->cfg.precision == DY_PRECISION_FP32, "the training step runs on the fp32 engine in this round");
+  DY_CHECK(net->finalized, "load weights before dy_train_init");
+  auto& L = net->L;
+  const int B = net->cfg.max_batch;
+  // which layers are trainable, which take part in the backward pass
+  for (int n = 1; n <= 82; ++n) L[n].unlocked = net->cfg.lock[n - 1] == 0;
+  // a layer's output needs a gradient iff the layer or one of its ancestors is unlocked
+  for (int n = 1; n <= 82; ++n) {
+    const LayerDef& d = L[n].def;
+    bool anc = false;
+    if (d.src0 > 0) anc |= L[d.src0].in_bwd;
+    if (d.src1 > 0) anc |= L[d.src1].in_bwd;
+    if (d.res > 0) anc |= L[d.res].in_bwd;
+    L[n].in_bwd = L[n].unlocked || anc;
+    L[n].need_in_grad = anc;
+  }
+  long long off = 0;
+  size_t max_out = 0, max_in = 0;
+  for (int n = 1; n <= 82; ++n) {
+    LayerState& s = L[n];
+    const LayerDef& d = s.def;
+    const int C = d.cout;
+    // master copies of the per-channel variables on the device
+    if (d.bn) {
+      DY_TRY(dev_alloc(net, (void**)&s.d_gamma, C * 4)); DY_TRY(dev_alloc(net, (void**)&s.d_beta, C * 4));
+      DY_TRY(dev_alloc(net, (void**)&s.d_mean, C * 4));  DY_TRY(dev_alloc(net, (void**)&s.d_var, C * 4));
+      DY_CUDA(cudaMemcpy(s.d_gamma, s.gamma.data(), C * 4, cudaMemcpyHostToDevice));
+      DY_CUDA(cudaMemcpy(s.d_beta, s.beta.data(), C * 4, cudaMemcpyHostToDevice));
+      DY_CUDA(cudaMemcpy(s.d_mean, s.mean.data(), C * 4, cudaMemcpyHostToDevice));
+      DY_CUDA(cudaMemcpy(s.d_var, s.var.data(), C * 4, cudaMemcpyHostToDevice));
+    } else {
+      DY_TRY(dev_alloc(net, (void**)&s.d_bias, C * 4));
+      DY_CUDA(cudaMemcpy(s.d_bias, s.bias.data(), C * 4, cudaMemcpyHostToDevice));
+    }
+    if (!s.in_bwd) continue;
+    DY_TRY(dev_alloc(net, (void**)&s.z, out_elems(d, B) * 4));
+    DY_TRY(dev_alloc(net, (void**)&s.dy, out_elems(d, B) * 4));
+    DY_TRY(dev_alloc(net, (void**)&s.stat, (size_t)4 * C * 8));
+    DY_TRY(dev_alloc(net, (void**)&s.bn_a, C * 4)); DY_TRY(dev_alloc(net, (void**)&s.bn_b, C * 4));
+    DY_TRY(dev_alloc(net, (void**)&s.bmean, C * 4)); DY_TRY(dev_alloc(net, (void**)&s.bvar, C * 4));
+    DY_TRY(dev_alloc(net, (void**)&s.binvstd, C * 4));
+    if (s.need_in_grad) DY_TRY(dev_alloc(net, (void**)&s.wt, (size_t)s.K * C * 4));
+    if (out_elems(d, B) > max_out) max_out = out_elems(d, B);
+    const size_t in_e = (size_t)B * (d.H * d.s) * (d.H * d.s) * (d.cin0 + d.cin1);
+    if (s.need_in_grad && in_e > max_in) max_in = in_e;
+    if (s.unlocked) {
+      s.off_w = off; off += (long long)s.K * C;
+      if (d.bn) { s.off_g = off; off += C; s.off_b = off; off += C; }
+      else { s.off_b = off; off += C; }
+    }
+  }
+  net->n_train = off;
+  DY_TRY(dev_alloc(net, (void**)&net->adam_m, (size_t)off * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->adam_v, (size_t)off * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->dz_scratch, max_out * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->dx_scratch, max_in * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->loss_acc, 8 * 8));
+  DY_TRY(dev_alloc(net, (void**)&net->mask_rois, (size_t)B * 10 * 4 * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->mask_assign, (size_t)B * 10 * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->mask_npos, (size_t)B * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->train_windows, (size_t)B * 16));
+  DY_TRY(dev_alloc(net, (void**)&net->ones_dev, 1024 * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->zeros_dev, 1024 * 4));
+  {
+    std::vector<float> ones(1024, 1.f);
+    DY_CUDA(cudaMemcpy(net->ones_dev, ones.data(), 1024 * 4, cudaMemcpyHostToDevice));
+  }
+  std::vector<float> w(B * 4);
+  for (int b = 0; b < B; ++b) { w[4 * b] = 0; w[4 * b + 1] = 0; w[4 * b + 2] = 1; w[4 * b + 3] = 1; }
+  DY_CUDA(cudaMemcpy(net->train_windows, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  net->train_ready = true;
+  return DY_OK;
+}
+
+static ConvGeom geom_of(const LayerDef& d, int B) {
+  ConvGeom g;
+  g.B = B; g.Ho = g.Wo = d.H; g.Hi = g.Wi = d.H * d.s; g.cin = d.cin0 + d.cin1; g.cout = d.cout; g.k = d.k; g.s = d.s;
+  tf_same_pad(g.Hi, d.k, d.s, &g.pad_t);
+  g.pad_l = g.pad_t;
+  return g;
+}
+
+// training-mode forward of one layer: batch-stat BN for unlocked layers (yolo3_net_pos.py:88-98),
+// moving statistics for locked ones (:76-81)
+static int train_forward_layer(dy_net* net, int n, const float* images, int B, cudaStream_t st) {
+  auto& L = net->L;
+  LayerState& s = L[n];
+  const LayerDef& d = s.def;
+  RefConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src0 = d.src0 == 0 ? images : L[d.src0].f32;
+  a.src1 = d.src1 > 0 ? L[d.src1].f32 : nullptr;
+  a.w = s.d_w_f32;
+  a.Ho = a.Wo = d.H; a.Hi = a.Wi = d.H * d.s;
+  a.c0 = d.cin0; a.c1 = d.cin1; a.cout = d.cout; a.k = d.k; a.s = d.s;
+  tf_same_pad(a.Hi, d.k, d.s, &a.pad_t);
+  a.pad_l = a.pad_t;
+  a.alpha = net->cfg.alpha;
+  const float* res = d.res > 0 ? L[d.res].f32 : nullptr;
+  const long long M = (long long)B * d.H * d.H;
+  if (!s.in_bwd) {            // frozen prefix: identical to inference
+    a.scale = s.d_scale; a.shift = s.d_shift; a.residual = res; a.out = s.f32; a.act = d.bn ? 1 : 0;
+    note_launch();
+    return launch_conv_ref(a, B, st);
+  }
+  if (!d.bn) {                // biased linear conv: y = conv + bias (scale = 1)
+    a.scale = net->ones_dev; a.shift = s.d_bias; a.residual = nullptr; a.out = s.f32; a.act = 0;
+    note_launch();
+    return launch_conv_ref(a, B, st);
+  }
+  // z = conv(x) with an identity epilogue (scale 1, shift 0, no activation)
+  a.scale = net->ones_dev; a.shift = net->zeros_dev; a.residual = nullptr; a.out = s.z; a.act = 0;
+  note_launch(3);
+  DY_TRY(launch_conv_ref(a, B, st));
+  if (s.unlocked) {
+    DY_CUDA(cudaMemsetAsync(s.stat, 0, (size_t)4 * d.cout * 8, st));
+    DY_TRY(launch_bn_stats(s.z, M, d.cout, s.stat, s.stat + d.cout, st));
+    DY_TRY(launch_bn_finalize(s.stat, s.stat + d.cout, M, d.cout, s.d_gamma, s.d_beta, net->cfg.bn_eps, s.bn_a,
+                              s.bn_b, s.bmean, s.bvar, s.binvstd, st));
+  } else {
+    DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, d.cout, s.bn_a, s.bn_b, st));
+  }
+  return launch_bn_act(s.z, s.bn_a, s.bn_b, d.cout, M * d.cout, net->cfg.alpha, 1, res, s.f32, st);
+}
+
+static int train_backward_layer(dy_net* net, int n, int B, float* grad_flat, cudaStream_t st) {
+  auto& L = net->L;
+  LayerState& s = L[n];
+  const LayerDef& d = s.def;
+  if (!s.in_bwd) return DY_OK;
+  const long long M = (long long)B * d.H * d.H;
+  const int C = d.cout;
+  float* dz = net->dz_scratch;
+  // residual shortcut: y = leaky(bn(conv)) + shortcut  ->  d shortcut += dy
+  if (d.res > 0 && L[d.res].in_bwd) { note_launch(); DY_TRY(launch_add(L[d.res].dy, s.dy, M * C, st)); }
+  double* s1 = s.stat + 2 * C;
+  double* s2 = s.stat + 3 * C;
+  if (d.bn) {
+    if (s.unlocked) {
+      DY_CUDA(cudaMemsetAsync(s1, 0, (size_t)2 * C * 8, st));
+      DY_TRY(launch_bn_bwd_reduce(s.dy, s.z, s.bn_a, s.bn_b, s.bmean, s.binvstd, net->cfg.alpha, 1, M, C, s1, s2, st));
+      DY_TRY(launch_copy_stats_to_grads(s1, s2, C, grad_flat + s.off_g, grad_flat + s.off_b, st));
+      DY_TRY(launch_bn_bwd_apply(s.dy, s.z, s.bn_a, s.bn_b, s.bmean, s.binvstd, s.d_gamma, s1, s2, net->cfg.alpha, 1,
+                                 0, M, C, dz, st));
+    } else {
+      DY_TRY(launch_bn_bwd_apply(s.dy, s.z, s.bn_a, s.bn_b, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 net->cfg.alpha, 1, 1, M, C, dz, st));
+    }
+    note_launch(3);
+  } else {
+    dz = s.dy;       // dz = dy
+    if (s.unlocked) {
+      DY_CUDA(cudaMemsetAsync(s1, 0, (size_t)C * 8, st));
+      DY_TRY(launch_bn_stats(s.dy, M, C, s1, nullptr, st));                       // d bias = column sums
+      DY_TRY(launch_copy_stats_to_grads(s1, s1, C, nullptr, grad_flat + s.off_b, st));
+      note_launch(2);
+    }
+  }
+  const ConvGeom g = geom_of(d, B);
+  if (s.unlocked) {
+    DY_CUDA(cudaMemsetAsync(grad_flat + s.off_w, 0, (size_t)s.K * C * 4, st));
+    const float* x0 = d.src0 == 0 ? nullptr : L[d.src0].f32;
+    DY_CHECK(x0 != nullptr, "convolutional1 cannot be trained from here (image gradient path)");
+    note_launch();
+    DY_TRY(launch_conv_wgrad(x0, d.cin0, d.src1 > 0 ? L[d.src1].f32 : nullptr, d.cin1, dz, grad_flat + s.off_w, g,
+                             net->num_sms, st));
+  }
+  if (s.need_in_grad) {
+    note_launch(3);
+    DY_TRY(launch_weight_transpose(s.d_w_f32, s.wt, d.k * d.k, g.cin, C, st));
+    float* d0 = (d.src0 > 0 && L[d.src0].in_bwd) ? L[d.src0].dy : nullptr;
+    float* d1 = (d.src1 > 0 && L[d.src1].in_bwd) ? L[d.src1].dy : nullptr;
+    if (d.src1 == 0 && d0) {
+      DY_TRY(launch_conv_dgrad(dz, s.wt, d0, g, 1, st));                         // accumulate in place
+    } else if (d0 || d1) {
+      DY_TRY(launch_conv_dgrad(dz, s.wt, net->dx_scratch, g, 0, st));
+      DY_TRY(launch_split_accumulate(net->dx_scratch, B, g.Hi, g.Wi, d.cin0, d.cin1, d0, d1, st));
+    }
+  }
+  return DY_OK;
+}
+
+}  // namespace dy
+
+extern "C" {
+
+int dy_train_init(dy_net* net) {
+  DY_CHECK(net != nullptr, "null net");
+  DY_CUDA(cudaSetDevice(net->cfg.device));
+  return train_init(net);
+}
+
+int64_t dy_train_param_count(dy_net* net) { return (net && net->train_ready) ? net->n_train : -1; }
+
+int dy_train_layer_span(dy_net* net, int32_t layer, int64_t* offset, int64_t* count) {
+  DY_CHECK(net && net->train_ready && layer >= 1 && layer <= 82 && offset && count, "bad argument");
+  const LayerState& s = net->L[layer];
+  if (!s.unlocked) { *offset = -1; *count = 0; return DY_OK; }
+  *offset = s.off_w;
+  *count = (long long)s.K * s.def.cout + (s.def.bn ? 2 : 1) * s.def.cout;
+  return DY_OK;
+}
+
+int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const float* yolo3_dev, const float* yolo2_dev,
+                     const float* yolo1_dev, const float* true_boxes_dev, const uint8_t* true_masks_dev,
+                     const int32_t* perm_prop_dev, const int32_t* perm_gt_dev, float det_thresh, float* losses_host,
+                     void* stream) {
+  DY_CHECK(net && images_dev && yolo3_dev && yolo2_dev && yolo1_dev && true_boxes_dev && true_masks_dev &&
+               perm_prop_dev && perm_gt_dev && losses_host, "null argument");
+  DY_CHECK(net->train_ready, "dy_train_init has not been called");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto& L = net->L;
+  for (int n = 1; n <= 82; ++n) DY_TRY(train_forward_layer(net, n, images_dev, B, st));
+  for (int n = 1; n <= 82; ++n)
+    if (L[n].in_bwd) DY_CUDA(cudaMemsetAsync(L[n].dy, 0, out_elems(L[n].def, B) * 4, st));
+  DY_CUDA(cudaMemsetAsync(net->loss_acc, 0, 8 * 8, st));
+  // detection loss + gradient into the three head maps
+  YoloLossArgs ya;
+  memset(&ya, 0, sizeof(ya));
+  const int heads[3] = {75, 67, 59};
+  const float* labs[3] = {yolo3_dev, yolo2_dev, yolo1_dev};
+  for (int j = 0; j < 3; ++j) {
+    DY_CHECK(L[heads[j]].in_bwd, "detection heads must be trainable");
+    ya.pred[j] = L[heads[j]].f32; ya.label[j] = labs[j]; ya.dpred[j] = L[heads[j]].dy;
+    ya.g[j] = L[heads[j]].def.H;
+  }
+  ya.B = B; ya.net = 32 * ya.g[2];
+  memcpy(ya.anchors, net->cfg.anchors, sizeof(ya.anchors));
+  ya.true_boxes = true_boxes_dev;
+  ya.ignore_thresh = 0.5f; ya.object_scale = 2.f; ya.noobject_scale = 1.f; ya.class_scale = 1.f; ya.coord_scale = 1.f;
+  ya.loss = net->loss_acc;
+  note_launch();
+  DY_TRY(launch_yolo_loss(ya, st));
+  // proposals for the mask loss: filter_detections on the training-mode predictions (:357-359)
+  DY_TRY(run_detect(net, L[75].f32, L[67].f32, L[59].f32, B, net->train_windows, det_thresh, nullptr, nullptr, nullptr,
+                    net->det_raw_ws, net->det_box_ws, net->det_count_ws, st));
+  MaskLossArgs ma;
+  memset(&ma, 0, sizeof(ma));
+  DY_CHECK(L[82].in_bwd, "the mask subnet must be trainable");
+  ma.det = net->det_raw_ws; ma.true_boxes = true_boxes_dev; ma.true_masks = true_masks_dev;
+  ma.perm_prop = perm_prop_dev; ma.perm_gt = perm_gt_dev; ma.mask_pos = L[82].f32; ma.dmask = L[82].dy;
+  ma.B = B; ma.max_det = net->cfg.max_detection; ma.S = net->S / 2; ma.H = net->S; ma.k = net->cfg.k_map;
+  ma.mask_scale = 5.f; ma.iou_thresh = 0.5f;
+  ma.rois = net->mask_rois; ma.assign = net->mask_assign; ma.npos = net->mask_npos;
+  ma.loss = net->loss_acc + 5;
+  note_launch(2);
+  DY_TRY(launch_mask_loss(ma, st));
+  // L2 regulariser over unlocked weights and biases (:38,118-123,138-140)
+  for (int n = 1; n <= 82; ++n) {
+    if (!L[n].unlocked) continue;
+    note_launch();
+    DY_TRY(launch_sumsq(L[n].d_w_f32, (long long)L[n].K * L[n].def.cout, 0.5 * kL2, net->loss_acc + 6, st));
+    if (!L[n].def.bn) DY_TRY(launch_sumsq(L[n].d_bias, L[n].def.cout, 0.5 * kL2, net->loss_acc + 6, st));
+  }
+  double acc[8];
+  DY_CUDA(cudaMemcpyAsync(acc, net->loss_acc, 8 * 8, cudaMemcpyDeviceToHost, st));
+  DY_CUDA(cudaStreamSynchronize(st));
+  // losses_host: total, obj, noobj, cls, xy, wh, mask, l2
+  double total = 0;
+  for (int i = 0; i < 7; ++i) total += acc[i];
+  losses_host[0] = (float)total;
+  for (int i = 0; i < 7; ++i) losses_host[1 + i] = (float)acc[i];
+  return DY_OK;
+}
+
+int dy_train_backward(dy_net* net, int32_t B, int32_t layer_hi, int32_t layer_lo, float* grad_flat_dev, void* stream) {
+  DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
+  DY_CHECK(layer_lo >= 1 && layer_hi <= 82 && layer_lo <= layer_hi, "layer range");
+  for (int n = layer_hi; n >= layer_lo; --n) DY_TRY(train_backward_layer(net, n, B, grad_flat_dev, (cudaStream_t)stream));
+  return DY_OK;
+}
+
+int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad_scale, void* stream) {
+  DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto& L = net->L;
+  net->adam_step += 1;
+  const double t = (double)net->adam_step;
+  const float lr_t = (float)(lr * sqrt(1.0 - pow((double)kAdamB2, t)) / (1.0 - pow((double)kAdamB1, t)));
+  for (int n = 1; n <= 82; ++n) {
+    LayerState& s = L[n];
+    if (!s.unlocked) continue;
+    const int C = s.def.cout;
+    const long long nw = (long long)s.K * C;
+    note_launch(3);
+    DY_TRY(launch_adam(s.d_w_f32, grad_flat_dev + s.off_w, net->adam_m + s.off_w, net->adam_v + s.off_w, nw, lr_t,
+                       kAdamB1, kAdamB2, kAdamEps, kL2, grad_scale, st));
+    if (s.def.bn) {
+      DY_TRY(launch_adam(s.d_gamma, grad_flat_dev + s.off_g, net->adam_m + s.off_g, net->adam_v + s.off_g, C, lr_t,
+                         kAdamB1, kAdamB2, kAdamEps, 0.f, grad_scale, st));
+      DY_TRY(launch_adam(s.d_beta, grad_flat_dev + s.off_b, net->adam_m + s.off_b, net->adam_v + s.off_b, C, lr_t,
+                         kAdamB1, kAdamB2, kAdamEps, 0.f, grad_scale, st));
+      DY_TRY(launch_moving_update(s.d_mean, s.d_var, s.bmean, s.bvar, C, kBnDecay, st));
+      DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, C, s.d_scale, s.d_shift, st));
+    } else {
+      DY_TRY(launch_adam(s.d_bias, grad_flat_dev + s.off_b, net->adam_m + s.off_b, net->adam_v + s.off_b, C, lr_t,
+                         kAdamB1, kAdamB2, kAdamEps, kL2, grad_scale, st));
+      DY_CUDA(cudaMemcpyAsync(s.d_shift, s.d_bias, C * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return DY_OK;
+}
+
+int dy_train_get_tensor(dy_net* net, int32_t layer, int32_t which, int32_t B, float* out_dev, void* stream) {
+  DY_CHECK(net && net->train_ready && out_dev && layer >= 1 && layer <= 82, "bad argument");
+  const LayerState& s = net->L[layer];
+  const float* src = which == 0 ? s.z : s.dy;
+  DY_CHECK(src != nullptr, "layer does not take part in the backward pass");
+  DY_CUDA(cudaMemcpyAsync(out_dev, src, out_elems(s.def, B) * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return DY_OK;
+}
+
+int dy_get_weights(dy_net* net, const char* tf_name, float* host, int64_t capacity) {
+  DY_CHECK(net && tf_name && host, "null argument");
+  std::string name(tf_name);
+  const std::string prefix = "yolo/convolutional";
+  DY_CHECK(name.compare(0, prefix.size(), prefix) == 0, "unknown variable");
+  size_t p = prefix.size();
+  int n = 0;
+  while (p < name.size() && name[p] >= '0' && name[p] <= '9') n = n * 10 + (name[p++] - '0');
+  DY_CHECK(n >= 1 && n <= 82 && p < name.size() && name[p] == '/', "unknown variable");
+  const std::string what = name.substr(p + 1);
+  LayerState& s = net->L[n];
+  const int C = s.def.cout;
+  const float* src = nullptr;
+  long long cnt = C;
+  std::vector<float>* hostcopy = nullptr;
+  if (what == "weights") { src = s.d_w_f32; cnt = (long long)s.K * C; hostcopy = &s.w; }
+  else if (what == "biases") { src = s.d_bias; hostcopy = &s.bias; }
+  else if (what == "BatchNorm/gamma") { src = s.d_gamma; hostcopy = &s.gamma; }
+  else if (what == "BatchNorm/beta") { src = s.d_beta; hostcopy = &s.beta; }
+  else if (what == "BatchNorm/moving_mean") { src = s.d_mean; hostcopy = &s.mean; }
+  else if (what == "BatchNorm/moving_variance") { src = s.d_var; hostcopy = &s.var; }
+  DY_CHECK(hostcopy != nullptr, "unknown variable");
+  DY_CHECK(capacity >= cnt, "output buffer too small");
+  if (src != nullptr && net->train_ready) {
+    DY_CUDA(cudaMemcpy(host, src, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  } else {
+    DY_CHECK((long long)hostcopy->size() == cnt, "variable was never loaded");
+    memcpy(host, hostcopy->data(), (size_t)cnt * 4);
+  }
+  return DY_OK;
 }
 
 }  // extern "C"

@@ -204,6 +204,65 @@ class Engine(object):
                                             _ptr(cnt), _ptr(msk)), 'dy_forward_host')
         return raw, box, cnt, msk
 
+    # ---- training step (fp32 engine) ----------------------------------------------------------
+    def train_init(self):
+        """Allocate the training state; returns the number of trainable scalars."""
+        _lib.check(self.lib.dy_train_init(self.h), 'dy_train_init')
+        self.n_train = int(self.lib.dy_train_param_count(self.h))
+        self.grad_flat = self.torch.zeros((self.n_train,), dtype=self.torch.float32, device=self.device)
+        return self.n_train
+
+    def layer_span(self, layer):
+        off, cnt = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.dy_train_layer_span(self.h, layer, C.byref(off), C.byref(cnt)), 'dy_train_layer_span')
+        return off.value, cnt.value
+
+    def train_forward(self, images, labels, true_boxes, true_masks, perm_prop, perm_gt, det_thresh):
+        """labels = [yolo3, yolo2, yolo1] (stride 8/16/32).  Returns the 8 loss scalars
+        (total, object, noobject, class, xy, wh, mask, l2) as a numpy array."""
+        t = self.torch
+        images = self._dev(images, t.float32)
+        B = images.shape[0]
+        lab = [self._dev(np.ascontiguousarray(l, np.float32).reshape(B, -1), t.float32) for l in labels]
+        tb = self._dev(np.ascontiguousarray(true_boxes, np.float32).reshape(B, -1), t.float32)
+        tm = self._dev(np.ascontiguousarray(true_masks).astype(np.uint8), t.uint8)
+        pp = self._dev(np.ascontiguousarray(perm_prop, np.int32), t.int32)
+        pg = self._dev(np.ascontiguousarray(perm_gt, np.int32), t.int32)
+        if pp.shape != (B, self.max_detection) or pg.shape != (B, 20):
+            raise ValueError('perm_prop must be [B,max_detection], perm_gt [B,20]')
+        losses = np.zeros(8, np.float32)
+        self._train_keep = (images, lab, tb, tm, pp, pg)
+        _lib.check(self.lib.dy_train_forward(self.h, _ptr(images), B, _ptr(lab[0]), _ptr(lab[1]), _ptr(lab[2]),
+                                             _ptr(tb), _ptr(tm), _ptr(pp), _ptr(pg), float(det_thresh),
+                                             losses.ctypes.data_as(C.c_void_p), self._stream()), 'dy_train_forward')
+        self._train_B = B
+        return losses
+
+    def train_backward(self, layer_hi=82, layer_lo=1, grad=None):
+        g = self.grad_flat if grad is None else grad
+        _lib.check(self.lib.dy_train_backward(self.h, self._train_B, layer_hi, layer_lo, _ptr(g), self._stream()),
+                   'dy_train_backward')
+        return g
+
+    def train_apply(self, lr, grad_scale=1.0, grad=None):
+        g = self.grad_flat if grad is None else grad
+        _lib.check(self.lib.dy_train_apply(self.h, _ptr(g), float(lr), float(grad_scale), self._stream()),
+                   'dy_train_apply')
+
+    def train_tensor(self, layer, which='dy'):
+        """Parity tap: 'z' = pre-BN conv output, 'dy' = gradient w.r.t. the layer output (NHWC)."""
+        h, w, c = self.layer_shape(layer)
+        out = self.torch.empty((self._train_B, h, w, c), dtype=self.torch.float32, device=self.device)
+        _lib.check(self.lib.dy_train_get_tensor(self.h, layer, 0 if which == 'z' else 1, self._train_B, _ptr(out),
+                                                self._stream()), 'dy_train_get_tensor')
+        return out
+
+    def get_weights(self, name, shape):
+        out = np.zeros(int(np.prod(shape)), np.float32)
+        _lib.check(self.lib.dy_get_weights(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), out.size),
+                   'dy_get_weights')
+        return out.reshape(shape)
+
     # ---- parity taps ------------------------------------------------------------------------
     def layer_shape(self, layer):
         h, w, c = C.c_int32(), C.c_int32(), C.c_int32()

@@ -149,6 +149,38 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
                   const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,
                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step.  Replaces sess.run([net.total_loss, optimizer], feed_dict) of
+ * train_yolo3_mask.py:146-149,216 = training-mode forward (batch-statistics BatchNorm for the
+ * unlocked layers, yolo3_net_pos.py:88-98) + loss_yolo (:631-747) + loss_mask (:750-860) + L2
+ * (:38) + backward + tf.train.AdamOptimizer (train_yolo3_mask.py:55).  fp32 engine.
+ *   yolo3/2/1_dev   label maps [B,g,g,3,8] for stride 8/16/32 (net.yolo3/2/1, :52-55)
+ *   true_boxes_dev  [B,20,5] (xc,yc,w,h,class) normalised (net.true_boxes, :56)
+ *   true_masks_dev  [B,20,S,S] bool bytes (net.true_masks, :57)
+ *   perm_prop_dev   [B,max_det] int32, perm_gt_dev [B,20] int32: the permutations that stand in
+ *                   for the reference's unseeded tf.random_shuffle (:781-782)
+ *   losses_host[8]  total (incl. L2), object, noobject, class, xy, wh, mask, l2
+ * dy_train_backward runs the backward pass of layers layer_hi..layer_lo (descending) and writes
+ * their parameter gradients into grad_flat_dev (layout: dy_train_layer_span; per layer weights
+ * HWIO, then gamma, beta or biases).  Calling it in descending ranges lets the caller all-reduce
+ * finished gradient buckets on another stream while earlier layers are still in backward.
+ * dy_train_apply: g*grad_scale (+L2) -> Adam -> parameters; updates the BN moving averages
+ * (decay 0.997, :74,92-95) and refreshes the inference-mode folded weights. */
+int dy_train_init(dy_net* net);
+int64_t dy_train_param_count(dy_net* net);
+int dy_train_layer_span(dy_net* net, int32_t layer, int64_t* offset, int64_t* count);
+int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const float* yolo3_dev, const float* yolo2_dev,
+                     const float* yolo1_dev, const float* true_boxes_dev, const uint8_t* true_masks_dev,
+                     const int32_t* perm_prop_dev, const int32_t* perm_gt_dev, float det_thresh, float* losses_host,
+                     void* stream);
+int dy_train_backward(dy_net* net, int32_t B, int32_t layer_hi, int32_t layer_lo, float* grad_flat_dev, void* stream);
+int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad_scale, void* stream);
+/* Parity tap of the training step: which = 0 -> pre-BatchNorm conv output z of `layer`,
+ * which = 1 -> d total_loss / d (layer output); fp32 NHWC [B,h,w,c]. */
+int dy_train_get_tensor(dy_net* net, int32_t layer, int32_t which, int32_t B, float* out_dev, void* stream);
+/* Current value of a variable by its TF name (Saver.save counterpart, train_yolo3_mask.py:221-226). */
+int dy_get_weights(dy_net* net, const char* tf_name, float* host, int64_t capacity);
+
 /* Tuning / test overrides of the conv engine's planning heuristics; value -1 = automatic.
  *   "tc_resident": 0 never / 1 whenever it fits -- keep a CTA's weight slab resident in smem
  *   "tc_halo":     0 never / 1 whenever legal   -- one halo'd activation box feeds all 3 horizontal taps
