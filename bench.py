@@ -331,6 +331,78 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[3]: training step (forward + losses + backward + all-reduce + Adam), batch
+    16 per GPU at 576x576, data parallel.  fp32 engine in this round."""
+    import numpy as np
+    import torch
+    import disyolo_b200 as dy
+    rank, local, world = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist = None
+    B = args.batch if args.batch != PER_GPU_BATCH else 16
+    eng = dy.Engine(image_size=IMAGE, max_batch=B, precision='fp32', device=local)
+    eng.load_weights(dy.init_weights('lively', 0))
+    tr = dy.DataParallelTrainer(eng, bucket_mb=25)
+    rng = np.random.default_rng(7 + rank)
+    img = torch.from_numpy(rng.random((B, IMAGE, IMAGE, 3), dtype=np.float32)).cuda()
+    base = IMAGE // 32
+    labels = [np.zeros((B, base * m, base * m, 3, 8), np.float32) for m in (4, 2, 1)]
+    tb = np.zeros((B, 20, 5), np.float32)
+    tm = np.zeros((B, 20, IMAGE, IMAGE), np.uint8)
+    anchors = np.array([[31, 23], [62, 58], [143, 91], [213, 186], [61, 337], [194, 432], [474, 248], [551, 93],
+                        [478, 454]], np.float32)
+    for b in range(B):
+        for j in range(6):
+            w, h = rng.uniform(0.1, 0.6, 2) * IMAGE
+            xc, yc = rng.uniform(w / 2, IMAGE - w / 2), rng.uniform(h / 2, IMAGE - h / 2)
+            cls = int(rng.integers(0, 3))
+            tb[b, j] = [xc / IMAGE, yc / IMAGE, w / IMAGE, h / IMAGE, cls]
+            tm[b, j, int(yc - h / 2):int(yc + h / 2), int(xc - w / 2):int(xc + w / 2)] = 1
+            inter = np.minimum(w, anchors[:, 0]) * np.minimum(h, anchors[:, 1])
+            a = int(np.argmax(inter / (w * h + anchors[:, 0] * anchors[:, 1] - inter)))
+            lab = labels[a // 3]
+            g = lab.shape[1]
+            lab[b, int(yc * g / IMAGE), int(xc * g / IMAGE), a % 3] = [xc / IMAGE, yc / IMAGE, w / IMAGE, h / IMAGE, 1,
+                                                                      cls == 0, cls == 1, cls == 2]
+    pp = np.stack([rng.permutation(30) for _ in range(B)]).astype(np.int32)
+    pg = np.stack([rng.permutation(20) for _ in range(B)]).astype(np.int32)
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        losses = tr.step(img, labels, tb, tm, pp, pg, THRESH, 1e-4)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    eng.lib.dy_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        losses = tr.step(img, labels, tb, tm, pp, pg, THRESH, 1e-4)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps(dict(metric='training images/s @576^2 (fwd+losses+bwd+allreduce+Adam)',
+                              value=world * B * steps / (ms / 1e3), unit='images/s', n_gpus=world, steps=steps,
+                              warmup=warm, ms_per_step=ms / steps, higher_is_better=True, scaling='weak',
+                              vs_baseline=None, dtype='f32', data='synthetic',
+                              config=dict(workload='DIS-YOLO training step, batch %d/GPU at 576x576, stage 1 '
+                                                   '(layers 53-82 trainable), data parallel' % B,
+                                          trainable_params=eng.n_train, buckets=len(tr.buckets)),
+                              losses=[float(v) for v in losses], gpu_launches=int(eng.lib.dy_launch_count(0)))))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -340,6 +412,7 @@ def main():
     ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
     ap.add_argument('--latency', type=int, default=200, help='batch-1 latency iterations (0 = skip)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--workload', default='inference', choices=['inference', 'train'])
     ap.add_argument('--traffic', type=float, default=None,
                     help='dram bytes per step of the conv kernel from the committed ncu capture (profiles/)')
     args = ap.parse_args()
@@ -352,7 +425,10 @@ def main():
         rank, _, _ = dist_env()
         if rank == 0:
             g.build()
-        run_ours(args)
+        if args.workload == 'train':
+            run_train(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == '__main__':

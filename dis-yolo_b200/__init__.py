@@ -16,7 +16,8 @@ works anywhere, but constructing a net without the built library or without a GP
 from . import _lib                                    # noqa: F401
 from .engine import Engine, layer_table               # noqa: F401
 from .weights import init_weights, save_npz, load_npz, variable_names  # noqa: F401
-from .yolo.yolo3_net_pos import YOLONet, Session      # noqa: F401
+from .yolo.yolo3_net_pos import YOLONet, Session, AdamOptimizer      # noqa: F401
+from .parallel import DataParallelTrainer, plan_buckets, BucketedAllReduce   # noqa: F401
 
-__all__ = ['Engine', 'YOLONet', 'Session', 'init_weights', 'save_npz', 'load_npz',
+__all__ = ['Engine', 'YOLONet', 'Session', 'AdamOptimizer', 'DataParallelTrainer', 'plan_buckets', 'init_weights', 'save_npz', 'load_npz',
            'variable_names', 'layer_table']

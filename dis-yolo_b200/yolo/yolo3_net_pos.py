@@ -40,8 +40,22 @@ class Handle(object):
         return self is other
 
 
+class AdamOptimizer(object):
+    """tf.train.AdamOptimizer(learning_rate).minimize(net.total_loss) (train_yolo3_mask.py:55)."""
+
+    def __init__(self, learning_rate=1e-4):
+        self.learning_rate = float(learning_rate)
+
+    def minimize(self, loss, global_step=None):
+        if not isinstance(loss, Handle) or loss.name != 'total_loss':
+            raise ValueError('minimize() expects net.total_loss')
+        h = Handle('adam_minimize', 'op')
+        h.optimizer = self
+        return h
+
+
 class YOLONet(object):
-    def __init__(self, training=False, precision='bf16', device=None, lock=None):
+    def __init__(self, training=False, precision=None, device=None, lock=None):
         # 1. parameters (yolo3_net_pos.py:15-37)
         self.batchsize = cfg.BATCH_SIZE
         self.classes = cfg.CLASSES
@@ -81,6 +95,10 @@ class YOLONet(object):
         self.logits = [self.predictions, self.detections, self.mask_pos]
         self.evaluation = Handle('evaluation', 'fetch')
 
+        if precision is None:
+            precision = 'fp32' if training else 'bf16'       # the training step runs on the fp32 engine
+        if training and precision != 'fp32':
+            raise ValueError('training=True needs precision="fp32" in this release')
         dev = int(cfg.GPU) if device is None else int(device)
         self.engine = Engine(image_size=self.image_size, max_batch=int(self.batchsize), precision=precision,
                              device=dev, anchors=self.anchors, num_classes=self.num_class, k_map=self.k,
@@ -91,9 +109,12 @@ class YOLONet(object):
 class Session(object):
     """The subset of tf.Session the reference's drivers use."""
 
-    def __init__(self, net):
+    def __init__(self, net, seed=0):
         self.net = net
         self.restored = False
+        self.rng = np.random.default_rng(seed)      # stands in for the unseeded tf.random_shuffle (:781-782)
+        self.train_ready = False
+        self.last_losses = None
 
     def restore(self, weights):
         """weights: dict {tf variable name: ndarray} (what Saver.restore would read,
@@ -110,8 +131,8 @@ class Session(object):
         net, feed = self.net, (feed_dict or {})
         single = not isinstance(fetches, (list, tuple))
         flist = [fetches] if single else list(fetches)
-        if bool(feed.get(net.is_training, False)):
-            raise NotImplementedError('training-mode fetches (is_training=True) are not built yet')
+        if any(getattr(f, 'name', '') in ('total_loss', 'adam_minimize') for f in flist):
+            return self._run_train(flist, feed, single)
         images = np.ascontiguousarray(feed[net.images], np.float32)
         if images.shape[1] != net.image_size or images.shape[2] != net.image_size:
             raise ValueError('images must be [B,%d,%d,3]' % (net.image_size, net.image_size))
@@ -152,4 +173,35 @@ class Session(object):
                             eng.mask_pos(B).cpu().numpy()])
             else:
                 raise KeyError('unknown fetch %r' % (f,))
+        return out[0] if single else out
+
+    def _run_train(self, flist, feed, single):
+        """sess.run([net.total_loss, optimizer], feed_dict) (train_yolo3_mask.py:146-149,216)."""
+        net, eng = self.net, self.net.engine
+        if not net.training:
+            raise RuntimeError('YOLONet(training=True) is required for loss / optimizer fetches')
+        if not self.train_ready:
+            eng.train_init()
+            self.train_ready = True
+        images = np.ascontiguousarray(feed[net.images], np.float32)
+        B = images.shape[0]
+        tb = np.ascontiguousarray(feed[net.true_boxes], np.float32).reshape(B, -1, 5)
+        tm = np.ascontiguousarray(feed[net.true_masks]).astype(np.uint8)
+        labels = [feed[net.yolo3], feed[net.yolo2], feed[net.yolo1]]
+        thresh = float(np.asarray(feed[net.det_thresh]).reshape(-1)[0])
+        pp = np.stack([self.rng.permutation(eng.max_detection) for _ in range(B)]).astype(np.int32)
+        pg = np.stack([self.rng.permutation(20) for _ in range(B)]).astype(np.int32)
+        losses = eng.train_forward(images, labels, tb, tm, pp, pg, thresh)
+        self.last_losses = dict(zip(('total', 'object', 'noobject', 'class', 'xy', 'wh', 'mask', 'l2'),
+                                    [float(v) for v in losses]))
+        out = []
+        for f in flist:
+            if f.name == 'total_loss':
+                out.append(float(losses[0]))
+            elif f.name == 'adam_minimize':
+                eng.train_backward(82, 1)
+                eng.train_apply(f.optimizer.learning_rate, 1.0)
+                out.append(None)
+            else:
+                raise KeyError('fetch %r cannot be combined with a training fetch' % (f,))
         return out[0] if single else out
