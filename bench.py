@@ -128,7 +128,9 @@ def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
         return
+    import torch
     import disyolo_b200 as dy
+    torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: use every host core
     W = dy.init_weights('lively', 0)
     t0 = time.perf_counter()
     ips, total, cores = cpu_reference_images_per_s(args.steps, max(1, min(args.warmup, 1)), W)
@@ -300,6 +302,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
         ips, total, cores = cpu_reference_images_per_s(3, 1, W)
         cpu = dict(value=ips, unit='images/s', cores=cores, kind='port',
                    sample='3 x 1 image 576x576 through oracle.evaluate (median), %.1f s CPU wall' % total)
