@@ -47,6 +47,8 @@ SIGNATURES = {
     'dy_finalize_weights': (C.c_int, [_P]),
     'dy_forward': (C.c_int, [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P]),
     'dy_forward_host': (C.c_int, [_P, _P, _I, _P, _F, _P, _P, _P, _P]),
+    'dy_forward_host_begin': (C.c_int, [_P, _P, _I, _P, _F, _I, C.POINTER(_I)]),
+    'dy_forward_host_end': (C.c_int, [_P, _I, _P, _P, _P, _P]),
     'dy_forward_network': (C.c_int, [_P, _P, _I, _P]),
     'dy_forward_profile': (C.c_int, [_P, _P, _I, _P, _P]),
     'dy_layer_shape': (C.c_int, [_P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),

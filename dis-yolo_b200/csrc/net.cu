@@ -373,10 +373,21 @@ struct dy_net {
   float* det_raw_ws = nullptr;
   float* det_box_ws = nullptr;
   int* det_count_ws = nullptr;
-  float* images_ws = nullptr;      // device staging for dy_forward_host
-  float* windows_ws = nullptr;
-  float* masks_ws = nullptr;
-  cudaStream_t host_stream = nullptr;
+  // dy_forward_host*: two device-side slots so that the copies of one step overlap the compute of
+  // the next (H2D, compute and D2H each on their own stream)
+  struct HostSlot {
+    float* images = nullptr;
+    float* windows = nullptr;
+    float* det_raw = nullptr;
+    float* det_box = nullptr;
+    int* det_count = nullptr;
+    float* masks = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr;
+    int B = 0;
+    bool busy = false, want_masks = false;
+  } slot[2];
+  int next_slot = 0;
+  cudaStream_t h2d_stream = nullptr, comp_stream = nullptr, d2h_stream = nullptr;
   // ---- training ----
   bool train_ready = false;
   long long n_train = 0;           // number of trainable scalars
@@ -810,7 +821,12 @@ int dy_destroy(dy_net* net) {
   cudaSetDevice(net->cfg.device);
   cudaDeviceSynchronize();
   for (void* p : net->allocs) cudaFree(p);
-  if (net->host_stream) cudaStreamDestroy(net->host_stream);
+  for (auto st : {net->h2d_stream, net->comp_stream, net->d2h_stream})
+    if (st) cudaStreamDestroy(st);
+  for (auto& sl : net->slot) {
+    if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+    if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
+  }
   delete net;
   return DY_OK;
 }
@@ -929,39 +945,84 @@ int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* win
   return DY_OK;
 }
 
-int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const float* windows_host, float det_thresh,
-                    float* det_raw_host, float* det_box_host, int32_t* det_count_host, float* masks_host) {
-  DY_CHECK(net && images_host && windows_host && det_box_host && det_count_host, "null argument");
+static int host_slots_init(dy_net* net) {
+  if (net->h2d_stream) return DY_OK;
+  const int S = net->S, Sm = S / 2, md = net->cfg.max_detection, MB = net->cfg.max_batch;
+  DY_CUDA(cudaStreamCreateWithFlags(&net->h2d_stream, cudaStreamNonBlocking));
+  DY_CUDA(cudaStreamCreateWithFlags(&net->comp_stream, cudaStreamNonBlocking));
+  DY_CUDA(cudaStreamCreateWithFlags(&net->d2h_stream, cudaStreamNonBlocking));
+  for (auto& sl : net->slot) {
+    DY_TRY(dev_alloc(net, (void**)&sl.images, (size_t)MB * S * S * 3 * 4, false));
+    DY_TRY(dev_alloc(net, (void**)&sl.windows, (size_t)MB * 16, false));
+    DY_TRY(dev_alloc(net, (void**)&sl.det_raw, (size_t)MB * md * 24, false));
+    DY_TRY(dev_alloc(net, (void**)&sl.det_box, (size_t)MB * md * 24, false));
+    DY_TRY(dev_alloc(net, (void**)&sl.det_count, (size_t)MB * 4, false));
+    DY_TRY(dev_alloc(net, (void**)&sl.masks, (size_t)MB * md * Sm * Sm * 4, false));
+    DY_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
+    DY_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
+  }
+  return DY_OK;
+}
+
+int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, const float* windows_host,
+                          float det_thresh, int32_t want_masks, int32_t* ticket) {
+  DY_CHECK(net && images_host && windows_host && ticket, "null argument");
   DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
   DY_CUDA(cudaSetDevice(net->cfg.device));
-  const int S = net->S, Sm = S / 2, md = net->cfg.max_detection;
-  if (!net->host_stream) DY_CUDA(cudaStreamCreateWithFlags(&net->host_stream, cudaStreamNonBlocking));
-  if (!net->images_ws) {
-    DY_TRY(dev_alloc(net, (void**)&net->images_ws, (size_t)net->cfg.max_batch * S * S * 3 * 4, false));
-    DY_TRY(dev_alloc(net, (void**)&net->windows_ws, (size_t)net->cfg.max_batch * 4 * 4, false));
-    DY_TRY(dev_alloc(net, (void**)&net->masks_ws, (size_t)net->cfg.max_batch * md * Sm * Sm * 4, false));
-  }
-  cudaStream_t st = net->host_stream;
-  DY_CUDA(cudaMemcpyAsync(net->images_ws, images_host, (size_t)B * S * S * 3 * 4, cudaMemcpyHostToDevice, st));
-  DY_CUDA(cudaMemcpyAsync(net->windows_ws, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, st));
-  DY_TRY(dy_forward(net, net->images_ws, B, net->windows_ws, det_thresh, net->det_raw_ws, net->det_box_ws,
-                    net->det_count_ws, masks_host ? net->masks_ws : nullptr, st));
-  DY_CUDA(cudaMemcpyAsync(det_count_host, net->det_count_ws, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  DY_CUDA(cudaMemcpyAsync(det_box_host, net->det_box_ws, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
-  if (det_raw_host)
-    DY_CUDA(cudaMemcpyAsync(det_raw_host, net->det_raw_ws, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
+  DY_TRY(host_slots_init(net));
+  const int id = net->next_slot;
+  auto& sl = net->slot[id];
+  DY_CHECK(!sl.busy, "both pipeline slots are in flight: call dy_forward_host_end first");
+  const int S = net->S;
+  DY_CUDA(cudaMemcpyAsync(sl.images, images_host, (size_t)B * S * S * 3 * 4, cudaMemcpyHostToDevice, net->h2d_stream));
+  DY_CUDA(cudaMemcpyAsync(sl.windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, net->h2d_stream));
+  DY_CUDA(cudaEventRecord(sl.ev_h2d, net->h2d_stream));
+  DY_CUDA(cudaStreamWaitEvent(net->comp_stream, sl.ev_h2d, 0));
+  DY_TRY(dy_forward(net, sl.images, B, sl.windows, det_thresh, sl.det_raw, sl.det_box, sl.det_count,
+                    want_masks ? sl.masks : nullptr, net->comp_stream));
+  DY_CUDA(cudaEventRecord(sl.ev_comp, net->comp_stream));
+  sl.B = B;
+  sl.busy = true;
+  sl.want_masks = want_masks != 0;
+  net->next_slot = id ^ 1;
+  *ticket = id;
+  return DY_OK;
+}
+
+int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
+                        int32_t* det_count_host, float* masks_host) {
+  DY_CHECK(net && det_box_host && det_count_host, "null argument");
+  DY_CHECK(ticket == 0 || ticket == 1, "bad ticket");
+  auto& sl = net->slot[ticket];
+  DY_CHECK(sl.busy, "ticket is not in flight");
+  DY_CHECK(!masks_host || sl.want_masks, "masks were not requested at dy_forward_host_begin");
+  const int Sm = net->S / 2, md = net->cfg.max_detection, B = sl.B;
+  cudaStream_t st = net->d2h_stream;
+  DY_CUDA(cudaStreamWaitEvent(st, sl.ev_comp, 0));
+  DY_CUDA(cudaMemcpyAsync(det_count_host, sl.det_count, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  DY_CUDA(cudaMemcpyAsync(det_box_host, sl.det_box, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
+  if (det_raw_host) DY_CUDA(cudaMemcpyAsync(det_raw_host, sl.det_raw, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
   DY_CUDA(cudaStreamSynchronize(st));
   if (masks_host) {
     const size_t per = (size_t)Sm * Sm;
     for (int b = 0; b < B; ++b) {
       const int n = det_count_host[b];
       if (n > 0)
-        DY_CUDA(cudaMemcpyAsync(masks_host + (size_t)b * md * per, net->masks_ws + (size_t)b * md * per,
+        DY_CUDA(cudaMemcpyAsync(masks_host + (size_t)b * md * per, sl.masks + (size_t)b * md * per,
                                 (size_t)n * per * 4, cudaMemcpyDeviceToHost, st));
     }
     DY_CUDA(cudaStreamSynchronize(st));
   }
+  sl.busy = false;
   return DY_OK;
+}
+
+int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const float* windows_host, float det_thresh,
+                    float* det_raw_host, float* det_box_host, int32_t* det_count_host, float* masks_host) {
+  DY_CHECK(net && images_host && windows_host && det_box_host && det_count_host, "null argument");
+  int32_t ticket = -1;
+  DY_TRY(dy_forward_host_begin(net, images_host, B, windows_host, det_thresh, masks_host != nullptr, &ticket));
+  return dy_forward_host_end(net, ticket, det_raw_host, det_box_host, det_count_host, masks_host);
 }
 
 int dy_layer_shape(dy_net* net, int32_t layer, int32_t* h, int32_t* w, int32_t* c) {

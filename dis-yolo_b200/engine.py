@@ -204,6 +204,39 @@ class Engine(object):
                                             _ptr(cnt), _ptr(msk)), 'dy_forward_host')
         return raw, box, cnt, msk
 
+    def forward_host_begin(self, images, windows, det_thresh, want_masks=True):
+        """Pipelined form: enqueue H2D + forward of one batch, return a ticket (see dy_forward_host_begin)."""
+        t = self.torch
+        B = int(images.shape[0])
+        S = self.image_size
+
+        def stage(key, x, shape):
+            if isinstance(x, t.Tensor) and x.is_pinned() and x.dtype == t.float32 and x.is_contiguous():
+                return x
+            buf = self.pinned(key, shape, t.float32)
+            buf.copy_(x if isinstance(x, t.Tensor) else t.from_numpy(np.ascontiguousarray(x, np.float32)))
+            return buf
+        n = getattr(self, '_begin_count', 0)
+        self._begin_count = n + 1
+        img = stage('img%d' % (n & 1), images, (B, S, S, 3))
+        win = stage('win%d' % (n & 1), windows, (B, 4))
+        ticket = C.c_int32(-1)
+        _lib.check(self.lib.dy_forward_host_begin(self.h, _ptr(img), B, _ptr(win), float(det_thresh),
+                                                  int(bool(want_masks)), C.byref(ticket)), 'dy_forward_host_begin')
+        return (ticket.value, B, bool(want_masks), (img, win))
+
+    def forward_host_end(self, ticket):
+        t = self.torch
+        tid, B, want_masks, _keep = ticket
+        md, sm = self.max_detection, self.mask_size
+        raw = self.pinned('raw%d' % tid, (B, md, 6), t.float32)
+        box = self.pinned('box%d' % tid, (B, md, 6), t.float32)
+        cnt = self.pinned('cnt%d' % tid, (B,), t.int32)
+        msk = self.pinned('msk%d' % tid, (B, md, sm, sm), t.float32) if want_masks else None
+        _lib.check(self.lib.dy_forward_host_end(self.h, tid, _ptr(raw), _ptr(box), _ptr(cnt), _ptr(msk)),
+                   'dy_forward_host_end')
+        return raw, box, cnt, msk
+
     # ---- training step (fp32 engine) ----------------------------------------------------------
     def train_init(self):
         """Allocate the training state; returns the number of trainable scalars."""

@@ -97,6 +97,17 @@ int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* win
 int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const float* windows_host, float det_thresh,
                     float* det_raw_host, float* det_box_host, int32_t* det_count_host, float* masks_host);
 
+/* The pipelined form of dy_forward_host for back-to-back batches: _begin enqueues H2D + forward
+ * for one batch and returns a ticket immediately; _end performs the D2H of that batch and blocks
+ * until the host buffers are filled.  Two tickets may be in flight, so
+ *     t0 = begin(batch0); loop { t1 = begin(next); end(t0); t0 = t1; }
+ * overlaps the copies of one batch with the convolutions of the next (three streams, two device
+ * slots).  dy_forward_host == begin + end. */
+int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, const float* windows_host,
+                          float det_thresh, int32_t want_masks, int32_t* ticket);
+int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
+                        int32_t* det_count_host, float* masks_host);
+
 /* Network only (conv1..82), no decode / NMS / masks: fills the head and score-map buffers. */
 int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream);
 

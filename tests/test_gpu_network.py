@@ -129,3 +129,30 @@ def test_session_facade_matches_oracle():
     finally:
         cfg.BATCH_SIZE = 2
         cfg.IMAGE_SIZE = 576
+
+
+def test_pipelined_host_forward_matches_sync():
+    """dy_forward_host_begin/_end with two batches in flight returns exactly what the synchronous
+    dy_forward_host returns for each batch."""
+    import torch
+    import disyolo_b200 as dy
+    B, size = 2, 160
+    eng = dy.Engine(image_size=size, max_batch=B, precision='bf16')
+    eng.load_weights(O.make_weights('lively', 0))
+    batches = [_inputs(B, size, s) for s in (11, 12, 13)]
+    want = []
+    for img, win in batches:
+        raw, box, cnt, msk = eng.forward_host(img, win, 0.2)
+        want.append((raw.numpy().copy(), box.numpy().copy(), cnt.numpy().copy(),
+                     [msk[b, :cnt[b]].numpy().copy() for b in range(B)]))
+    tk = eng.forward_host_begin(batches[0][0], batches[0][1], 0.2)
+    for i in range(3):
+        nxt = eng.forward_host_begin(batches[i + 1][0], batches[i + 1][1], 0.2) if i < 2 else None
+        raw, box, cnt, msk = eng.forward_host_end(tk)
+        assert np.array_equal(raw.numpy(), want[i][0]) and np.array_equal(cnt.numpy(), want[i][2])
+        for b in range(B):
+            assert np.array_equal(msk[b, :cnt[b]].numpy(), want[i][3][b])
+        tk = nxt
+    with pytest.raises(Exception):
+        eng.forward_host_end((0, B, True, None))        # nothing in flight any more
+    eng.close()
