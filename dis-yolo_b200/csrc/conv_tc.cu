@@ -158,6 +158,38 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
   q[1] = b;
 }
 
+// TMA staged path, phase 1: 16 columns = two 16-byte chunks (index ch0, ch0+1) of a swizzled row;
+// (+ residual already in place) -> bf16 in place; pad pixels / rows beyond M become zeros because
+// the TMA store writes every row of the box
+__device__ __forceinline__ void epilogue_chunk_swz(const ConvParams& p, const uint32_t (&r)[16],
+                                                   const float* s_scale, const float* s_shift, int c0,
+                                                   bool has_res, bool valid, uint8_t* srow, int ch0, int rsw) {
+  float v[16];
+  bn_act16(p, r, s_scale, s_shift, c0, v);
+  uint4* qa = reinterpret_cast<uint4*>(srow + ((ch0 ^ rsw) << 4));
+  uint4* qb = reinterpret_cast<uint4*>(srow + (((ch0 + 1) ^ rsw) << 4));
+  if (has_res) {
+    const uint4 ra = *qa, rb = *qb;
+    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+      const float2 f = __bfloat1622float2(h);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+  uint4 a = make_uint4(0, 0, 0, 0), b = a;
+  if (valid) {
+    a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
+    a.z = pack_bf16(v[4], v[5]);   a.w = pack_bf16(v[6], v[7]);
+    b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
+    b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+  }
+  *qa = a;
+  *qb = b;
+}
+
 // destination element offset of a pixel's row in an output form (without the channel), or -1
 __device__ __forceinline__ long long dest_offset(const ConvParams& p, const OutDesc& o, const PixelInfo& px,
                                                  long long m) {
@@ -196,7 +228,7 @@ template <int KCHUNK>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
-               const __grid_constant__ ConvParams p) {
+               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ ConvParams p) {
   static_assert(KCHUNK == 64 || KCHUNK == 32, "K chunk is one 128B or 64B swizzle row");
   constexpr uint32_t kLayout = (KCHUNK == 64) ? 2u : 4u;          // SWIZZLE_128B : SWIZZLE_64B
   constexpr uint32_t kSBO = (KCHUNK == 64) ? 1024u : 512u;        // 8 rows of the swizzle atom
@@ -211,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __shared__ __align__(16) float s_scale[2][256];                 // per epilogue warpgroup
   __shared__ __align__(16) float s_shift[2][256];
   __shared__ long long s_dst[2][2][kBlockM];                      // [warpgroup][output][row] element offset / -1
+  __shared__ __align__(8) uint64_t res_full[2][2];                // [warpgroup][staging buffer] residual landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,7 +256,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));     // [resident weights][stages...]
   const uint32_t stages_off = bres_bytes;
   constexpr uint32_t kRowBytes = KCHUNK * 2;
-  const uint32_t epi_pitch = (uint32_t)p.slab * 2 + 16;                 // staging row pitch (bank-conflict pad)
+  // staging row pitch: padded for the cooperative path, dense (hardware-swizzled) for the TMA path
+  const uint32_t epi_pitch = p.tma_epi ? (uint32_t)p.slab * 2 : (uint32_t)p.slab * 2 + 16;
   const uint32_t epi_off = stages_off + (uint32_t)p.num_stages * stage_bytes;
   const int num_tiles = p.n_tiles_m * p.n_tiles_n;
   const bool has_res = p.residual != nullptr;
@@ -233,6 +267,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
     if (has_res) tma_prefetch_desc(&mapR);
+    if (p.tma_epi) tma_prefetch_desc(&mapO);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.num_stages; ++i) {
@@ -244,6 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp of the owning warpgroup
     }
     mbar_init(&bres_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i >> 1][i & 1], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -272,7 +308,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int n0 = (tile % p.n_tiles_n) * p.block_n;
         if (has_res) {
           // pull the residual tile towards L2 now; the epilogue reads it a few microseconds later
-          for (int c = 0; c < p.block_n; c += 64) tma_prefetch_2d(&mapR, n0 + c, m0);
+          const int step = p.slab ? p.slab : 64;
+          for (int c = 0; c < p.block_n; c += step) tma_prefetch_2d(&mapR, n0 + c, m0);
         }
         for (int s = 0; s < p.num_seg; ++s) {
           const ConvSeg& sg = p.seg[s];   // stays in constant param space (dynamic tap index)
@@ -353,6 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     float* my_scale = s_scale[wg];
     float* my_shift = s_shift[wg];
     int cached_n0 = -1;
+    uint32_t res_par = 0u;                              // bit b = parity of res_full[wg][b]; persists across tiles
     int it = wg;
     for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
       const int acc = wg;
@@ -406,6 +444,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             }
             if (px.valid)
               epilogue_chunk_direct(p, px, m, n0 + c0 + 16, r1, my_scale, my_shift, c0 + 16, has_res, ra1, rb1);
+          }
+        }
+      } else if (p.tma_epi) {
+        // ---------------- TMA staged path ----------------
+        // Two swizzled staging buffers per warpgroup.  The residual slab is TMA-loaded INTO the
+        // buffer (the first two slabs while the MMAs of this tile are still running), phase 1
+        // updates it in place thread-per-row (swizzle => conflict-free), then one elected thread
+        // TMA-stores the slab.  No global load/store instruction is executed for out[0].
+        const uint32_t buf_bytes = (uint32_t)kBlockM * p.slab * 2;
+        uint8_t* stg0 = smem_gen + epi_off + (size_t)wg * 2 * buf_bytes;
+        const int row = q * 32 + lane;
+        const int rsw = (p.slab == 64) ? (row & 7) : ((row >> 1) & 3);      // this row's swizzle XOR
+        const int vpr = p.slab >> 3, vsh = (p.slab == 64) ? 3 : 2;
+        const int nslab = p.block_n / p.slab;
+        const bool elected = wg_tid == 0;
+        const bool dual = p.out[1].mode != OUT_NONE;
+        if (dual) s_dst[wg][1][row] = dest_offset(p, p.out[1], px, m);
+        if (elected) {
+          bulk_wait_read<0>();                              // last tile's stores have left the buffers
+          if (has_res) {
+            for (int s2 = 0; s2 < nslab && s2 < 2; ++s2) {
+              mbar_expect_tx(&res_full[wg][s2], buf_bytes);
+              tma_load_2d(stg0 + (size_t)s2 * buf_bytes, &mapR, &res_full[wg][s2], n0 + s2 * p.slab, m0);
+            }
+          }
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        for (int sidx = 0; sidx < nslab; ++sidx) {
+          const int slab0 = sidx * p.slab;
+          const int bsel = sidx & 1;
+          uint8_t* stg = stg0 + (size_t)bsel * buf_bytes;
+          if (has_res) {
+            mbar_wait(&res_full[wg][bsel], (res_par >> bsel) & 1u);
+            res_par ^= 1u << bsel;
+          } else {
+            if (sidx >= 2 && elected) bulk_wait_read<1>();   // the store that last used this buffer is done
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          }
+          uint8_t* srow = stg + (size_t)row * epi_pitch;
+          tmem_ld16(taddr + (uint32_t)slab0, r0);
+          for (int c0 = 0; c0 < p.slab; c0 += 32) {
+            tmem_ld_wait();
+            const bool more1 = c0 + 16 < p.slab;
+            if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
+            epilogue_chunk_swz(p, r0, my_scale, my_shift, slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
+            if (more1) {
+              tmem_ld_wait();
+              if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
+              epilogue_chunk_swz(p, r1, my_scale, my_shift, slab0 + c0 + 16, has_res, px.valid, srow, (c0 + 16) >> 3,
+                                 rsw);
+            }
+          }
+          fence_proxy_async_smem();                          // generic-proxy smem writes -> async proxy (TMA)
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          if (elected) {
+            tma_store_2d(&mapO, stg, n0 + slab0, m0);
+            bulk_commit();
+          }
+          if (dual) {
+            // second destination form (space-to-depth / upsampled): cooperative vector stores
+            for (int idx = wg_tid; idx < kBlockM * vpr; idx += 128) {
+              const int rr = idx >> vsh, cj = idx & (vpr - 1);
+              const long long d1 = s_dst[wg][1][rr];
+              if (d1 < 0) continue;
+              const int sw = (p.slab == 64) ? (rr & 7) : ((rr >> 1) & 3);
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + ((cj ^ sw) << 4));
+              store_vec(p, p.out[1], d1, n0 + slab0 + cj * 8, v);
+            }
+            if (has_res && sidx + 2 < nslab) asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          }
+          if (elected && has_res && sidx + 2 < nslab) {
+            bulk_wait_read<0>();                             // this buffer's store has read it: refill
+            mbar_expect_tx(&res_full[wg][bsel], buf_bytes);
+            tma_load_2d(stg, &mapR, &res_full[wg][bsel], n0 + (sidx + 2) * p.slab, m0);
           }
         }
       } else {
@@ -484,6 +597,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (p.tma_epi && wg_tid == 0) bulk_wait_all<0>();      // stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -552,7 +666,9 @@ static size_t resident_bytes_of(int kchunk, const ConvParams& p) {
 }
 
 static size_t epilogue_bytes_of(const ConvParams& p) {
-  return p.slab ? 2 * (size_t)kBlockM * ((size_t)p.slab * 2 + 16) : 0;
+  if (!p.slab) return 0;
+  if (p.tma_epi) return 2 * 2 * (size_t)kBlockM * p.slab * 2;          // 2 warpgroups x 2 swizzled buffers
+  return 2 * (size_t)kBlockM * ((size_t)p.slab * 2 + 16);
 }
 
 size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p) {
@@ -570,7 +686,8 @@ int conv_tc_pick_stages(int kchunk, const ConvParams& p) {
 }
 
 int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                   const CUtensorMap& r, const ConvParams& p, int num_sms, cudaStream_t stream) {
+                   const CUtensorMap& r, const CUtensorMap& o, const ConvParams& p, int num_sms,
+                   cudaStream_t stream) {
   DY_CHECK(kchunk == 64 || kchunk == 32, "kchunk");
   DY_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n");
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
@@ -593,14 +710,14 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr64 = true;
     }
-    conv_tc_kernel<64><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, p);
+    conv_tc_kernel<64><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
   } else {
     static bool attr32 = false;
     if (!attr32) {
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32 = true;
     }
-    conv_tc_kernel<32><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, p);
+    conv_tc_kernel<32><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
   }
   DY_CUDA(cudaGetLastError());
   return DY_OK;

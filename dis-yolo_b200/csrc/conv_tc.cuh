@@ -66,7 +66,9 @@ struct ConvParams {
   int a_rows;      // rows per A box: 128, or kHaloRows when taps share a halo'd box
   int max_ntap;    // max seg[].ntap (sizes the per-stage weight slots when weights are streamed)
   int b_resident;  // 1: the CTA's whole [block_n x K] weight slab is loaded to smem once
-  int slab;        // epilogue staging width in columns (64 or 32); 0 = direct per-thread stores (fp32 heads)
+  int slab;        // epilogue staging width in columns (64 or 32); 0 = direct per-thread stores
+  int tma_epi;     // staged epilogue only: out[0] (P1 layout) leaves through TMA stores, the residual
+                   // arrives through TMA loads into the same swizzled staging buffers
   int tmem_cols;   // power of two >= 2*block_n, >= 32
   const float* scale;  // [n_tiles_n*block_n] folded BN scale (1 for biased convs)
   const float* shift;  // [n_tiles_n*block_n] folded BN shift / bias
@@ -87,6 +89,7 @@ int conv_tc_pick_stages(int kchunk, const ConvParams& p);
 
 // kchunk in {32, 64}
 int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
-                   const CUtensorMap& r, const ConvParams& p, int num_sms, cudaStream_t stream);
+                   const CUtensorMap& r, const CUtensorMap& o, const ConvParams& p, int num_sms,
+                   cudaStream_t stream);
 
 }  // namespace dy

@@ -108,7 +108,7 @@ static void tf_same_pad(int in, int k, int s, int* before) {
 // ---------------------------------------------------------------------------------------------
 struct TcPlan {
   int kchunk = 64;
-  CUtensorMap a0, a1, b, r;
+  CUtensorMap a0, a1, b, r, o;
   ConvParams p;
 };
 
@@ -132,6 +132,7 @@ struct TcConvDesc {
 static int g_opt_resident = -1;     // 0: never keep weights resident, 1: whenever the slab fits
 static int g_opt_halo = -1;         // 0: never share a halo'd A box between taps, 1: whenever legal
 static int g_opt_staged = -1;       // 0: per-thread row stores, 1: smem-staged cooperative stores
+static int g_opt_tma_epi = -1;      // 0: cooperative staged epilogue, 1: TMA store / TMA residual staged epilogue
 static int g_opt_conv1_tc = -1;     // 0: conv1 on CUDA cores, otherwise the tcgen05 im2col stem kernel
 
 static int pick_block_n(int cout_pad, long long rows, int num_sms) {
@@ -171,7 +172,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   //   resident : the CTA's whole weight slab lives in smem (only when all of N fits: <= 80 KB)
   //   halo     : 3x3 -- one 136-row activation box per kernel row feeds the 3 horizontal taps
   //   staged   : epilogue goes through smem for coalesced residual reads / output stores
-  bool resident = false, halo = false, staged = false;
+  bool resident = false, halo = false, staged = false, tma = false;
   int block_n = pick_block_n(d.cout_pad, rows_max, num_sms);
   const bool enough_work = m_tiles >= num_sms;
   const bool fits = d.cout_pad <= 256 && (size_t)d.cout_pad * K * 2 <= kResidentSlabMax;
@@ -181,22 +182,23 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (enough_work) {
     if (d.k == 1) {
       resident = fits;
-      staged = up2;
+      if (d.cin1 == 0) staged = tma = d.cout_pad >= 64;        // bottleneck 1x1s: TMA-store epilogue
+      else staged = tma = d.cout_pad == 64;                    // 1x1 over concat: only the thin one gains
+      if (up2) staged = true;
     } else if (d.s == 1) {
       if (fits) {
-        resident = halo = true;
-        staged = has_res || dual;
+        resident = halo = staged = tma = true;
       } else if (d.cout_pad <= 128) {
-        halo = true;
-        staged = has_res || dual;
+        halo = staged = tma = true;
       } else if (d.cout_pad == 256) {
-        halo = staged = has_res;
+        staged = tma = true;                                    // N=256 tile, 3 stages + 64 KB staging
       } else {
-        staged = true;
+        staged = true;                                          // MMA bound: keep 4 stages, small staging
+        tma = has_res && d.cout_pad == 512;
       }
     } else {
       if (fits) resident = halo = true;
-      else if (d.cout_pad <= 128) halo = true;
+      else if (d.cout_pad <= 128) halo = staged = tma = true;
     }
   } else {
     staged = up2;
@@ -206,6 +208,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (g_opt_halo == 0) halo = false;
   if (g_opt_halo == 1 && d.k == 3) halo = true;
   if (g_opt_staged >= 0) staged = g_opt_staged != 0;
+  if (g_opt_tma_epi >= 0) tma = g_opt_tma_epi != 0;
   if (resident) block_n = d.cout_pad;
   if (halo && !resident) {
     // three streamed weight chunks per stage: keep a stage <= ~64 KB so that >= 3 stages fit
@@ -284,6 +287,8 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   const bool bf16_out = d.out[0].mode == OUT_SAME || d.out[0].mode == OUT_S2D || d.out[0].mode == OUT_UP2;
   if (!bf16_out || p.block_n % 32 != 0) staged = false;
   p.slab = !staged ? 0 : (p.block_n % 64 == 0 && p.block_n <= 128 ? 64 : 32);
+  p.tma_epi = (staged && tma && d.out[0].mode == OUT_SAME) ? 1 : 0;
+  if (p.tma_epi && p.block_n % 64 == 0) p.slab = 64;
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
   p.num_stages = conv_tc_pick_stages(kchunk, p);
   DY_CHECK(p.num_stages >= 2, "no room for a shared-memory pipeline");
@@ -295,11 +300,17 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
     plan->a1 = plan->a0;
   }
   DY_TRY(make_tmap_2d(&plan->b, d.wpk, d.cout_pad, K, K, kchunk, p.block_n));
+  const int rbox = p.slab ? p.slab : 64;
   if (d.residual != nullptr) {
     DY_CHECK(d.cout % 64 == 0 && p.block_n % 64 == 0, "residual layers need cout % 64 == 0");
-    DY_TRY(make_tmap_2d(&plan->r, d.residual, rows_max, d.cout, d.cout, 64, kBlockM));   // L2 prefetch only
+    DY_TRY(make_tmap_2d(&plan->r, d.residual, rows_max, d.cout, d.cout, rbox, kBlockM));  // L2 prefetch / TMA load
   } else {
     plan->r = plan->a0;
+  }
+  if (p.tma_epi) {
+    DY_TRY(make_tmap_2d(&plan->o, d.out[0].ptr, rows_max, d.cout, d.out[0].ld, p.slab, kBlockM));
+  } else {
+    plan->o = plan->a0;
   }
   return DY_OK;
 }
@@ -311,7 +322,7 @@ static int run_tc_plan(TcPlan& plan, int B, int num_sms, cudaStream_t st) {
   p.M = (int)M;
   p.n_tiles_m = (int)((M + kBlockM - 1) / kBlockM);
   note_launch();
-  return launch_conv_tc(plan.kchunk, plan.a0, plan.a1, plan.b, plan.r, p, num_sms, st);
+  return launch_conv_tc(plan.kchunk, plan.a0, plan.a1, plan.b, plan.r, plan.o, p, num_sms, st);
 }
 
 // pack HWIO fp32 weights -> [cout_pad][K] bf16 (K index = (kh*k+kw)*cin + ci, zero rows beyond cout)
@@ -765,6 +776,7 @@ int dy_set_option(const char* name, int32_t value) {
   if (n == "tc_resident") g_opt_resident = value;
   else if (n == "tc_halo") g_opt_halo = value;
   else if (n == "tc_staged") g_opt_staged = value;
+  else if (n == "tc_tma_epi") g_opt_tma_epi = value;
   else if (n == "conv1_tc") g_opt_conv1_tc = value;
   else {
     set_error("unknown option " + n);
