@@ -5,6 +5,7 @@
 //   * conv_ref: plain fp32 direct convolution = the FP32 verification mode of the network
 //     (north_star: "within 1e-4 in a TF32/FP32-accumulate verification mode").
 #include "conv_misc.cuh"
+#include "conv_tc.cuh"
 
 namespace dy {
 
@@ -100,24 +101,29 @@ conv1_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio, co
 // Tiles are 128 consecutive pixels in (n,y,x) raster order; W % 32 == 0 keeps a segment in one row.
 // ------------------------------------------------------------------------------------------
 constexpr int kC1Threads = 384;
-constexpr int kC1Stages = 4;
+constexpr int kC1Stages = 3;
+constexpr int kPatchW = 112;                 // pixels x0-4 .. x0+32 (37 x 3 = 111 floats): the TMA box must start 16-byte aligned
+constexpr int kPatchLead = 4;                // leading pixels before x0 inside the patch
 
+// v2: the fp32 patches arrive by TMA (3-D map [N][H][W*3], out-of-bounds = zero padding for free),
+// double buffered per producer warp; the space-to-depth output leaves through per-warp TMA stores
+// (each 32-pixel segment is 16 pixel pairs x 128 contiguous bytes in the s2d tensor).
 __global__ void __launch_bounds__(kC1Threads, 1)
-conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio, const float* __restrict__ scale,
-                const float* __restrict__ shift, float alpha, int B, int H, int W,
-                __nv_bfloat16* __restrict__ out_s2d, __nv_bfloat16* __restrict__ out_same) {
+conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constant__ CUtensorMap mapOut,
+                const float* __restrict__ w_hwio, const float* __restrict__ scale, const float* __restrict__ shift,
+                float alpha, int B, int H, int W, __nv_bfloat16* __restrict__ out_same) {
   __shared__ __align__(1024) uint8_t sA[kC1Stages][128 * 64];     // A tiles, SWIZZLE_64B rows of 64 B
   __shared__ __align__(1024) uint8_t sB[32 * 64];                 // weights [32 cout][32 k], same layout
-  __shared__ __align__(16) float patch[4][3][104];                // warp-private input patches
-  __shared__ __align__(16) float ssc[32], ssh[32];
+  __shared__ __align__(1024) uint8_t sOut[4][2048];               // per epilogue warp: 16 pairs x 128 B, SWIZZLE_128B
+  __shared__ __align__(128) float patch[4][2][3 * kPatchW + 16];  // per producer warp, double buffered (1408 B each)
   __shared__ __align__(8) uint64_t full_bar[kC1Stages], empty_bar[kC1Stages], tfull_bar[4], tempty_bar[4];
+  __shared__ __align__(8) uint64_t patch_bar[4][2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)B * H * W;
   const int num_tiles = (int)((total + 127) / 128);
 
-  // weights -> sB (bf16, K padded with zeros), scale/shift -> smem
   for (int i = threadIdx.x; i < 32 * 4; i += blockDim.x) {
     const int n = i >> 2, j = i & 3;                              // row n, 16-byte chunk j (k = 8j..8j+7)
     uint32_t pk[4];
@@ -131,11 +137,9 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
     }
     *reinterpret_cast<uint4*>(sB + n * 64 + ((j ^ ((n >> 1) & 3)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-  if (threadIdx.x < 32) {
-    ssc[threadIdx.x] = scale[threadIdx.x];
-    ssh[threadIdx.x] = shift[threadIdx.x];
-  }
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapImg);
+    tma_prefetch_desc(&mapOut);
     for (int i = 0; i < kC1Stages; ++i) {
       mbar_init(&full_bar[i], 4);      // one arrive per producer warp
       mbar_init(&empty_bar[i], 1);     // tcgen05.commit
@@ -143,6 +147,8 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);    // one arrive per epilogue warp
+      mbar_init(&patch_bar[i][0], 1);
+      mbar_init(&patch_bar[i][1], 1);
     }
     fence_mbar_init();
   }
@@ -150,8 +156,7 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
     tmem_alloc(&tmem_base_smem, 128);
     tmem_relinquish();
   }
-  // generic-proxy writes of sB must be visible to the tensor core (async proxy)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_proxy_async_smem();            // generic-proxy writes of sB -> tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -159,41 +164,23 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
 
   if (warp < 4) {
     // ================================ im2col producers ================================
-    float* mypatch = &patch[warp][0][0];
-    float pre[12];                                                  // next tile's patch, in flight
-    auto issue_loads = [&](int tile) {
-      const long long p0 = (long long)tile * 128 + warp * 32;       // first pixel of this warp's segment
-      const bool seg_ok = p0 < total;
+    auto issue_patch = [&](int tile, int buf) {                    // lane 0 only
+      const long long p0 = (long long)tile * 128 + warp * 32;
       const int x0 = (int)(p0 % W);
       const long long t = p0 / W;
-      const int y = (int)(t % H), n = (int)(t / H);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int yy = y + r - 1;
-        const bool row_ok = seg_ok && yy >= 0 && yy < H;
-        const float* rowp = img + (((long long)n * H + yy) * W + x0 - 1) * 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int e = lane + 32 * i;                              // element of the 34-pixel x 3-channel row
-          const int xx = x0 - 1 + e / 3;
-          pre[r * 4 + i] = (row_ok && e < 102 && xx >= 0 && xx < W) ? __ldg(rowp + e) : 0.f;
-        }
-      }
+      const int y = (int)(t % H), n = (int)(t / H);                 // n >= B for segments past the end: zero fill
+      mbar_expect_tx(&patch_bar[warp][buf], 3 * kPatchW * 4);
+      tma_load_3d(&patch[warp][buf][0], &mapImg, &patch_bar[warp][buf], (x0 - kPatchLead) * 3, y - 1, n);
     };
     int it = 0;
-    if ((int)blockIdx.x < num_tiles) issue_loads(blockIdx.x);
+    if (lane == 0 && (int)blockIdx.x < num_tiles) issue_patch(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int stage = it % kC1Stages;
+      const int stage = it % kC1Stages, buf = it & 1;
       const uint32_t ph = (uint32_t)(it / kC1Stages) & 1u;
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (lane + 32 * i < 104) mypatch[r * 104 + lane + 32 * i] = pre[r * 4 + i];
-      __syncwarp();
-      if (tile + (int)gridDim.x < num_tiles) issue_loads(tile + gridDim.x);
-      // this lane's pixel: taps (kh,kw,c) = patch[kh][(lane+kw)*3 + c], k = (kh*3+kw)*3 + c
+      if (lane == 0 && tile + (int)gridDim.x < num_tiles) issue_patch(tile + gridDim.x, buf ^ 1);
+      mbar_wait(&patch_bar[warp][buf], (uint32_t)(it >> 1) & 1u);
+      const float* mp = &patch[warp][buf][0];
+      // this lane's pixel: tap (kh,kw,c) = patch[kh][(lane + kw - 1 + kPatchLead)*3 + c], k = (kh*3+kw)*3 + c
       uint32_t pk[16];
 #pragma unroll
       for (int kk = 0; kk < 16; ++kk) {
@@ -201,20 +188,20 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int k = 2 * kk + h;
-          v[h] = (k < 27) ? mypatch[(k / 9) * 104 + lane * 3 + (k % 9)] : 0.f;
+          v[h] = (k < 27) ? mp[(k / 9) * kPatchW + (lane + kPatchLead - 1) * 3 + (k % 9)] : 0.f;
         }
         __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
         pk[kk] = *reinterpret_cast<uint32_t*>(&hh);
       }
       if (lane == 0) mbar_wait(&empty_bar[stage], ph ^ 1u);          // MMA has released this stage
-      __syncwarp();
+      __syncwarp();                                                  // also: every lane is done reading the patch
       const int row = warp * 32 + lane;
       uint8_t* rp = &sA[stage][row * 64];
       const int sw = (row >> 1) & 3;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(rp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
@@ -240,13 +227,21 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
     // ================================ epilogue ================================
     const int q = warp & 3;
     const int Hq = H / 2 + 1, Wq = W / 2 + 1;
+    float sc[32], sh[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      sc[c] = __ldg(scale + c);
+      sh[c] = __ldg(shift + c);
+    }
+    uint8_t* so = &sOut[q][0];
+    const bool use_tma = out_same == nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 3;
-      const long long pix = (long long)tile * 128 + q * 32 + lane;
-      const bool ok = pix < total;
-      const int x = (int)(pix % W);
-      const long long t = pix / W;
+      const long long p0 = (long long)tile * 128 + q * 32;           // first pixel of this warp's segment
+      const bool seg_ok = p0 < total;                                // W % 32 == 0: all 32 pixels or none
+      const int x0 = (int)(p0 % W);
+      const long long t = p0 / W;
       const int y = (int)(t % H), n = (int)(t / H);
       mbar_wait(&tfull_bar[acc], (uint32_t)(it >> 2) & 1u);
       tc_fence_after();
@@ -258,34 +253,44 @@ conv1_tc_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);                  // accumulator is in registers now
-      if (ok) {
-        uint32_t packed[16];
+      if (!seg_ok) continue;
+      uint32_t packed[16];
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const uint32_t a = c < 16 ? r0[c] : r1[c - 16], b = c < 16 ? r0[c + 1] : r1[c - 15];
-          float v0 = fmaf(__uint_as_float(a), ssc[c], ssh[c]);
-          float v1 = fmaf(__uint_as_float(b), ssc[c + 1], ssh[c + 1]);
-          v0 = fmaxf(alpha * v0, v0);
-          v1 = fmaxf(alpha * v1, v1);
-          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        if (out_s2d != nullptr) {
-          const long long r = ((long long)n * Hq + (y >> 1)) * Wq + (x >> 1);
-          uint4* d = reinterpret_cast<uint4*>(out_s2d + r * 128 + (((y & 1) << 1) | (x & 1)) * 32);
+      for (int c = 0; c < 32; c += 2) {
+        const uint32_t a = c < 16 ? r0[c] : r1[c - 16], b = c < 16 ? r0[c + 1] : r1[c - 15];
+        float v0 = fmaf(__uint_as_float(a), sc[c], sh[c]);
+        float v1 = fmaf(__uint_as_float(b), sc[c + 1], sh[c + 1]);
+        v0 = fmaxf(alpha * v0, v0);
+        v1 = fmaxf(alpha * v1, v1);
+        __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (use_tma) {
+        // pixel pair (lane>>1) = one 128-byte row of the s2d tensor; SWIZZLE_128B chunk = c ^ (pair & 7)
+        if (lane == 0) bulk_wait_read<0>();                          // previous tile's store has read sOut
+        __syncwarp();
+        const int pair = lane >> 1, half = lane & 1;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            d[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(so + pair * 128 + (((half * 4 + j) ^ (pair & 7)) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const long long r = ((long long)n * Hq + (y >> 1)) * Wq + (x0 >> 1);
+          tma_store_2d(&mapOut, so, (y & 1) * 64, (int)r);
+          bulk_commit();
         }
-        if (out_same != nullptr) {
-          const long long r = ((long long)n * (H + 1) + y) * (W + 1) + x;
-          uint4* d = reinterpret_cast<uint4*>(out_same + r * 32);
+      } else {
+        const int x = x0 + lane;
+        const long long r = ((long long)n * (H + 1) + y) * (W + 1) + x;
+        uint4* d = reinterpret_cast<uint4*>(out_same + r * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            d[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-        }
+        for (int i = 0; i < 4; ++i)
+          d[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
       }
     }
+    if (use_tma && lane == 0) bulk_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -433,10 +438,18 @@ conv_ref_kernel(RefConvArgs a) {
 int launch_conv1(const float* img, const float* w_hwio, const float* scale, const float* shift, float alpha,
                  int B, int H, int W, __nv_bfloat16* out_s2d, __nv_bfloat16* out_same, int use_tc, int num_sms,
                  cudaStream_t st) {
-  if (use_tc && W % 32 == 0) {
+  if (use_tc && W % 32 == 0 && (out_s2d == nullptr) != (out_same == nullptr)) {
     const long long tiles = ((long long)B * H * W + 127) / 128;
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    conv1_tc_kernel<<<grid, kC1Threads, 0, st>>>(img, w_hwio, scale, shift, alpha, B, H, W, out_s2d, out_same);
+    CUtensorMap mimg, mout;
+    DY_TRY(make_tmap_image_f32(&mimg, img, B, H, W, kPatchW, 3));
+    if (out_s2d != nullptr) {
+      const long long rows = (long long)B * (H / 2 + 1) * (W / 2 + 1);
+      DY_TRY(make_tmap_2d(&mout, out_s2d, rows, 128, 128, 64, 16));
+    } else {
+      mout = mimg;
+    }
+    conv1_tc_kernel<<<grid, kC1Threads, 0, st>>>(mimg, mout, w_hwio, scale, shift, alpha, B, H, W, out_same);
   } else {
     dim3 grid((W + 127) / 128, H, B);
     conv1_kernel<<<grid, 128, 0, st>>>(img, w_hwio, scale, shift, alpha, B, H, W, out_s2d, out_same);

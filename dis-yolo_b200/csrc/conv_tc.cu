@@ -400,12 +400,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const long long m = (long long)m0 + q * 32 + lane;
       PixelInfo px;
       {
-        int x = (int)(m % Wp);
-        long long t = m / Wp;
-        px.x = x;
-        px.y = (int)(t % Hp);
-        px.n = (int)(t / Hp);
-        px.valid = (m < p.M) && (x < p.W) && (px.y < p.H);
+        // 32-bit unsigned arithmetic (M < 2^31 is checked on the host): two cheap divisions per tile
+        const uint32_t mu = (uint32_t)m;
+        const uint32_t t = mu / (uint32_t)Wp;
+        px.x = (int)(mu - t * (uint32_t)Wp);
+        px.n = (int)(t / (uint32_t)Hp);
+        px.y = (int)(t - (uint32_t)px.n * (uint32_t)Hp);
+        px.valid = (m < p.M) && (px.x < p.W) && (px.y < p.H);
       }
       if (n0 != cached_n0) {
         // (re)stage this N tile's folded BN scale/shift; 128 threads of the warpgroup only
@@ -669,6 +670,28 @@ static size_t epilogue_bytes_of(const ConvParams& p) {
   if (!p.slab) return 0;
   if (p.tma_epi) return 2 * 2 * (size_t)kBlockM * p.slab * 2;          // 2 warpgroups x 2 swizzled buffers
   return 2 * (size_t)kBlockM * ((size_t)p.slab * 2 + 16);
+}
+
+int make_tmap_image_f32(CUtensorMap* out, const float* base, int N, int H, int W, int box_w_elems, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return DY_ERR_CUDA;
+  }
+  DY_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "image base must be 16B aligned");
+  DY_CHECK(((long long)W * 3 * 4) % 16 == 0 && (box_w_elems * 4) % 16 == 0 && box_w_elems <= 256, "image row geometry");
+  cuuint64_t gdim[3] = {(cuuint64_t)W * 3, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[2] = {(cuuint64_t)W * 3 * 4, (cuuint64_t)H * W * 3 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_w_elems, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (image) failed with CUresult " + std::to_string((int)r));
+    return DY_ERR_CUDA;
+  }
+  return DY_OK;
 }
 
 size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p) {

@@ -84,6 +84,9 @@ struct ConvParams {
 int make_tmap_2d(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld_elems,
                  int box_cols, int box_rows);
 
+// 3-D fp32 tensor map over an NHWC RGB image batch viewed as [N][H][W*3]; out-of-bounds reads give 0
+int make_tmap_image_f32(CUtensorMap* out, const float* base, int N, int H, int W, int box_w_elems, int box_rows);
+
 size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p);
 int conv_tc_pick_stages(int kchunk, const ConvParams& p);
 

@@ -327,55 +327,59 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
 // bin (by,bx) of box d, sigmoid(0)=0.5 outside the box.  One thread = 4 consecutive x (float4
 // store); planar score maps make the gather a coalesced row read.
 // ------------------------------------------------------------------------------------------
-constexpr int kMaskRowSplit = 4;   // CTAs per (detection, image)
+constexpr int kMaskRowsPerCta = 32;
 
+// One warp per row at a time: the row's vertical bin is warp-uniform, rows above/below the box are a
+// pure 0.5 fill, and every warp store instruction writes 512 contiguous bytes (streaming stores).
 __global__ void __launch_bounds__(256) mask_kernel(MaskArgs a) {
   const int d = blockIdx.y, b = blockIdx.z;
   if (d >= a.det_count[b]) return;
-  __shared__ int s_gx[kMaxK + 1], s_gy[kMaxK + 1];
-  if (threadIdx.x <= kMaxK) {
-    const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
-    s_gx[threadIdx.x] = threadIdx.x <= a.k ? ed[threadIdx.x] : 0x7fffffff;
-    s_gy[threadIdx.x] = threadIdx.x <= a.k ? ed[kMaxK + 1 + threadIdx.x] : 0x7fffffff;
-  }
-  __syncthreads();
+  const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
   int gx[kMaxK + 1], gy[kMaxK + 1];
 #pragma unroll
   for (int j = 0; j <= kMaxK; ++j) {
-    gx[j] = s_gx[j];
-    gy[j] = s_gy[j];
+    gx[j] = (j <= a.k) ? __ldg(ed + j) : 0x7fffffff;
+    gy[j] = (j <= a.k) ? __ldg(ed + kMaxK + 1 + j) : 0x7fffffff;
   }
-  const int quads_per_row = a.S >> 2;
-  const int rows_per_cta = (a.S + kMaskRowSplit - 1) / kMaskRowSplit;
-  const int y_begin = blockIdx.x * rows_per_cta;
-  const int y_end = min(a.S, y_begin + rows_per_cta);
-  const int nq = (y_end - y_begin) * quads_per_row;
+  const int x_lo = gx[0], x_hi = gx[a.k], y_lo = gy[0], y_hi = gy[a.k];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qpr = a.S >> 2;
+  const int y0 = blockIdx.x * kMaskRowsPerCta;
+  const int y1 = min(a.S, y0 + kMaskRowsPerCta);
   const float* sbase = a.score + b * a.s_img;
   float* obase = a.out + ((long long)b * a.max_det + d) * a.S * a.S;
-  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-    const int y = y_begin + q / quads_per_row;
-    const int x0 = (q % quads_per_row) << 2;
-    int by = -1;
-#pragma unroll
-    for (int j = 0; j < kMaxK; ++j)
-      if (j < a.k && y >= gy[j] && y < gy[j + 1]) by = j;
-    float4 o = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-    if (by >= 0 && x0 + 3 >= gx[0] && x0 < gx[a.k]) {
-      float v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int x = x0 + i;
-        int bx = -1;
-#pragma unroll
-        for (int j = 0; j < kMaxK; ++j)
-          if (j < a.k && x >= gx[j] && x < gx[j + 1]) bx = j;
-        float val = 0.5f;
-        if (bx >= 0) val = sigmoidf_(__ldg(sbase + (long long)(by * a.k + bx) * a.s_ch + y * a.s_row + x * a.s_pix));
-        v[i] = val;
-      }
-      o = make_float4(v[0], v[1], v[2], v[3]);
+  const float4 half4 = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+  for (int y = y0 + warp; y < y1; y += 8) {
+    float4* orow = reinterpret_cast<float4*>(obase + (long long)y * a.S);
+    if (y < y_lo || y >= y_hi) {
+      for (int q = lane; q < qpr; q += 32) __stcs(orow + q, half4);
+      continue;
     }
-    __stcs(reinterpret_cast<float4*>(obase + (long long)y * a.S + x0), o);   // streaming store
+    int by = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxK; ++j)
+      if (j < a.k && y >= gy[j]) by = j;
+    const float* srow = sbase + (long long)(by * a.k) * a.s_ch + (long long)y * a.s_row;
+    for (int q = lane; q < qpr; q += 32) {
+      const int x0 = q << 2;
+      float4 o = half4;
+      if (x0 + 3 >= x_lo && x0 < x_hi) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int x = x0 + i;
+          int bx = 0;
+#pragma unroll
+          for (int j = 1; j < kMaxK; ++j)
+            if (j < a.k && x >= gx[j]) bx = j;
+          float val = 0.5f;
+          if (x >= x_lo && x < x_hi) val = sigmoidf_(__ldg(srow + (long long)bx * a.s_ch + (long long)x * a.s_pix));
+          v[i] = val;
+        }
+        o = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      __stcs(orow + q, o);
+    }
   }
 }
 
@@ -417,7 +421,7 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
 int launch_masks(const MaskArgs& a, cudaStream_t st) {
   DY_CHECK(a.S % 4 == 0, "score map size must be a multiple of 4");
   DY_CHECK(a.max_det <= 65535 && a.B <= 65535, "grid limits");
-  dim3 grid(kMaskRowSplit, a.max_det, a.B);
+  dim3 grid((a.S + kMaskRowsPerCta - 1) / kMaskRowsPerCta, a.max_det, a.B);
   mask_kernel<<<grid, 256, 0, st>>>(a);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
