@@ -104,6 +104,9 @@ constexpr int kC1Threads = 384;
 constexpr int kC1Stages = 3;
 constexpr int kPatchW = 112;                 // pixels x0-4 .. x0+32 (37 x 3 = 111 floats): the TMA box must start 16-byte aligned
 constexpr int kPatchLead = 4;                // leading pixels before x0 inside the patch
+constexpr int kC1Patches = 4;                // patch prefetch depth per producer warp (TMA latency > 1 tile time)
+constexpr int kC1PatchFloats = 3 * kPatchW + 16;   // 1408 B, a multiple of 128 B
+constexpr size_t kC1SmemBytes = 3 * 8192 + 2048 + 4 * 2048 + 4 * kC1Patches * kC1PatchFloats * 4 + 1024;
 
 // v2: the fp32 patches arrive by TMA (3-D map [N][H][W*3], out-of-bounds = zero padding for free),
 // double buffered per producer warp; the space-to-depth output leaves through per-warp TMA stores
@@ -112,12 +115,17 @@ __global__ void __launch_bounds__(kC1Threads, 1)
 conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constant__ CUtensorMap mapOut,
                 const float* __restrict__ w_hwio, const float* __restrict__ scale, const float* __restrict__ shift,
                 float alpha, int B, int H, int W, __nv_bfloat16* __restrict__ out_same) {
-  __shared__ __align__(1024) uint8_t sA[kC1Stages][128 * 64];     // A tiles, SWIZZLE_64B rows of 64 B
-  __shared__ __align__(1024) uint8_t sB[32 * 64];                 // weights [32 cout][32 k], same layout
-  __shared__ __align__(1024) uint8_t sOut[4][2048];               // per epilogue warp: 16 pairs x 128 B, SWIZZLE_128B
-  __shared__ __align__(128) float patch[4][2][3 * kPatchW + 16];  // per producer warp, double buffered (1408 B each)
+  // dynamic smem: [A tiles: kC1Stages x 8 KB, SWIZZLE_64B rows of 64 B][weights 2 KB, same layout]
+  // [per epilogue warp 2 KB: 16 pixel pairs x 128 B, SWIZZLE_128B][patches: 4 warps x kC1Patches x 1408 B]
+  extern __shared__ uint8_t c1_smem_raw[];
+  uint8_t* c1_smem = c1_smem_raw + ((1024u - (smem_u32(c1_smem_raw) & 1023u)) & 1023u);
+  uint8_t (*sA)[128 * 64] = reinterpret_cast<uint8_t (*)[128 * 64]>(c1_smem);
+  uint8_t* sB = c1_smem + kC1Stages * 8192;
+  uint8_t (*sOut)[2048] = reinterpret_cast<uint8_t (*)[2048]>(sB + 2048);
+  float (*patch)[kC1Patches][kC1PatchFloats] =
+      reinterpret_cast<float (*)[kC1Patches][kC1PatchFloats]>(sB + 2048 + 4 * 2048);
   __shared__ __align__(8) uint64_t full_bar[kC1Stages], empty_bar[kC1Stages], tfull_bar[4], tempty_bar[4];
-  __shared__ __align__(8) uint64_t patch_bar[4][2];
+  __shared__ __align__(8) uint64_t patch_bar[4][kC1Patches];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,8 +155,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);    // one arrive per epilogue warp
-      mbar_init(&patch_bar[i][0], 1);
-      mbar_init(&patch_bar[i][1], 1);
+      for (int b2 = 0; b2 < kC1Patches; ++b2) mbar_init(&patch_bar[i][b2], 1);
     }
     fence_mbar_init();
   }
@@ -173,12 +180,16 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
       tma_load_3d(&patch[warp][buf][0], &mapImg, &patch_bar[warp][buf], (x0 - kPatchLead) * 3, y - 1, n);
     };
     int it = 0;
-    if (lane == 0 && (int)blockIdx.x < num_tiles) issue_patch(blockIdx.x, 0);
+    if (lane == 0)
+      for (int d = 0; d < kC1Patches - 1; ++d)
+        if ((long long)blockIdx.x + (long long)d * gridDim.x < num_tiles) issue_patch(blockIdx.x + d * gridDim.x, d);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int stage = it % kC1Stages, buf = it & 1;
+      const int stage = it % kC1Stages, buf = it % kC1Patches;
       const uint32_t ph = (uint32_t)(it / kC1Stages) & 1u;
-      if (lane == 0 && tile + (int)gridDim.x < num_tiles) issue_patch(tile + gridDim.x, buf ^ 1);
-      mbar_wait(&patch_bar[warp][buf], (uint32_t)(it >> 1) & 1u);
+      // refill the buffer that was consumed last iteration (all lanes passed the __syncwarp after reading it)
+      if (lane == 0 && (long long)tile + (long long)(kC1Patches - 1) * gridDim.x < num_tiles)
+        issue_patch(tile + (kC1Patches - 1) * gridDim.x, (it + kC1Patches - 1) % kC1Patches);
+      mbar_wait(&patch_bar[warp][buf], (uint32_t)(it / kC1Patches) & 1u);
       const float* mp = &patch[warp][buf][0];
       // this lane's pixel: tap (kh,kw,c) = patch[kh][(lane + kw - 1 + kPatchLead)*3 + c], k = (kh*3+kw)*3 + c
       uint32_t pk[16];
@@ -449,7 +460,12 @@ int launch_conv1(const float* img, const float* w_hwio, const float* scale, cons
     } else {
       mout = mimg;
     }
-    conv1_tc_kernel<<<grid, kC1Threads, 0, st>>>(mimg, mout, w_hwio, scale, shift, alpha, B, H, W, out_same);
+    static bool attr = false;
+    if (!attr) {
+      DY_CUDA(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC1SmemBytes));
+      attr = true;
+    }
+    conv1_tc_kernel<<<grid, kC1Threads, kC1SmemBytes, st>>>(mimg, mout, w_hwio, scale, shift, alpha, B, H, W, out_same);
   } else {
     dim3 grid((W + 127) / 128, H, B);
     conv1_kernel<<<grid, 128, 0, st>>>(img, w_hwio, scale, shift, alpha, B, H, W, out_s2d, out_same);
