@@ -244,6 +244,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __shared__ __align__(16) float s_shift[2][256];
   __shared__ long long s_dst[2][2][kBlockM];                      // [warpgroup][output][row] element offset / -1
   __shared__ __align__(8) uint64_t res_full[2][2];                // [warpgroup][staging buffer] residual landed
+  __shared__ uint32_t tap_a16[kMaxSeg][3];                        // A start offset inside the stage, >>4
+  __shared__ uint32_t tap_b16[kMaxSeg][3];                        // B start (absolute if resident, else in-stage), >>4
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,6 +288,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
+  if (warp == 3 && lane < kMaxSeg * 3) {
+    // per-(segment, tap) descriptor offsets for the MMA issuers (tile-invariant)
+    const int sgi = lane / 3, t = lane % 3;
+    if (sgi < p.num_seg && t < p.seg[sgi].ntap) {
+      tap_a16[sgi][t] = ((uint32_t)p.seg[sgi].tap_row[t] * kRowBytes) >> 4;
+      tap_b16[sgi][t] = p.b_resident ? (smem_base + (uint32_t)p.seg[sgi].tap_b0[t] * b_bytes) >> 4
+                                     : (a_bytes + (uint32_t)t * b_bytes) >> 4;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -301,9 +312,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         for (int kb = 0; kb < p.num_chunks; ++kb)
           tma_load_2d(smem_gen + (size_t)kb * b_bytes, &mapB, &bres_bar, kb * KCHUNK, n0c);
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // With dual issue the ring is split in two halves, one per MMA issuer (= per tile parity), so
+      // that every mbarrier still has exactly one producer and one consumer.
+      const int ring_sz = p.dual_issue ? p.num_stages / 2 : p.num_stages;
+      int rstage[2] = {0, 0};
+      uint32_t rphase[2] = {0u, 0u};
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int ring = p.dual_issue ? (it & 1) : 0;
+        int stage = ring ? rstage[1] : rstage[0];
+        uint32_t phase = ring ? rphase[1] : rphase[0];
         const int m0 = (tile / p.n_tiles_n) * kBlockM;
         const int n0 = (tile % p.n_tiles_n) * p.block_n;
         if (has_res) {
@@ -316,62 +334,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const CUtensorMap* am = sg.map ? &mapA1 : &mapA0;
           const uint32_t tx = a_tx + (p.b_resident ? 0u : (uint32_t)sg.ntap * b_bytes);
           for (int c = 0; c < sg.nchunk; ++c) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], tx);
-            uint8_t* sa = smem_gen + stages_off + (size_t)stage * stage_bytes;
-            tma_load_2d(sa, am, &full_bar[stage], sg.col0 + c * KCHUNK, m0 + sg.shift);
+            const int gs = ring * ring_sz + stage;                   // global stage slot
+            mbar_wait(&empty_bar[gs], phase ^ 1u);
+            mbar_expect_tx(&full_bar[gs], tx);
+            uint8_t* sa = smem_gen + stages_off + (size_t)gs * stage_bytes;
+            tma_load_2d(sa, am, &full_bar[gs], sg.col0 + c * KCHUNK, m0 + sg.shift);
             if (!p.b_resident) {
               for (int t = 0; t < sg.ntap; ++t)
-                tma_load_2d(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[stage],
+                tma_load_2d(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[gs],
                             (sg.tap_b0[t] + c) * KCHUNK, n0);
             }
-            if (++stage == p.num_stages) {
+            if (++stage == ring_sz) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
+        if (ring) { rstage[1] = stage; rphase[1] = phase; } else { rstage[0] = stage; rphase[0] = phase; }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (elect_one()) {
+  } else if (warp == 1 || warp == 3) {
+    // ================================ MMA issuers ================================
+    // Two issuing threads: issuer i owns accumulator stage i, i.e. every other tile of this CTA.
+    // For thin layers (N <= 64: 32-cycle MMAs) the per-stage wait/commit and per-MMA descriptor work
+    // of a single thread is the bottleneck; the smem ring is consumed in tile order either way.
+    if ((warp == 1 || p.dual_issue) && elect_one()) {
+      const int issuer = (warp == 3) ? 1 : 0;
+      const int it_step = p.dual_issue ? 2 : 1;
       const uint32_t idesc = umma_idesc_bf16(p.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
+      // descriptor bits that never change: LBO=1, SBO, version, layout
+      const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46) | ((uint64_t)kLayout << 61);
+      const uint32_t S = (uint32_t)(p.dual_issue ? p.num_stages / 2 : p.num_stages);   // this issuer's ring
+      const uint32_t ring_base = (uint32_t)issuer * S;
+      const uint32_t b16 = b_bytes >> 4;
       if (p.b_resident) {
         mbar_wait(&bres_bar, 0);                        // resident weights have landed
         tc_fence_after();
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      uint32_t stage = 0, phase = 0;
+      int it = issuer;
+      for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += it_step * gridDim.x, it += it_step) {
         const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);    // epilogue has drained this accumulator
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        uint32_t first = 1u;
+        mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        uint32_t acc_flag = 0u;
         for (int s = 0; s < p.num_seg; ++s) {
-          const ConvSeg& sg = p.seg[s];   // stays in constant param space (dynamic tap index)
-          for (int c = 0; c < sg.nchunk; ++c) {
-            mbar_wait(&full_bar[stage], phase);         // TMA bytes have landed
+          const int nchunk = p.seg[s].nchunk, ntap = p.seg[s].ntap;
+          for (int c = 0; c < nchunk; ++c) {
+            const uint32_t gs = ring_base + stage;
+            mbar_wait(&full_bar[gs], phase);            // TMA bytes have landed
             tc_fence_after();
-            const uint32_t sa = smem_base + stages_off + (uint32_t)stage * stage_bytes;
-            for (int t = 0; t < sg.ntap; ++t) {
+            const uint32_t sa16 = (smem_base + stages_off + gs * stage_bytes) >> 4;
+            for (int t = 0; t < ntap; ++t) {
               // same box, start address advanced by whole rows: tap t of the shared halo'd segment
-              const uint64_t adesc = umma_desc(sa + (uint32_t)sg.tap_row[t] * kRowBytes, kSBO, kLayout);
-              const uint32_t sb = p.b_resident ? smem_base + (uint32_t)(sg.tap_b0[t] + c) * b_bytes
-                                               : sa + a_bytes + (uint32_t)t * b_bytes;
-              const uint64_t bdesc = umma_desc(sb, kSBO, kLayout);
+              const uint64_t adesc = desc_hi | (uint64_t)(sa16 + tap_a16[s][t]);
+              const uint64_t bdesc = desc_hi | (uint64_t)(p.b_resident ? tap_b16[s][t] + (uint32_t)c * b16
+                                                                       : sa16 + tap_b16[s][t]);
 #pragma unroll
               for (int k = 0; k < KCHUNK / 16; ++k) {
                 // +32 bytes (16 bf16) along K inside the swizzle row: +2 in the (addr>>4) field
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ^ 1u);
-                first = 0u;
+                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc_flag);
+                acc_flag = 1u;
               }
             }
-            umma_commit(&empty_bar[stage]);             // frees the smem slot when the MMAs retire
-            if (++stage == p.num_stages) {
+            umma_commit(&empty_bar[gs]);                // frees the smem slot when the MMAs retire
+            if (++stage == S) {
               stage = 0;
               phase ^= 1u;
             }
@@ -391,6 +419,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     float* my_shift = s_shift[wg];
     int cached_n0 = -1;
     uint32_t res_par = 0u;                              // bit b = parity of res_full[wg][b]; persists across tiles
+    uint32_t sc = 0u;                                   // slabs processed by this warpgroup so far (buffer = sc & 1)
+    bool res_primed = false;
     int it = wg;
     for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
       const int acc = wg;
@@ -420,7 +450,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
       uint32_t r0[16], r1[16];
-      if (p.slab == 0) {
+      if (p.debug_skip == 1) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      } else if (p.slab == 0) {
         // ---------------- direct path: the row's owner thread reads/writes global memory ----------------
         const __nv_bfloat16* res_row = has_res ? p.residual + m * p.res_ld + n0 : nullptr;
         const bool do_res = has_res && px.valid;
@@ -449,10 +482,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
       } else if (p.tma_epi) {
         // ---------------- TMA staged path ----------------
-        // Two swizzled staging buffers per warpgroup.  The residual slab is TMA-loaded INTO the
-        // buffer (the first two slabs while the MMAs of this tile are still running), phase 1
-        // updates it in place thread-per-row (swizzle => conflict-free), then one elected thread
-        // TMA-stores the slab.  No global load/store instruction is executed for out[0].
+        // Two swizzled staging buffers per warpgroup used round-robin over ALL slabs of ALL tiles of
+        // this warpgroup (slab counter `sc`).  The residual slab is TMA-loaded INTO its buffer one
+        // slab ahead (the next tile's first slab is requested at the end of the current tile, so it
+        // lands while that tile's MMAs are still running); phase 1 updates the buffer in place
+        // thread-per-row (swizzle => conflict-free) and one elected thread TMA-stores it.  A buffer
+        // is reused two slabs later, so only `wait_group.read 1` is ever needed: no store latency is
+        // exposed.  No global load/store instruction is executed for out[0].
         const uint32_t buf_bytes = (uint32_t)kBlockM * p.slab * 2;
         uint8_t* stg0 = smem_gen + epi_off + (size_t)wg * 2 * buf_bytes;
         const int row = q * 32 + lane;
@@ -462,26 +498,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool elected = wg_tid == 0;
         const bool dual = p.out[1].mode != OUT_NONE;
         if (dual) s_dst[wg][1][row] = dest_offset(p, p.out[1], px, m);
-        if (elected) {
-          bulk_wait_read<0>();                              // last tile's stores have left the buffers
-          if (has_res) {
-            for (int s2 = 0; s2 < nslab && s2 < 2; ++s2) {
-              mbar_expect_tx(&res_full[wg][s2], buf_bytes);
-              tma_load_2d(stg0 + (size_t)s2 * buf_bytes, &mapR, &res_full[wg][s2], n0 + s2 * p.slab, m0);
-            }
-          }
+        if (elected && has_res && !res_primed) {
+          // very first slab of this warpgroup: nothing has used the buffers yet
+          mbar_expect_tx(&res_full[wg][sc & 1], buf_bytes);
+          tma_load_2d(stg0 + (size_t)(sc & 1) * buf_bytes, &mapR, &res_full[wg][sc & 1], n0, m0);
         }
+        res_primed = true;
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        for (int sidx = 0; sidx < nslab; ++sidx) {
+        for (int sidx = 0; sidx < nslab; ++sidx, ++sc) {
           const int slab0 = sidx * p.slab;
-          const int bsel = sidx & 1;
+          const int bsel = sc & 1;
           uint8_t* stg = stg0 + (size_t)bsel * buf_bytes;
           if (has_res) {
             mbar_wait(&res_full[wg][bsel], (res_par >> bsel) & 1u);
             res_par ^= 1u << bsel;
           } else {
-            if (sidx >= 2 && elected) bulk_wait_read<1>();   // the store that last used this buffer is done
+            if (elected) bulk_wait_read<1>();                // the store two slabs ago has read this buffer
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           }
           uint8_t* srow = stg + (size_t)row * epi_pitch;
@@ -490,19 +523,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tmem_ld_wait();
             const bool more1 = c0 + 16 < p.slab;
             if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
-            epilogue_chunk_swz(p, r0, my_scale, my_shift, slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
+            if (p.debug_skip != 2)
+              epilogue_chunk_swz(p, r0, my_scale, my_shift, slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
             if (more1) {
               tmem_ld_wait();
               if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
-              epilogue_chunk_swz(p, r1, my_scale, my_shift, slab0 + c0 + 16, has_res, px.valid, srow, (c0 + 16) >> 3,
-                                 rsw);
+              if (p.debug_skip != 2)
+                epilogue_chunk_swz(p, r1, my_scale, my_shift, slab0 + c0 + 16, has_res, px.valid, srow,
+                                   (c0 + 16) >> 3, rsw);
             }
           }
-          fence_proxy_async_smem();                          // generic-proxy smem writes -> async proxy (TMA)
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          if (p.debug_skip == 0 || p.debug_skip >= 4) {
+            fence_proxy_async_smem();                        // generic-proxy smem writes -> async proxy (TMA)
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          }
           if (elected) {
-            tma_store_2d(&mapO, stg, n0 + slab0, m0);
-            bulk_commit();
+            if (p.debug_skip == 0) {
+              tma_store_2d(&mapO, stg, n0 + slab0, m0);
+              bulk_commit();
+            }
+            if (has_res) {
+              // request the residual of the NEXT slab (this tile's, or the first one of this
+              // warpgroup's next tile) into the other buffer, whose last store is one slab old
+              int nm0 = m0, nn0 = n0 + slab0 + p.slab;
+              bool have = sidx + 1 < nslab;
+              if (!have) {
+                const int ntile = tile + 2 * (int)gridDim.x;
+                if (ntile < num_tiles) {
+                  have = true;
+                  nm0 = (ntile / p.n_tiles_n) * kBlockM;
+                  nn0 = (ntile % p.n_tiles_n) * p.block_n;
+                }
+              }
+              if (have) {
+                bulk_wait_read<1>();
+                mbar_expect_tx(&res_full[wg][bsel ^ 1], buf_bytes);
+                tma_load_2d(stg0 + (size_t)(bsel ^ 1) * buf_bytes, &mapR, &res_full[wg][bsel ^ 1], nn0, nm0);
+              }
+            }
           }
           if (dual) {
             // second destination form (space-to-depth / upsampled): cooperative vector stores
@@ -514,12 +572,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + ((cj ^ sw) << 4));
               store_vec(p, p.out[1], d1, n0 + slab0 + cj * 8, v);
             }
-            if (has_res && sidx + 2 < nslab) asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-          }
-          if (elected && has_res && sidx + 2 < nslab) {
-            bulk_wait_read<0>();                             // this buffer's store has read it: refill
-            mbar_expect_tx(&res_full[wg][bsel], buf_bytes);
-            tma_load_2d(stg, &mapR, &res_full[wg][bsel], n0 + (sidx + 2) * p.slab, m0);
           }
         }
       } else {

@@ -63,10 +63,13 @@ struct ConvParams {
   ConvSeg seg[kMaxSeg];
   int num_chunks;  // number of weight K chunks = sum of seg[].nchunk * seg[].ntap
   int num_stages;  // smem pipeline depth
+  int tile_stages; // pipeline stages consumed per tile = sum of seg[].nchunk
+  int dual_issue;  // 1: two MMA-issuer threads, each with its own half of the stage ring (thin layers)
   int a_rows;      // rows per A box: 128, or kHaloRows when taps share a halo'd box
   int max_ntap;    // max seg[].ntap (sizes the per-stage weight slots when weights are streamed)
   int b_resident;  // 1: the CTA's whole [block_n x K] weight slab is loaded to smem once
   int slab;        // epilogue staging width in columns (64 or 32); 0 = direct per-thread stores
+  int debug_skip;  // measurement aid: 1 = epilogue only drains the accumulator barrier (no math, no stores)
   int tma_epi;     // staged epilogue only: out[0] (P1 layout) leaves through TMA stores, the residual
                    // arrives through TMA loads into the same swizzled staging buffers
   int tmem_cols;   // power of two >= 2*block_n, >= 32

@@ -133,6 +133,8 @@ static int g_opt_resident = -1;     // 0: never keep weights resident, 1: whenev
 static int g_opt_halo = -1;         // 0: never share a halo'd A box between taps, 1: whenever legal
 static int g_opt_staged = -1;       // 0: per-thread row stores, 1: smem-staged cooperative stores
 static int g_opt_tma_epi = -1;      // 0: cooperative staged epilogue, 1: TMA store / TMA residual staged epilogue
+static int g_opt_dual = -1;         // 0: one MMA issuer, 1: two issuers whenever the ring has >= 4 stages
+static int g_opt_skip_epi = 0;      // measurement only: conv epilogues do nothing
 static int g_opt_conv1_tc = -1;     // 0: conv1 on CUDA cores, otherwise the tcgen05 im2col stem kernel
 
 static int pick_block_n(int cout_pad, long long rows, int num_sms) {
@@ -276,7 +278,9 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
     }
   }
   int nchunks = 0, max_ntap = 1;
+  p.tile_stages = 0;
   for (int i = 0; i < ns; ++i) {
+    p.tile_stages += p.seg[i].nchunk;
     nchunks += p.seg[i].nchunk * p.seg[i].ntap;
     if (p.seg[i].ntap > max_ntap) max_ntap = p.seg[i].ntap;
   }
@@ -288,10 +292,18 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (!bf16_out || p.block_n % 32 != 0) staged = false;
   p.slab = !staged ? 0 : (p.block_n % 64 == 0 && p.block_n <= 128 ? 64 : 32);
   p.tma_epi = (staged && tma && d.out[0].mode == OUT_SAME) ? 1 : 0;
+  p.debug_skip = g_opt_skip_epi > 0 ? g_opt_skip_epi : 0;
   if (p.tma_epi && p.block_n % 64 == 0) p.slab = 64;
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
   p.num_stages = conv_tc_pick_stages(kchunk, p);
   DY_CHECK(p.num_stages >= 2, "no room for a shared-memory pipeline");
+  // two MMA issuers for thin tiles (32/64-cycle MMAs: the issue thread, not the tensor pipe, is the
+  // bottleneck); each issuer needs its own half ring with at least one tile's worth of stages in flight
+  bool dual_issue = enough_work && p.block_n <= 64 && p.num_stages >= 6;
+  if (g_opt_dual == 0) dual_issue = false;
+  if (g_opt_dual == 1) dual_issue = p.num_stages >= 4;
+  if (dual_issue) p.num_stages &= ~1;
+  p.dual_issue = dual_issue ? 1 : 0;
   const int a0_cols = (d.s == 2) ? 4 * d.cin0 : d.cin0;
   DY_TRY(make_tmap_2d(&plan->a0, d.a0, rows_max, a0_cols, a0_cols, kchunk, p.a_rows));
   if (d.cin1 > 0) {
@@ -778,6 +790,8 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_staged") g_opt_staged = value;
   else if (n == "tc_tma_epi") g_opt_tma_epi = value;
   else if (n == "conv1_tc") g_opt_conv1_tc = value;
+  else if (n == "tc_skip_epilogue") g_opt_skip_epi = value;
+  else if (n == "tc_dual_issue") g_opt_dual = value;
   else {
     set_error("unknown option " + n);
     return DY_ERR_NOTFOUND;

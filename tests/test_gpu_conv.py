@@ -118,12 +118,13 @@ def test_conv_linearity_property():
     assert np.array_equal(y2, 2.0 * y1)       # power-of-two scaling is exact in bf16/fp32
 
 
-@pytest.mark.parametrize('resident,halo,staged,tma', [(1, 1, 1, 1), (0, 1, 0, 0), (1, 0, 0, 0), (0, 0, 1, 0),
-                                                      (0, 1, 1, 1), (0, 0, 1, 1)])
+@pytest.mark.parametrize('resident,halo,staged,tma,dual', [(1, 1, 1, 1, 1), (0, 1, 0, 0, 0), (1, 0, 0, 0, 1),
+                                                           (0, 0, 1, 0, 0), (0, 1, 1, 1, 1), (0, 0, 1, 1, 0),
+                                                           (0, 0, 0, 0, 1)])
 @pytest.mark.parametrize('case', [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4], CASES[5], CASES[6], CASES[7],
                                   CASES[8], CASES[10]],
                          ids=lambda c: 'B%d_%dx%d_%d-%d_k%ds%d' % c[:7])
-def test_conv_bf16_forced_modes(case, resident, halo, staged, tma):
+def test_conv_bf16_forced_modes(case, resident, halo, staged, tma, dual):
     """Every planning mode of the tensor-core engine (weights resident in smem or streamed; one
     halo'd activation box shared by the three horizontal taps or one box per tap) must give the
     same result as the default plan -- bit for bit, since the MMA order along K is unchanged."""
@@ -139,12 +140,14 @@ def test_conv_bf16_forced_modes(case, resident, halo, staged, tma):
         set_option('tc_halo', halo)
         set_option('tc_staged', staged)
         set_option('tc_tma_epi', tma)
+        set_option('tc_dual_issue', dual)
         got = conv_layer(xc, w, case[6], scale, shift, case[7], 0.1, rc, 'bf16').cpu().numpy()
     finally:
         set_option('tc_resident', -1)
         set_option('tc_halo', -1)
         set_option('tc_staged', -1)
         set_option('tc_tma_epi', -1)
+        set_option('tc_dual_issue', -1)
     e = rel_err(got, want)
     assert e < 5e-3, 'resident=%d halo=%d staged=%d tma=%d rel err %.3g' % (resident, halo, staged, tma, e)
     assert float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 0.25))) < 1e-2
