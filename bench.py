@@ -424,8 +424,9 @@ def main():
     ap.add_argument('--latency', type=int, default=200, help='batch-1 latency iterations (0 = skip)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--workload', default='inference', choices=['inference', 'train'])
-    ap.add_argument('--traffic', type=float, default=None,
-                    help='dram bytes per step of the conv kernel from the committed ncu capture (profiles/)')
+    ap.add_argument('--traffic', type=float, default=25.9e9,
+                    help='DRAM bytes per step of the conv kernel (sum over its 81 launches) from the committed ncu '
+                         'launch list profiles/r1_launches.csv')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
