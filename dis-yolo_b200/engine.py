@@ -158,6 +158,23 @@ class Engine(object):
                                        _ptr(out.get('masks')), self._stream()), 'dy_forward')
         return out
 
+    def capture_graph(self, images, windows, det_thresh, out):
+        """Capture one forward (conv1..82 + decode + NMS + masks, ~86 launches) into a CUDA graph over
+        fixed device buffers; `graph.replay()` then re-runs it with one launch.  Used for the batch-1
+        latency path (launch overhead dominates there)."""
+        t = self.torch
+        s = t.cuda.Stream(device=self.device)
+        s.wait_stream(t.cuda.current_stream(self.device))
+        with t.cuda.stream(s):
+            for _ in range(2):
+                self.forward(images, windows, det_thresh, out=out)     # warm-up: one-time attribute calls
+        t.cuda.current_stream(self.device).wait_stream(s)
+        t.cuda.synchronize(self.device)
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g):
+            self.forward(images, windows, det_thresh, out=out)
+        return g
+
     def forward_network(self, images):
         images = self._dev(images, self.torch.float32)
         _lib.check(self.lib.dy_forward_network(self.h, _ptr(images), images.shape[0], self._stream()),

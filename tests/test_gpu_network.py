@@ -156,3 +156,25 @@ def test_pipelined_host_forward_matches_sync():
     with pytest.raises(Exception):
         eng.forward_host_end((0, B, True, None))        # nothing in flight any more
     eng.close()
+
+
+def test_cuda_graph_replay_matches_eager():
+    import torch
+    import disyolo_b200 as dy
+    B, size = 1, 160
+    eng = dy.Engine(image_size=size, max_batch=B, precision='bf16')
+    eng.load_weights(O.make_weights('lively', 0))
+    img, win = _inputs(B, size, 21)
+    img_d, win_d = torch.from_numpy(img).cuda(), torch.from_numpy(win).cuda()
+    out = eng.forward(img_d, win_d, 0.2)
+    torch.cuda.synchronize()
+    want = {k: v.clone() for k, v in out.items()}
+    g = eng.capture_graph(img_d, win_d, 0.2, out)
+    for v in out.values():
+        v.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    n = int(want['det_count'][0])
+    assert torch.equal(out['det_raw'], want['det_raw']) and torch.equal(out['det_count'], want['det_count'])
+    assert torch.equal(out['masks'][0, :n], want['masks'][0, :n])
+    eng.close()
