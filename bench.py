@@ -54,49 +54,101 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    In-process NVML polling every ~2 ms (a 64-image step is ~11 ms, too short for `nvidia-smi -lms`);
+    falls back to one `nvidia-smi --query-gpu` line per 100 ms if NVML cannot be loaded."""
+
+    REASONS = (('hw_slowdown', 'nvmlClocksEventReasonHwSlowdown', 0x8),
+               ('hw_thermal_slowdown', 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+               ('sw_thermal_slowdown', 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+               ('sw_power_cap', 'nvmlClocksEventReasonSwPowerCap', 0x4))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.h = index, [], None, None, None
+        self.stop_flag = False
+        self.thread = None
+        self.mx = None
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            try:
+                return int(vis.split(',')[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self._physical_index()), '--query-gpu=' + q,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread = threading.Thread(target=self._read_smi, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for t, line in self.rows:
-            if t < t0 - 0.05 or t > t1 + 0.05:
-                continue
+    def _read_smi(self):
+        for line in self.proc.stdout:
             f = [x.strip() for x in line.split(',')]
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                mhz, self.mx = float(f[0]), float(f[1])
             except Exception:
                 continue
-            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], f[3:7]):
+            bits = 0
+            for (name, _, bit), v in zip(self.REASONS, f[3:7]):
                 if v.lower().startswith('active'):
+                    bits |= bit
+            self.rows.append((time.time(), mhz, bits))
+
+    def stop(self, t0, t1):
+        if self.thread is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no NVML and no nvidia-smi'], samples=0)
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        sm, reasons = [], set()
+        for t, mhz, bits in self.rows:
+            if t < t0 or t > t1:
+                continue
+            sm.append(mhz)
+            for name, attr, bit in self.REASONS:
+                if bits & (getattr(self.nv, attr, bit) if self.nv else bit):
                     reasons.add(name)
         sm.sort()
-        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
-                    samples=len(sm))
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=self.mx, reasons=sorted(reasons),
+                    samples=len(sm), source='nvml' if self.nv else 'nvidia-smi')
 
 
 def dist_env():
@@ -435,7 +487,7 @@ def run_train(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)

@@ -236,8 +236,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tfull_bar[2];
-  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t tfull_bar[4];
+  __shared__ __align__(8) uint64_t tempty_bar[4];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_scale[2][256];                 // per epilogue warpgroup
@@ -276,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp of the owning warpgroup
     }
@@ -372,11 +372,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc_fence_after();
       }
       uint32_t stage = 0, phase = 0;
+      const int acc_sh = p.num_acc == 4 ? 2 : 1;
       int it = issuer;
       for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += it_step * gridDim.x, it += it_step) {
-        const int acc = it & 1;
+        const int acc = it & (p.num_acc - 1);           // num_acc is 2 or 4: parity(acc) == parity(it) == issuer
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> acc_sh) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         uint32_t acc_flag = 0u;
         for (int s = 0; s < p.num_seg; ++s) {
@@ -423,8 +424,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     bool res_primed = false;
     int it = wg;
     for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
-      const int acc = wg;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = it & (p.num_acc - 1);             // this warpgroup owns the accumulators of its tile parity
+      const uint32_t acc_phase = (uint32_t)(it >> (p.num_acc == 4 ? 2 : 1)) & 1u;
       const int m0 = (tile / p.n_tiles_n) * kBlockM;
       const int n0 = (tile % p.n_tiles_n) * p.block_n;
       const long long m = (long long)m0 + q * 32 + lane;
@@ -766,7 +767,8 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
   DY_CHECK(kchunk == 64 || kchunk == 32, "kchunk");
   DY_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n");
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
-  DY_CHECK(p.tmem_cols >= 2 * p.block_n && p.tmem_cols <= 512, "tmem_cols");
+  DY_CHECK(p.num_acc == 2 || p.num_acc == 4, "num_acc");
+  DY_CHECK(p.tmem_cols >= p.num_acc * p.block_n && p.tmem_cols <= 512, "tmem_cols");
   DY_CHECK(p.a_rows == kBlockM || p.a_rows == kHaloRows, "a_rows");
   DY_CHECK(p.max_ntap >= 1 && p.max_ntap <= 3, "max_ntap");
   DY_CHECK(p.slab == 0 || ((p.slab == 32 || p.slab == 64) && p.block_n % p.slab == 0), "slab");

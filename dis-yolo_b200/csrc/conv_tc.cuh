@@ -64,6 +64,7 @@ struct ConvParams {
   int num_chunks;  // number of weight K chunks = sum of seg[].nchunk * seg[].ntap
   int num_stages;  // smem pipeline depth
   int tile_stages; // pipeline stages consumed per tile = sum of seg[].nchunk
+  int num_acc;     // TMEM accumulator stages: 2, or 4 (two per MMA issuer) for thin dual-issue tiles
   int dual_issue;  // 1: two MMA-issuer threads, each with its own half of the stage ring (thin layers)
   int a_rows;      // rows per A box: 128, or kHaloRows when taps share a halo'd box
   int max_ntap;    // max seg[].ntap (sizes the per-stage weight slots when weights are streamed)

@@ -304,6 +304,12 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (g_opt_dual == 1) dual_issue = p.num_stages >= 4;
   if (dual_issue) p.num_stages &= ~1;
   p.dual_issue = dual_issue ? 1 : 0;
+  // four TMEM accumulator stages (two per issuer) when they fit: otherwise each issuer would be
+  // serialised with its own epilogue warpgroup
+  p.num_acc = (dual_issue && 4 * p.block_n <= 512) ? 4 : 2;
+  tc = 32;
+  while (tc < p.num_acc * p.block_n) tc <<= 1;
+  p.tmem_cols = tc;
   const int a0_cols = (d.s == 2) ? 4 * d.cin0 : d.cin0;
   DY_TRY(make_tmap_2d(&plan->a0, d.a0, rows_max, a0_cols, a0_cols, kchunk, p.a_rows));
   if (d.cin1 > 0) {
