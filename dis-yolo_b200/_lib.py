@@ -60,6 +60,7 @@ SIGNATURES = {
     'dy_nms': (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),
     'dy_assemble_masks': (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     'dy_conv_layer': (C.c_int, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P]),
+    'dy_conv_backward': (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P]),
     'dy_train_init': (C.c_int, [_P]),
     'dy_train_param_count': (C.c_int64, [_P]),
     'dy_train_layer_span': (C.c_int, [_P, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -15,6 +15,7 @@
 #include "conv_tc.cuh"
 #include "postproc.cuh"
 #include "train.cuh"
+#include "train_tc.cuh"
 
 namespace dy {
 
@@ -136,6 +137,7 @@ static int g_opt_tma_epi = -1;      // 0: cooperative staged epilogue, 1: TMA st
 static int g_opt_dual = -1;         // 0: one MMA issuer, 1: two issuers whenever the ring has >= 4 stages
 static int g_opt_skip_epi = 0;      // measurement only: conv epilogues do nothing
 static int g_opt_conv1_tc = -1;     // 0: conv1 on CUDA cores, otherwise the tcgen05 im2col stem kernel
+static int g_wg_dbg[4] = {0, 0, 0, 0};   // bring-up aid: wgrad UMMA descriptor overrides (0 = computed)
 
 static int pick_block_n(int cout_pad, long long rows, int num_sms) {
   static const int cands[] = {256, 128, 64, 32, 16};
@@ -378,6 +380,17 @@ struct LayerState {
   float *bn_a = nullptr, *bn_b = nullptr, *bmean = nullptr, *bvar = nullptr, *binvstd = nullptr;
   double* stat = nullptr;      // [4*cout]: sum, sumsq | s1, s2
   long long off_w = -1, off_g = -1, off_b = -1;   // offsets into the flat trainable vector
+  // ---- training state (bf16 tensor-core engine) ----
+  int Cg = 0;                       // channels of dyb: cout rounded up to 32
+  __nv_bfloat16* zb = nullptr;      // pre-BN conv output of this step, P1
+  __nv_bfloat16* dyb = nullptr;     // gradient w.r.t. this layer's output, P1, Cg channels
+  float* dyf = nullptr;             // biased linear convs: fp32 NHWC gradient written by the loss kernels
+  __nv_bfloat16* wdg0 = nullptr;    // dgrad operand towards src0: [cin0][k*k*Cg], taps rotated by 180 degrees
+  __nv_bfloat16* wdg1 = nullptr;    // dgrad operand towards src1 (concat branch, 1x1): [cin1][Cg]
+  TcPlan plan_z, plan_dg0, plan_dg1;
+  WgradPlan plan_wg;
+  bool dg0 = false, dg1 = false;    // which input gradients this layer produces
+  bool res_acc = false;             // shortcut gradient: accumulate (true) or first write (copy)
 };
 
 }  // namespace dy
@@ -431,6 +444,8 @@ struct dy_net {
   float* train_windows = nullptr;
   float* ones_dev = nullptr;       // [1024] identity scale for "conv only" passes
   float* zeros_dev = nullptr;
+  __nv_bfloat16* dzb_scratch = nullptr;   // bf16 engine: dz of the layer being differentiated (P1)
+  __nv_bfloat16* pool_scratch = nullptr;  // bf16 engine: 2x2-pooled dz of a concat consumer (P1, low resolution)
   long long adam_step = 0;
 };
 
@@ -798,6 +813,10 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "conv1_tc") g_opt_conv1_tc = value;
   else if (n == "tc_skip_epilogue") g_opt_skip_epi = value;
   else if (n == "tc_dual_issue") g_opt_dual = value;
+  else if (n == "wgrad_lbo_a") { g_wg_dbg[0] = value; wgrad_set_debug(g_wg_dbg[0], g_wg_dbg[1], g_wg_dbg[2], g_wg_dbg[3]); }
+  else if (n == "wgrad_sbo_a") { g_wg_dbg[1] = value; wgrad_set_debug(g_wg_dbg[0], g_wg_dbg[1], g_wg_dbg[2], g_wg_dbg[3]); }
+  else if (n == "wgrad_lbo_b") { g_wg_dbg[2] = value; wgrad_set_debug(g_wg_dbg[0], g_wg_dbg[1], g_wg_dbg[2], g_wg_dbg[3]); }
+  else if (n == "wgrad_sbo_b") { g_wg_dbg[3] = value; wgrad_set_debug(g_wg_dbg[0], g_wg_dbg[1], g_wg_dbg[2], g_wg_dbg[3]); }
   else {
     set_error("unknown option " + n);
     return DY_ERR_NOTFOUND;
@@ -1278,6 +1297,69 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
   return rc;
 }
 
+int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
+                     const float* w_host, int32_t k, int32_t cout, float* dx_dev, float* dw_dev, void* stream) {
+  DY_CHECK(x_dev && dz_dev && w_host && (dx_dev || dw_dev), "null argument");
+  DY_CHECK(k == 1 || k == 3, "k");
+  DY_CHECK(cin % 32 == 0 && cin >= 32, "the bf16 engine needs cin % 32 == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = DY_OK;
+  std::vector<void*> tmp;
+  auto talloc = [&](void** p, size_t bytes) -> int {
+    DY_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+    tmp.push_back(*p);
+    DY_CUDA(cudaMemsetAsync(*p, 0, bytes ? bytes : 16, st));
+    return DY_OK;
+  };
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(st);
+    for (void* p : tmp) cudaFree(p);
+  };
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int Cg = (cout + 31) / 32 * 32, K = k * k * cin;
+  const size_t rows_pad = (size_t)B * (H + 1) * (W + 1) + 64;
+  __nv_bfloat16 *d_x = nullptr, *d_dz = nullptr, *d_dx = nullptr, *d_wdg = nullptr;
+  float *d_w = nullptr, *d_one = nullptr, *d_zero = nullptr;
+  const int npad = cin > 1024 ? cin : 1024;
+  std::vector<float> ones(npad, 1.f);
+  if ((rc = talloc((void**)&d_x, rows_pad * cin * 2)) || (rc = talloc((void**)&d_dz, rows_pad * Cg * 2)) ||
+      (rc = talloc((void**)&d_dx, rows_pad * cin * 2)) || (rc = talloc((void**)&d_wdg, (size_t)cin * k * k * Cg * 2)) ||
+      (rc = talloc((void**)&d_w, (size_t)K * cout * 4)) || (rc = talloc((void**)&d_one, (size_t)npad * 4)) ||
+      (rc = talloc((void**)&d_zero, (size_t)npad * 4))) {
+    cleanup();
+    return rc;
+  }
+  cudaMemcpyAsync(d_w, w_host, (size_t)K * cout * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_one, ones.data(), (size_t)npad * 4, cudaMemcpyHostToDevice, st);
+  note_launch(2);
+  rc = launch_nhwc_to_p1(x_dev, d_x, B, H, W, cin, FORM_SAME, st);
+  if (rc == DY_OK) rc = launch_f32_to_p1(dz_dev, B, H, W, cout, d_dz, Cg, st);
+  if (rc == DY_OK && dx_dev) {
+    note_launch(3);
+    rc = launch_pack_dgrad_bf16(d_w, k, cin, 0, cin, cout, Cg, d_wdg, st);
+    TcConvDesc c;
+    c.a0 = d_dz; c.cin0 = Cg; c.cout = cin; c.k = k; c.s = 1; c.H = H; c.W = W; c.max_batch = B;
+    c.wpk = d_wdg; c.cout_pad = cin; c.scale = d_one; c.shift = d_zero; c.act = 0; c.alpha = 0.1f;
+    c.out[0] = OutDesc{d_dx, OUT_SAME, cin};
+    c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
+    TcPlan plan;
+    if (rc == DY_OK) rc = build_tc_plan(c, num_sms, &plan);
+    if (rc == DY_OK) rc = run_tc_plan(plan, B, num_sms, st);
+    if (rc == DY_OK) rc = launch_p1_to_nhwc(d_dx, dx_dev, B, H, W, cin, FORM_SAME, st);
+  }
+  if (rc == DY_OK && dw_dev) {
+    note_launch();
+    cudaMemsetAsync(dw_dev, 0, (size_t)K * cout * 4, st);
+    WgradPlan wp;
+    rc = build_wgrad_plan(d_x, cin, nullptr, 0, d_dz, Cg, cout, k, H, W, (long long)B * (H + 1) * (W + 1), dw_dev, &wp);
+    if (rc == DY_OK) rc = run_wgrad_plan(wp, B, H, W, num_sms, st);
+  }
+  cleanup();
+  return rc;
+}
+
 }  // extern "C"
 
 // =============================================================================================
@@ -1292,11 +1374,12 @@ static const float kL2 = 1e-4f;            // yolo3_net_pos.py:38
 static const float kAdamB1 = 0.9f, kAdamB2 = 0.999f, kAdamEps = 1e-8f;
 
 static size_t out_elems(const LayerDef& d, int B) { return (size_t)B * d.H * d.H * d.cout; }
+static int train_init_tc(dy_net* net);
 
 static int train_init(dy_net* net) {
   if (net->train_ready) return DY_OK;
-  DY_CHECK(net->cfg.precision == DY_PRECISION_FP32, "the training step runs on the fp32 engine in this round");
   DY_CHECK(net->finalized, "load weights before dy_train_init");
+  const bool bf16 = net->cfg.precision == DY_PRECISION_BF16;
   auto& L = net->L;
   const int B = net->cfg.max_batch;
   // which layers are trainable, which take part in the backward pass
@@ -1330,13 +1413,31 @@ static int train_init(dy_net* net) {
       DY_CUDA(cudaMemcpy(s.d_bias, s.bias.data(), C * 4, cudaMemcpyHostToDevice));
     }
     if (!s.in_bwd) continue;
-    DY_TRY(dev_alloc(net, (void**)&s.z, out_elems(d, B) * 4));
-    DY_TRY(dev_alloc(net, (void**)&s.dy, out_elems(d, B) * 4));
+    if (bf16) {
+      // tensor-core engine: the backward pass differentiates stride-1 convs fed by P1 activations
+      if (d.s != 1 || d.src0 == 0 || s.need_s2d) {
+        set_error("bf16 training needs convolutional1 and the stride-2 convolutions (2, 5, 10, 27, 44) and every "
+                  "layer feeding them locked (the reference's stage 1); use precision=fp32 for a fully unlocked net");
+        return DY_ERR_UNSUPPORTED;
+      }
+      s.Cg = (C + 31) / 32 * 32;
+      const size_t rows_pad = (size_t)B * (d.H + 1) * (d.H + 1) + 64;
+      if (d.bn) DY_TRY(dev_alloc(net, (void**)&s.zb, rows_pad * C * 2));
+      else DY_TRY(dev_alloc(net, (void**)&s.dyf, out_elems(d, B) * 4));
+      DY_TRY(dev_alloc(net, (void**)&s.dyb, rows_pad * s.Cg * 2));
+      if (!s.d_w_f32) {                      // fp32 master copy of the weights
+        DY_TRY(dev_alloc(net, (void**)&s.d_w_f32, (size_t)s.K * C * 4));
+        DY_CUDA(cudaMemcpy(s.d_w_f32, s.w.data(), (size_t)s.K * C * 4, cudaMemcpyHostToDevice));
+      }
+    } else {
+      DY_TRY(dev_alloc(net, (void**)&s.z, out_elems(d, B) * 4));
+      DY_TRY(dev_alloc(net, (void**)&s.dy, out_elems(d, B) * 4));
+    }
     DY_TRY(dev_alloc(net, (void**)&s.stat, (size_t)4 * C * 8));
     DY_TRY(dev_alloc(net, (void**)&s.bn_a, C * 4)); DY_TRY(dev_alloc(net, (void**)&s.bn_b, C * 4));
     DY_TRY(dev_alloc(net, (void**)&s.bmean, C * 4)); DY_TRY(dev_alloc(net, (void**)&s.bvar, C * 4));
     DY_TRY(dev_alloc(net, (void**)&s.binvstd, C * 4));
-    if (s.need_in_grad) DY_TRY(dev_alloc(net, (void**)&s.wt, (size_t)s.K * C * 4));
+    if (s.need_in_grad && !bf16) DY_TRY(dev_alloc(net, (void**)&s.wt, (size_t)s.K * C * 4));
     if (out_elems(d, B) > max_out) max_out = out_elems(d, B);
     const size_t in_e = (size_t)B * (d.H * d.s) * (d.H * d.s) * (d.cin0 + d.cin1);
     if (s.need_in_grad && in_e > max_in) max_in = in_e;
@@ -1349,8 +1450,10 @@ static int train_init(dy_net* net) {
   net->n_train = off;
   DY_TRY(dev_alloc(net, (void**)&net->adam_m, (size_t)off * 4));
   DY_TRY(dev_alloc(net, (void**)&net->adam_v, (size_t)off * 4));
-  DY_TRY(dev_alloc(net, (void**)&net->dz_scratch, max_out * 4));
-  DY_TRY(dev_alloc(net, (void**)&net->dx_scratch, max_in * 4));
+  if (!bf16) {
+    DY_TRY(dev_alloc(net, (void**)&net->dz_scratch, max_out * 4));
+    DY_TRY(dev_alloc(net, (void**)&net->dx_scratch, max_in * 4));
+  }
   DY_TRY(dev_alloc(net, (void**)&net->loss_acc, 8 * 8));
   DY_TRY(dev_alloc(net, (void**)&net->mask_rois, (size_t)B * 10 * 4 * 4));
   DY_TRY(dev_alloc(net, (void**)&net->mask_assign, (size_t)B * 10 * 4));
@@ -1365,6 +1468,7 @@ static int train_init(dy_net* net) {
   std::vector<float> w(B * 4);
   for (int b = 0; b < B; ++b) { w[4 * b] = 0; w[4 * b + 1] = 0; w[4 * b + 2] = 1; w[4 * b + 3] = 1; }
   DY_CUDA(cudaMemcpy(net->train_windows, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  if (bf16) DY_TRY(train_init_tc(net));
   net->train_ready = true;
   return DY_OK;
 }
@@ -1477,6 +1581,195 @@ static int train_backward_layer(dy_net* net, int n, int B, float* grad_flat, cud
   return DY_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Training step on the tensor-core engine (precision = bf16): bf16 operands and activations, fp32
+// accumulation, fp32 master weights / BN statistics / gradients / Adam.  See train_tc.cuh.
+// ---------------------------------------------------------------------------------------------
+static int repack_tc(dy_net* net, int n, cudaStream_t st) {
+  LayerState& s = net->L[n];
+  const LayerDef& d = s.def;
+  if (s.unlocked) {
+    note_launch();
+    DY_TRY(launch_pack_fwd_bf16(s.d_w_f32, s.K, d.cout, s.cout_pad, s.d_wpk, st));
+  }
+  const float* w = s.d_w_f32;
+  if (s.wdg0) {
+    note_launch();
+    DY_TRY(launch_pack_dgrad_bf16(w, d.k, d.cin0 + d.cin1, 0, d.cin0, d.cout, s.Cg, s.wdg0, st));
+  }
+  if (s.wdg1) {
+    note_launch();
+    DY_TRY(launch_pack_dgrad_bf16(w, d.k, d.cin0 + d.cin1, d.cin0, d.cin1, d.cout, s.Cg, s.wdg1, st));
+  }
+  return DY_OK;
+}
+
+static int train_init_tc(dy_net* net) {
+  auto& L = net->L;
+  const int B = net->cfg.max_batch;
+  // scratch: dz of the layer being differentiated, and its 2x2-pooled copy for concat consumers
+  size_t max_dz = 0, max_pool = 0;
+  for (int n = 1; n <= 82; ++n) {
+    const LayerState& s = L[n];
+    const LayerDef& d = s.def;
+    if (!s.in_bwd) continue;
+    const size_t rows_pad = (size_t)B * (d.H + 1) * (d.H + 1) + 64;
+    if (d.bn && rows_pad * d.cout > max_dz) max_dz = rows_pad * d.cout;
+    if (d.src1 > 0 && L[d.src1].in_bwd) {
+      const size_t rp = (size_t)B * (d.H / 2 + 1) * (d.H / 2 + 1) + 64;
+      if (rp * s.Cg > max_pool) max_pool = rp * s.Cg;
+    }
+  }
+  DY_TRY(dev_alloc(net, (void**)&net->dzb_scratch, max_dz * 2));
+  DY_TRY(dev_alloc(net, (void**)&net->pool_scratch, max_pool * 2));
+  // Backward visits layers 82 -> 1; inside a layer the order is shortcut, src0, src1.  The first
+  // writer of a gradient buffer overwrites it, every later one accumulates through the conv
+  // kernel's residual input (in place: each tile reads its residual before it stores).
+  std::vector<char> written(83, 0);
+  for (int n = 82; n >= 1; --n) {
+    LayerState& s = L[n];
+    const LayerDef& d = s.def;
+    if (!s.in_bwd) continue;
+    const long long rows_max = (long long)B * (d.H + 1) * (d.H + 1);
+    const __nv_bfloat16* dz = d.bn ? net->dzb_scratch : s.dyb;
+    if (d.res > 0 && L[d.res].in_bwd) {
+      s.res_acc = written[d.res] != 0;
+      written[d.res] = 1;
+    }
+    if (d.bn) {      // forward: z = conv(x), identity epilogue
+      TcConvDesc c;
+      c.a0 = L[d.src0].same;
+      c.a1 = d.src1 > 0 ? L[d.src1].up : nullptr;
+      DY_CHECK(c.a0 != nullptr && (d.src1 == 0 || c.a1 != nullptr), "layer input buffer missing");
+      c.cin0 = d.cin0; c.cin1 = d.cin1; c.cout = d.cout; c.k = d.k; c.s = 1; c.H = c.W = d.H; c.max_batch = B;
+      c.wpk = s.d_wpk; c.cout_pad = s.cout_pad; c.scale = net->ones_dev; c.shift = net->zeros_dev; c.act = 0;
+      c.alpha = net->cfg.alpha;
+      c.out[0] = OutDesc{s.zb, OUT_SAME, d.cout};
+      c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
+      DY_TRY(build_tc_plan(c, net->num_sms, &s.plan_z));
+    }
+    if (s.unlocked) {
+      DY_TRY(build_wgrad_plan(L[d.src0].same, d.cin0, d.src1 > 0 ? L[d.src1].up : nullptr, d.cin1, dz, s.Cg, d.cout,
+                              d.k, d.H, d.H, rows_max, nullptr, &s.plan_wg));
+    }
+    if (d.src0 > 0 && L[d.src0].in_bwd) {
+      LayerState& t = L[d.src0];
+      DY_CHECK(t.Cg == d.cin0, "producer gradient width");
+      s.dg0 = true;
+      DY_TRY(dev_alloc(net, (void**)&s.wdg0, (size_t)d.cin0 * d.k * d.k * s.Cg * 2));
+      TcConvDesc c;
+      c.a0 = dz; c.cin0 = s.Cg; c.cout = d.cin0; c.k = d.k; c.s = 1; c.H = c.W = d.H; c.max_batch = B;
+      c.wpk = s.wdg0; c.cout_pad = d.cin0; c.scale = net->ones_dev; c.shift = net->zeros_dev; c.act = 0;
+      c.alpha = net->cfg.alpha;
+      c.residual = written[d.src0] ? t.dyb : nullptr;
+      c.out[0] = OutDesc{t.dyb, OUT_SAME, d.cin0};
+      c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
+      DY_TRY(build_tc_plan(c, net->num_sms, &s.plan_dg0));
+      written[d.src0] = 1;
+    }
+    if (d.src1 > 0 && L[d.src1].in_bwd) {
+      LayerState& t = L[d.src1];
+      DY_CHECK(t.Cg == d.cin1 && d.k == 1, "concat branch gradient width");
+      s.dg1 = true;
+      DY_TRY(dev_alloc(net, (void**)&s.wdg1, (size_t)d.cin1 * s.Cg * 2));
+      TcConvDesc c;      // 1x1 dgrad at the LOW resolution on the 2x2-pooled dz (pooling commutes with a 1x1 conv)
+      c.a0 = net->pool_scratch; c.cin0 = s.Cg; c.cout = d.cin1; c.k = 1; c.s = 1; c.H = c.W = d.H / 2; c.max_batch = B;
+      c.wpk = s.wdg1; c.cout_pad = d.cin1; c.scale = net->ones_dev; c.shift = net->zeros_dev; c.act = 0;
+      c.alpha = net->cfg.alpha;
+      c.residual = written[d.src1] ? t.dyb : nullptr;
+      c.out[0] = OutDesc{t.dyb, OUT_SAME, d.cin1};
+      c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
+      DY_TRY(build_tc_plan(c, net->num_sms, &s.plan_dg1));
+      written[d.src1] = 1;
+    }
+    DY_TRY(repack_tc(net, n, 0));
+  }
+  DY_CUDA(cudaDeviceSynchronize());
+  return DY_OK;
+}
+
+static int train_forward_layer_tc(dy_net* net, int n, const float* images, int B, cudaStream_t st) {
+  auto& L = net->L;
+  LayerState& s = L[n];
+  const LayerDef& d = s.def;
+  if (n == 1) {
+    note_launch();
+    return launch_conv1(images, s.d_w_f32, s.d_scale, s.d_shift, net->cfg.alpha, B, net->S, net->S, s.s2d, s.same,
+                        g_opt_conv1_tc != 0, net->num_sms, st);
+  }
+  // frozen prefix and the biased linear convs (bias lives in d_shift): the inference plan
+  if (!s.in_bwd || !d.bn) return run_tc_plan(s.plan, B, net->num_sms, st);
+  DY_TRY(run_tc_plan(s.plan_z, B, net->num_sms, st));
+  const long long rows = (long long)B * (d.H + 1) * (d.H + 1);
+  const long long M = (long long)B * d.H * d.H;
+  note_launch(3);
+  if (s.unlocked) {
+    DY_CUDA(cudaMemsetAsync(s.stat, 0, (size_t)4 * d.cout * 8, st));
+    DY_TRY(launch_bn_stats_p1(s.zb, rows, d.cout, s.stat, s.stat + d.cout, st));
+    DY_TRY(launch_bn_finalize(s.stat, s.stat + d.cout, M, d.cout, s.d_gamma, s.d_beta, net->cfg.bn_eps, s.bn_a,
+                              s.bn_b, s.bmean, s.bvar, s.binvstd, st));
+  } else {
+    DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, d.cout, s.bn_a, s.bn_b, st));
+  }
+  return launch_bn_act_p1(s.zb, s.bn_a, s.bn_b, d.res > 0 ? L[d.res].same : nullptr, B, d.H, d.H, d.cout,
+                          net->cfg.alpha, 1, s.same, s.up, st);
+}
+
+static int train_backward_layer_tc(dy_net* net, int n, int B, float* grad_flat, cudaStream_t st) {
+  auto& L = net->L;
+  LayerState& s = L[n];
+  const LayerDef& d = s.def;
+  if (!s.in_bwd) return DY_OK;
+  const long long rows = (long long)B * (d.H + 1) * (d.H + 1);
+  const long long M = (long long)B * d.H * d.H;
+  const int C = d.cout;
+  double* s1 = s.stat + 2 * C;
+  double* s2 = s.stat + 3 * C;
+  if (d.res > 0 && L[d.res].in_bwd) {      // y = leaky(bn(conv)) + shortcut  ->  d shortcut (+)= dy
+    note_launch();
+    if (s.res_acc) DY_TRY(launch_add_p1(L[d.res].dyb, s.dyb, rows * C, st));
+    else DY_TRY(launch_copy_p1(L[d.res].dyb, s.dyb, rows * C, st));
+  }
+  if (d.bn) {
+    if (s.unlocked) {
+      DY_CUDA(cudaMemsetAsync(s1, 0, (size_t)2 * C * 8, st));
+      DY_TRY(launch_bn_bwd_reduce_p1(s.dyb, s.zb, s.bn_a, s.bn_b, s.bmean, s.binvstd, net->cfg.alpha, 1, rows, C, s1,
+                                     s2, st));
+      DY_TRY(launch_copy_stats_to_grads(s1, s2, C, grad_flat + s.off_g, grad_flat + s.off_b, st));
+      DY_TRY(launch_bn_bwd_apply_p1(s.dyb, s.zb, s.bn_a, s.bn_b, s.bmean, s.binvstd, s.d_gamma, s1, s2,
+                                    net->cfg.alpha, 1, 0, B, d.H, d.H, C, net->dzb_scratch, st));
+    } else {
+      DY_TRY(launch_bn_bwd_apply_p1(s.dyb, s.zb, s.bn_a, s.bn_b, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                    net->cfg.alpha, 1, 1, B, d.H, d.H, C, net->dzb_scratch, st));
+    }
+    note_launch(3);
+  } else {
+    // biased linear conv: dz = dy (the loss kernels wrote it in fp32 NHWC); d bias = column sums
+    DY_TRY(launch_f32_to_p1(s.dyf, B, d.H, d.H, C, s.dyb, s.Cg, st));
+    note_launch();
+    if (s.unlocked) {
+      DY_CUDA(cudaMemsetAsync(s1, 0, (size_t)C * 8, st));
+      DY_TRY(launch_bn_stats(s.dyf, M, C, s1, nullptr, st));
+      DY_TRY(launch_copy_stats_to_grads(s1, s1, C, nullptr, grad_flat + s.off_b, st));
+      note_launch(2);
+    }
+  }
+  if (s.unlocked) {
+    DY_CUDA(cudaMemsetAsync(grad_flat + s.off_w, 0, (size_t)s.K * C * 4, st));
+    s.plan_wg.p.dw = grad_flat + s.off_w;
+    note_launch();
+    DY_TRY(run_wgrad_plan(s.plan_wg, B, d.H, d.H, net->num_sms, st));
+  }
+  if (s.dg0) DY_TRY(run_tc_plan(s.plan_dg0, B, net->num_sms, st));
+  if (s.dg1) {
+    note_launch();
+    DY_TRY(launch_pool2x2_p1(d.bn ? net->dzb_scratch : s.dyb, B, d.H / 2, d.H / 2, s.Cg, net->pool_scratch, st));
+    DY_TRY(run_tc_plan(s.plan_dg1, B, net->num_sms, st));
+  }
+  return DY_OK;
+}
+
 }  // namespace dy
 
 extern "C" {
@@ -1508,9 +1801,17 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
   cudaStream_t st = (cudaStream_t)stream;
   auto& L = net->L;
-  for (int n = 1; n <= 82; ++n) DY_TRY(train_forward_layer(net, n, images_dev, B, st));
-  for (int n = 1; n <= 82; ++n)
-    if (L[n].in_bwd) DY_CUDA(cudaMemsetAsync(L[n].dy, 0, out_elems(L[n].def, B) * 4, st));
+  const bool tc = net->cfg.precision == DY_PRECISION_BF16;
+  if (tc) {
+    for (int n = 1; n <= 82; ++n) DY_TRY(train_forward_layer_tc(net, n, images_dev, B, st));
+    // only the loss kernels' fp32 targets need clearing: every bf16 gradient buffer is fully rewritten
+    for (int n = 1; n <= 82; ++n)
+      if (L[n].dyf) DY_CUDA(cudaMemsetAsync(L[n].dyf, 0, out_elems(L[n].def, B) * 4, st));
+  } else {
+    for (int n = 1; n <= 82; ++n) DY_TRY(train_forward_layer(net, n, images_dev, B, st));
+    for (int n = 1; n <= 82; ++n)
+      if (L[n].in_bwd) DY_CUDA(cudaMemsetAsync(L[n].dy, 0, out_elems(L[n].def, B) * 4, st));
+  }
   DY_CUDA(cudaMemsetAsync(net->loss_acc, 0, 8 * 8, st));
   // detection loss + gradient into the three head maps
   YoloLossArgs ya;
@@ -1519,7 +1820,7 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   const float* labs[3] = {yolo3_dev, yolo2_dev, yolo1_dev};
   for (int j = 0; j < 3; ++j) {
     DY_CHECK(L[heads[j]].in_bwd, "detection heads must be trainable");
-    ya.pred[j] = L[heads[j]].f32; ya.label[j] = labs[j]; ya.dpred[j] = L[heads[j]].dy;
+    ya.pred[j] = L[heads[j]].f32; ya.label[j] = labs[j]; ya.dpred[j] = tc ? L[heads[j]].dyf : L[heads[j]].dy;
     ya.g[j] = L[heads[j]].def.H;
   }
   ya.B = B; ya.net = 32 * ya.g[2];
@@ -1536,7 +1837,9 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   memset(&ma, 0, sizeof(ma));
   DY_CHECK(L[82].in_bwd, "the mask subnet must be trainable");
   ma.det = net->det_raw_ws; ma.true_boxes = true_boxes_dev; ma.true_masks = true_masks_dev;
-  ma.perm_prop = perm_prop_dev; ma.perm_gt = perm_gt_dev; ma.mask_pos = L[82].f32; ma.dmask = L[82].dy;
+  ma.perm_prop = perm_prop_dev; ma.perm_gt = perm_gt_dev; ma.mask_pos = L[82].f32;
+  ma.dmask = tc ? L[82].dyf : L[82].dy;
+  ma.mp_planar = tc ? 1 : 0;           // the bf16 engine keeps the score maps planar [B,kk,S,S]
   ma.B = B; ma.max_det = net->cfg.max_detection; ma.S = net->S / 2; ma.H = net->S; ma.k = net->cfg.k_map;
   ma.mask_scale = 5.f; ma.iou_thresh = 0.5f;
   ma.rois = net->mask_rois; ma.assign = net->mask_assign; ma.npos = net->mask_npos;
@@ -1564,7 +1867,11 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
 int dy_train_backward(dy_net* net, int32_t B, int32_t layer_hi, int32_t layer_lo, float* grad_flat_dev, void* stream) {
   DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
   DY_CHECK(layer_lo >= 1 && layer_hi <= 82 && layer_lo <= layer_hi, "layer range");
-  for (int n = layer_hi; n >= layer_lo; --n) DY_TRY(train_backward_layer(net, n, B, grad_flat_dev, (cudaStream_t)stream));
+  const bool tc = net->cfg.precision == DY_PRECISION_BF16;
+  for (int n = layer_hi; n >= layer_lo; --n) {
+    if (tc) DY_TRY(train_backward_layer_tc(net, n, B, grad_flat_dev, (cudaStream_t)stream));
+    else DY_TRY(train_backward_layer(net, n, B, grad_flat_dev, (cudaStream_t)stream));
+  }
   return DY_OK;
 }
 
@@ -1595,6 +1902,8 @@ int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad
                          kAdamB1, kAdamB2, kAdamEps, kL2, grad_scale, st));
       DY_CUDA(cudaMemcpyAsync(s.d_shift, s.d_bias, C * 4, cudaMemcpyDeviceToDevice, st));
     }
+    // tensor-core engine: refresh the bf16 GEMM operands (forward and dgrad) from the fp32 master weights
+    if (net->cfg.precision == DY_PRECISION_BF16) DY_TRY(repack_tc(net, n, st));
   }
   return DY_OK;
 }
@@ -1602,6 +1911,16 @@ int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad
 int dy_train_get_tensor(dy_net* net, int32_t layer, int32_t which, int32_t B, float* out_dev, void* stream) {
   DY_CHECK(net && net->train_ready && out_dev && layer >= 1 && layer <= 82, "bad argument");
   const LayerState& s = net->L[layer];
+  if (net->cfg.precision == DY_PRECISION_BF16) {
+    const LayerDef& d = s.def;
+    if (which != 0 && s.dyf) {
+      DY_CUDA(cudaMemcpyAsync(out_dev, s.dyf, out_elems(d, B) * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      return DY_OK;
+    }
+    const __nv_bfloat16* src16 = which == 0 ? s.zb : s.dyb;
+    DY_CHECK(src16 != nullptr && s.Cg == d.cout, "layer has no such training tensor");
+    return launch_p1_to_nhwc(src16, out_dev, B, d.H, d.H, d.cout, FORM_SAME, (cudaStream_t)stream);
+  }
   const float* src = which == 0 ? s.z : s.dy;
   DY_CHECK(src != nullptr, "layer does not take part in the backward pass");
   DY_CUDA(cudaMemcpyAsync(out_dev, src, out_elems(s.def, B) * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

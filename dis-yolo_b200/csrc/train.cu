@@ -481,7 +481,9 @@ __global__ void __launch_bounds__(kT) mask_loss_kernel(MaskLossArgs a) {
         if (x >= gx[j]) bx = j;
       }
       const long long e = (((long long)b * a.S + y) * a.S + x) * kk + by * a.k + bx;
-      const float l = a.mask_pos[e];
+      const float l = a.mp_planar
+                          ? a.mask_pos[(((long long)b * kk + by * a.k + bx) * a.S + y) * a.S + x]
+                          : a.mask_pos[e];
       const float t = gm[(long long)(y * f) * a.H + x * f] ? 1.f : 0.f;
       part += (double)(fmaxf(l, 0.f) - l * t + log1pf(expf(-fabsf(l))));
       atomicAdd(a.dmask + e, wgt * (1.f / (1.f + expf(-l)) - t));

@@ -64,7 +64,8 @@ struct MaskLossArgs {
   const unsigned char* true_masks;   // [B,20,H,W] bool
   const int* perm_prop;     // [B,max_det] permutation standing in for tf.random_shuffle (:782)
   const int* perm_gt;       // [B,20]                                                 (:781)
-  const float* mask_pos;    // [B,S,S,kk] logits (NHWC)
+  const float* mask_pos;    // [B,S,S,kk] logits (NHWC), or planar [B,kk,S,S] when mp_planar
+  int mp_planar;
   float* dmask;             // [B,S,S,kk] gradient (accumulated with atomics; zero on entry)
   int B, max_det, S, H, k;
   float mask_scale, iou_thresh;

@@ -1,0 +1,646 @@
+// Training step on the tensor-core engine: wgrad tcgen05 kernel, bf16 P1 BatchNorm / activation /
+// pooling kernels, weight repacking (see train_tc.cuh).
+#include "train_tc.cuh"
+
+#include "conv_tc.cuh"
+
+namespace dy {
+
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(f[0], f[1]); q.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[2], f[3]); q.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[4], f[5]); q.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[6], f[7]); q.w = *reinterpret_cast<uint32_t*>(&h);
+  return q;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 u = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w; f[4] = v.x; f[5] = v.y; f[6] = v.z; f[7] = v.w;
+}
+
+static int grid_for(long long total, int cap = 148 * 8) {
+  long long g = (total + kT - 1) / kT;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// -------------------------------------------------------------------------------------------
+// per-channel reductions over a P1 matrix [rows, C]: thread (tx, ty) owns the 8 channels of vector
+// column tx for rows ty, ty+R, ...; fp32 partial sums are flushed to double every 32 rows
+// -------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kT)
+p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ z,
+                 const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
+                 const float* __restrict__ invstd, float alpha, int act, long long rows, int C, int rows_per_block,
+                 double* __restrict__ o1, double* __restrict__ o2) {
+  __shared__ double sm[16 * kT];
+  const int cv = C >> 3;
+  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv, R = kT / cv;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  double d1[8], d2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d1[j] = d2[j] = 0.0;
+  float fa[8], fb[8], fm[8], fi[8];
+  if (BWD && ty < R) {
+    load8f(a + tx * 8, fa);
+    load8f(b + tx * 8, fb);
+    load8f(mean + tx * 8, fm);
+    load8f(invstd + tx * 8, fi);
+  }
+  if (ty < R) {
+    long long r = r0 + ty;
+    while (r < r1) {
+      float p1[8], p2[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p1[j] = p2[j] = 0.f;
+      for (int it = 0; it < 32 && r < r1; ++it, r += R) {
+        float fu[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(u + r * C) + tx), fu);
+        if (BWD) {
+          float fz[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C) + tx), fz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g = fu[j];
+            if (act && !(fmaf(fz[j], fa[j], fb[j]) > 0.f)) g *= alpha;
+            p1[j] += g;
+            p2[j] += g * ((fz[j] - fm[j]) * fi[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            p1[j] += fu[j];
+            p2[j] += fu[j] * fu[j];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d1[j] += (double)p1[j];
+        d2[j] += (double)p2[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sm[j * kT + threadIdx.x] = d1[j];
+    sm[(8 + j) * kT + threadIdx.x] = d2[j];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 16 * cv; o += kT) {
+    const int j = o / cv, x = o - j * cv;
+    double t = 0.0;
+    for (int r = 0; r < R; ++r) t += sm[j * kT + r * cv + x];
+    const int ch = x * 8 + (j & 7);
+    if (j < 8) atomicAdd(o1 + ch, t);
+    else if (o2) atomicAdd(o2 + ch, t);
+  }
+}
+
+__device__ __forceinline__ bool p1_pixel(long long r, int Hp, int Wp, int H, int W, int* n, int* y, int* x) {
+  const long long t = r / Wp;
+  *x = (int)(r - t * Wp);
+  *n = (int)(t / Hp);
+  *y = (int)(t - (long long)(*n) * Hp);
+  return *x < W && *y < H;
+}
+
+__global__ void __launch_bounds__(kT)
+bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
+                 const __nv_bfloat16* __restrict__ residual, long long rows, int H, int W, int C, float alpha, int act,
+                 __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up) {
+  const int cv = C >> 3, Hp = H + 1, Wp = W + 1;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long r = i / cv;
+    const int v = (int)(i - r * cv);
+    int n, y, x;
+    if (!p1_pixel(r, Hp, Wp, H, W, &n, &y, &x)) continue;
+    float fz[8], fa[8], fb[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C) + v), fz);
+    load8f(a + v * 8, fa);
+    load8f(b + v * 8, fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(fz[j], fa[j], fb[j]);
+      if (act) t = fmaxf(alpha * t, t);
+      fz[j] = t;
+    }
+    if (residual) {
+      float fr[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(residual + r * C) + v), fr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fz[j] += fr[j];
+    }
+    const uint4 q = pack8(fz);
+    if (out_same) reinterpret_cast<uint4*>(out_same + r * C)[v] = q;
+    if (out_up) {
+      const long long Wu = 2 * W + 1, Hu = 2 * H + 1;
+      const long long ru = ((long long)n * Hu + 2 * y) * Wu + 2 * x;
+      reinterpret_cast<uint4*>(out_up + ru * C)[v] = q;
+      reinterpret_cast<uint4*>(out_up + (ru + 1) * C)[v] = q;
+      reinterpret_cast<uint4*>(out_up + (ru + Wu) * C)[v] = q;
+      reinterpret_cast<uint4*>(out_up + (ru + Wu + 1) * C)[v] = q;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                       const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ gamma,
+                       const double* __restrict__ s1, const double* __restrict__ s2, float alpha, int act, int mode,
+                       long long rows, long long rows_out, long long mvalid, int H, int W, int C,
+                       __nv_bfloat16* __restrict__ dz) {
+  const int cv = C >> 3, Hp = H + 1, Wp = W + 1;
+  const long long total = rows_out * cv;
+  const float invM = 1.f / (float)mvalid;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long r = i / cv;
+    const int v = (int)(i - r * cv);
+    int n, y, x;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (r < rows && p1_pixel(r, Hp, Wp, H, W, &n, &y, &x)) {
+      float fg[8], fz[8], fa[8], fb[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C) + v), fg);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C) + v), fz);
+      load8f(a + v * 8, fa);
+      load8f(b + v * 8, fb);
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(fmaf(fz[j], fa[j], fb[j]) > 0.f)) fg[j] *= alpha;
+      }
+      if (mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fg[j] *= fa[j];
+      } else {
+        float fm[8], fi[8], fgm[8];
+        load8f(mean + v * 8, fm);
+        load8f(invstd + v * 8, fi);
+        load8f(gamma + v * 8, fgm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (fz[j] - fm[j]) * fi[j];
+          fg[j] = fgm[j] * fi[j] * (fg[j] - (float)s1[v * 8 + j] * invM - xh * (float)s2[v * 8 + j] * invM);
+        }
+      }
+      q = pack8(fg);
+    }
+    reinterpret_cast<uint4*>(dz + r * C)[v] = q;
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+f32_to_p1_kernel(const float* __restrict__ src, long long rows, long long rows_out, int H, int W, int C, int Cg,
+                 __nv_bfloat16* __restrict__ dst) {
+  const int cv = Cg >> 3, Hp = H + 1, Wp = W + 1;
+  const long long total = rows_out * cv;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long r = i / cv;
+    const int v = (int)(i - r * cv);
+    int n, y, x;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (r < rows && p1_pixel(r, Hp, Wp, H, W, &n, &y, &x)) {
+      const float* s = src + (((long long)n * H + y) * W + x) * C;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (v * 8 + j < C) ? __ldg(s + v * 8 + j) : 0.f;
+      q = pack8(f);
+    }
+    reinterpret_cast<uint4*>(dst + r * Cg)[v] = q;
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+pool2x2_p1_kernel(const __nv_bfloat16* __restrict__ src, long long rows, long long rows_out, int h, int w, int C,
+                  __nv_bfloat16* __restrict__ dst) {
+  const int cv = C >> 3, Hp = h + 1, Wp = w + 1;
+  const long long total = rows_out * cv;
+  const long long Wu = 2 * w + 1, Hu = 2 * h + 1;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long r = i / cv;
+    const int v = (int)(i - r * cv);
+    int n, y, x;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (r < rows && p1_pixel(r, Hp, Wp, h, w, &n, &y, &x)) {
+      const long long ru = ((long long)n * Hu + 2 * y) * Wu + 2 * x;
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + ru * C) + v), f0);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + (ru + 1) * C) + v), f1);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + (ru + Wu) * C) + v), f2);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + (ru + Wu + 1) * C) + v), f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f0[j] = (f0[j] + f1[j]) + (f2[j] + f3[j]);
+      q = pack8(f0);
+    }
+    reinterpret_cast<uint4*>(dst + r * C)[v] = q;
+  }
+}
+
+__global__ void add_p1_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, long long nvec,
+                              int copy) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 s = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    if (copy) {
+      reinterpret_cast<uint4*>(dst)[i] = s;
+    } else {
+      float fd[8], fs[8];
+      unpack8(reinterpret_cast<const uint4*>(dst)[i], fd);
+      unpack8(s, fs);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fd[j] += fs[j];
+      reinterpret_cast<uint4*>(dst)[i] = pack8(fd);
+    }
+  }
+}
+
+// [K][cout] fp32 -> [cout_pad][K] bf16 through a 32x32 smem tile (both sides coalesced)
+__global__ void pack_fwd_kernel(const float* __restrict__ w, int K, int cout, int cout_pad,
+                                __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int kk = k0 + i, co = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (kk < K && co < cout) ? w[(size_t)kk * cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int co = c0 + i, kk = k0 + threadIdx.x;
+    if (co < cout_pad && kk < K) out[(size_t)co * K + kk] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, int k, int cin_total, int ci0, int cin_sel, int cout,
+                                  int Cg, __nv_bfloat16* __restrict__ out) {
+  const int kk = k * k;
+  const long long total = (long long)cin_sel * kk * Cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cg);
+    const long long t = i / Cg;
+    const int tp = (int)(t % kk);
+    const int ci = (int)(t / kk);
+    float v = 0.f;
+    if (co < cout) v = w[((size_t)(kk - 1 - tp) * cin_total + ci0 + ci) * cout + co];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// wgrad: one CTA per (tap, 128-input-channel block, N tile, K split).  256 threads:
+//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue.
+// Stage = A [128 channels x 64 pixel rows] + B [block_n channels x 64 pixel rows], both exactly as
+// TMA delivers the forward's activation boxes: channel-contiguous rows, 128B/64B swizzle.  For the
+// MMA these are MN-major operands: "leading" offset = distance between two 64-(32-)channel boxes,
+// "stride" offset = 8 pixel rows; one K=16 step advances the start address by 16 rows.
+// -------------------------------------------------------------------------------------------
+constexpr int kWgradRows = 64;     // pixel rows (K) per pipeline stage
+constexpr int kWgradMaxStages = 6;
+
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+__global__ void __launch_bounds__(kT, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
+                const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ WgradParams p, int dbg_lbo_a,
+                int dbg_sbo_a, int dbg_lbo_b, int dbg_sbo_b) {
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[kWgradMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kWgradMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- which unit of work ----
+  int u = blockIdx.x;
+  const int ks = u % p.ksplit; u /= p.ksplit;
+  const int nt = u % p.n_tiles_n; u /= p.n_tiles_n;
+  const int blk_total = p.src_blk[0] + (p.nsrc > 1 ? p.src_blk[1] : 0);
+  const int cb = u % blk_total;
+  const int tap = u / blk_total;
+  const int src = cb >= p.src_blk[0] ? 1 : 0;
+  const int ci0 = (src ? cb - p.src_blk[0] : cb) * 128;
+  const int c_src = p.src_c[src], aw = p.src_aw[src];
+  const int a_valid = ((c_src - ci0 < 128) ? (c_src - ci0) : 128) / aw;     // boxes holding real channels
+  const int b_boxes = p.block_n / p.z_aw;
+  const int n0 = nt * p.block_n;
+  const int c_begin = ks * p.chunks_per_split;
+  int c_end = c_begin + p.chunks_per_split;
+  if (c_end > p.total_chunks) c_end = p.total_chunks;
+  const int nchunks = c_end - c_begin;
+
+  const uint32_t a_box = (uint32_t)kWgradRows * aw * 2;          // bytes of one A box
+  const uint32_t b_box = (uint32_t)kWgradRows * p.z_aw * 2;
+  const uint32_t a_bytes = 128u * kWgradRows * 2;                // 16 KB: all 128 channels
+  const uint32_t stage_bytes = a_bytes + (uint32_t)p.block_n * kWgradRows * 2;
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+  // channels beyond the source's extent are never loaded: their A rows must read as zero
+  if (a_valid * aw < 128) {
+    uint4* q = reinterpret_cast<uint4*>(smem_gen);
+    const int nvec = (int)((uint32_t)p.num_stages * stage_bytes / 16);
+    for (int i = threadIdx.x; i < nvec; i += kT) q[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(src ? &mapX1 : &mapX0);
+    tma_prefetch_desc(&mapZ);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_smem, 256u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (elect_one() && nchunks > 0) {
+      const CUtensorMap* xm = src ? &mapX1 : &mapX0;
+      const uint32_t tx = (uint32_t)a_valid * a_box + (uint32_t)b_boxes * b_box;
+      const int shift = p.tap_shift[tap];
+      uint32_t stage = 0, phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_expect_tx(&full_bar[stage], tx);
+        uint8_t* sa = smem_gen + (size_t)stage * stage_bytes;
+        const int row = c * kWgradRows;
+        for (int j = 0; j < a_valid; ++j) tma_load_2d(sa + (size_t)j * a_box, xm, &full_bar[stage], ci0 + j * aw, row + shift);
+        for (int j = 0; j < b_boxes; ++j)
+          tma_load_2d(sa + a_bytes + (size_t)j * b_box, &mapZ, &full_bar[stage], n0 + j * p.z_aw, row);
+        if (++stage == (uint32_t)p.num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one() && nchunks > 0) {
+      // instruction descriptor: bf16 x bf16 -> fp32, M=128, N=block_n, A and B MN-major (bits 15, 16)
+      const uint32_t idesc = umma_idesc_bf16(p.block_n) | (1u << 15) | (1u << 16);
+      const uint32_t lay_a = aw == 64 ? 2u : 4u, lay_b = p.z_aw == 64 ? 2u : 4u;
+      const uint32_t lbo_a = dbg_lbo_a ? (uint32_t)dbg_lbo_a : a_box, sbo_a = dbg_sbo_a ? (uint32_t)dbg_sbo_a : 8u * aw * 2;
+      const uint32_t lbo_b = dbg_lbo_b ? (uint32_t)dbg_lbo_b : b_box, sbo_b = dbg_sbo_b ? (uint32_t)dbg_sbo_b : 8u * p.z_aw * 2;
+      const uint32_t kstep_a = 16u * aw * 2, kstep_b = 16u * p.z_aw * 2;   // 16 pixel rows
+      uint32_t stage = 0, phase = 0, acc = 0u;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+        for (int k = 0; k < kWgradRows / 16; ++k) {
+          const uint64_t adesc = mn_desc(sa + k * kstep_a, lbo_a, sbo_a, lay_a);
+          const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep_b, lbo_b, sbo_b, lay_b);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
+          acc = 1u;
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == (uint32_t)p.num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(&tfull_bar);
+    }
+  } else if (warp >= 4 && nchunks > 0) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // input channel inside the block == TMEM lane
+    const bool valid = ci0 + row < c_src;
+    float* drow = p.dw + ((size_t)tap * p.cin_total + p.src_koff[src] + ci0 + row) * p.cout;
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t r[16];
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      tmem_ld16(taddr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = n0 + c0 + j;
+          if (co < p.cout) atomicAdd(drow + co, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256u);
+  }
+}
+
+int g_wdbg[4] = {0, 0, 0, 0};
+
+}  // namespace
+
+void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
+  g_wdbg[0] = lbo_a; g_wdbg[1] = sbo_a; g_wdbg[2] = lbo_b; g_wdbg[3] = sbo_b;
+}
+
+int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* sum, double* sumsq, cudaStream_t st) {
+  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT, "channel count");
+  const int R = kT / (C / 8);
+  int rpb = R * 64;
+  long long blocks = (rows + rpb - 1) / rpb;
+  if (blocks > 148 * 4) {
+    blocks = 148 * 4;
+    rpb = (int)((rows + blocks - 1) / blocks);
+  }
+  p1_reduce_kernel<false><<<(int)blocks, kT, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0, rows, C,
+                                                      rpb, sum, sumsq);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
+                            const float* mean, const float* invstd, float alpha, int act, long long rows, int C,
+                            double* s1, double* s2, cudaStream_t st) {
+  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT, "channel count");
+  const int R = kT / (C / 8);
+  int rpb = R * 64;
+  long long blocks = (rows + rpb - 1) / rpb;
+  if (blocks > 148 * 4) {
+    blocks = 148 * 4;
+    rpb = (int)((rows + blocks - 1) / blocks);
+  }
+  p1_reduce_kernel<true><<<(int)blocks, kT, 0, st>>>(dy, z, a, b, mean, invstd, alpha, act, rows, C, rpb, s1, s2);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, const __nv_bfloat16* residual, int B,
+                     int H, int W, int C, float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up,
+                     cudaStream_t st) {
+  DY_CHECK(C % 8 == 0, "channel count");
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  bn_act_p1_kernel<<<grid_for(rows * (C / 8)), kT, 0, st>>>(z, a, b, residual, rows, H, W, C, alpha, act, out_same,
+                                                            out_up);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+static long long round_up64(long long r) { return (r + 63) / 64 * 64; }
+
+int launch_bn_bwd_apply_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
+                           const float* mean, const float* invstd, const float* gamma, const double* s1,
+                           const double* s2, float alpha, int act, int mode, int B, int H, int W, int C,
+                           __nv_bfloat16* dz, cudaStream_t st) {
+  DY_CHECK(C % 8 == 0, "channel count");
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  const long long ro = round_up64(rows);
+  bn_bwd_apply_p1_kernel<<<grid_for(ro * (C / 8)), kT, 0, st>>>(dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act,
+                                                                mode, rows, ro, (long long)B * H * W, H, W, C, dz);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_f32_to_p1(const float* src, int B, int H, int W, int C, __nv_bfloat16* dst, int Cg, cudaStream_t st) {
+  DY_CHECK(Cg % 8 == 0 && Cg >= C, "channel count");
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  const long long ro = round_up64(rows);
+  f32_to_p1_kernel<<<grid_for(ro * (Cg / 8)), kT, 0, st>>>(src, rows, ro, H, W, C, Cg, dst);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_pool2x2_p1(const __nv_bfloat16* src, int B, int h, int w, int C, __nv_bfloat16* dst, cudaStream_t st) {
+  DY_CHECK(C % 8 == 0, "channel count");
+  const long long rows = (long long)B * (h + 1) * (w + 1);
+  const long long ro = round_up64(rows);
+  pool2x2_p1_kernel<<<grid_for(ro * (C / 8)), kT, 0, st>>>(src, rows, ro, h, w, C, dst);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_add_p1(__nv_bfloat16* dst, const __nv_bfloat16* src, long long n, cudaStream_t st) {
+  DY_CHECK(n % 8 == 0, "element count");
+  add_p1_kernel<<<grid_for(n / 8), kT, 0, st>>>(dst, src, n / 8, 0);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_copy_p1(__nv_bfloat16* dst, const __nv_bfloat16* src, long long n, cudaStream_t st) {
+  DY_CHECK(n % 8 == 0, "element count");
+  add_p1_kernel<<<grid_for(n / 8), kT, 0, st>>>(dst, src, n / 8, 1);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_pack_fwd_bf16(const float* w, int K, int cout, int cout_pad, __nv_bfloat16* out, cudaStream_t st) {
+  dim3 grid((K + 31) / 32, (cout_pad + 31) / 32), block(32, 8);
+  pack_fwd_kernel<<<grid, block, 0, st>>>(w, K, cout, cout_pad, out);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_pack_dgrad_bf16(const float* w, int k, int cin_total, int ci0, int cin_sel, int cout, int Cg,
+                           __nv_bfloat16* out, cudaStream_t st) {
+  pack_dgrad_kernel<<<grid_for((long long)cin_sel * k * k * Cg), kT, 0, st>>>(w, k, cin_total, ci0, cin_sel, cout, Cg,
+                                                                               out);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, int c1, const __nv_bfloat16* dz,
+                     int zc, int cout, int k, int H, int W, long long rows_max, float* dw, WgradPlan* plan) {
+  DY_CHECK(k == 1 || k == 3, "kernel size");
+  DY_CHECK(c0 % 32 == 0 && c1 % 32 == 0 && zc % 32 == 0 && c0 > 0, "channel counts must be multiples of 32");
+  DY_CHECK(c1 == 0 || k == 1, "concat only feeds 1x1 convs");
+  DY_CHECK(cout <= zc, "dz must hold at least cout channels");
+  WgradParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.nsrc = c1 > 0 ? 2 : 1;
+  p.src_c[0] = c0; p.src_c[1] = c1;
+  p.src_aw[0] = c0 % 64 == 0 ? 64 : 32;
+  p.src_aw[1] = (c1 > 0 && c1 % 64 == 0) ? 64 : 32;
+  p.src_koff[0] = 0; p.src_koff[1] = c0;
+  p.src_blk[0] = (c0 + 127) / 128;
+  p.src_blk[1] = (c1 + 127) / 128;
+  p.ntap = k * k;
+  const int Wp = W + 1;
+  for (int kh = 0; kh < k; ++kh)
+    for (int kw = 0; kw < k; ++kw) p.tap_shift[kh * k + kw] = k == 3 ? (kh - 1) * Wp + (kw - 1) : 0;
+  p.cin_total = c0 + c1;
+  p.cout = cout;
+  p.zc = zc;
+  p.z_aw = zc % 64 == 0 ? 64 : 32;
+  p.block_n = zc >= 256 ? 256 : zc;          // zc in {32, 64, 128, 256, 512, 1024}
+  DY_CHECK(zc % p.block_n == 0 && p.block_n % p.z_aw == 0 && p.block_n % 16 == 0, "dz channel tiling");
+  p.n_tiles_n = zc / p.block_n;
+  const size_t stage = 128 * (size_t)kWgradRows * 2 + (size_t)p.block_n * kWgradRows * 2;
+  int ns = (int)((200 * 1024) / stage);
+  if (ns > kWgradMaxStages) ns = kWgradMaxStages;
+  p.num_stages = ns;
+  p.dw = dw;
+  DY_TRY(make_tmap_2d(&plan->x[0], x0, rows_max, c0, c0, p.src_aw[0], kWgradRows));
+  if (c1 > 0) DY_TRY(make_tmap_2d(&plan->x[1], x1, rows_max, c1, c1, p.src_aw[1], kWgradRows));
+  else plan->x[1] = plan->x[0];
+  DY_TRY(make_tmap_2d(&plan->z, dz, rows_max, zc, zc, p.z_aw, kWgradRows));
+  return DY_OK;
+}
+
+int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream_t st) {
+  WgradParams& p = plan.p;
+  const long long M = (long long)B * (H + 1) * (W + 1);
+  DY_CHECK(M < (1ll << 31) - 256, "too many rows");
+  p.M = (int)M;
+  p.total_chunks = (int)((M + kWgradRows - 1) / kWgradRows);
+  const int units = p.ntap * (p.src_blk[0] + (p.nsrc > 1 ? p.src_blk[1] : 0)) * p.n_tiles_n;
+  int ksplit = (2 * num_sms + units - 1) / units;
+  if (ksplit < 1) ksplit = 1;
+  // keep at least 8 chunks (512 pixel rows) per CTA so that the pipeline fill is amortised
+  const int max_split = (p.total_chunks + 7) / 8;
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  p.chunks_per_split = (p.total_chunks + ksplit - 1) / ksplit;
+  p.ksplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  const size_t stage = 128 * (size_t)kWgradRows * 2 + (size_t)p.block_n * kWgradRows * 2;
+  const size_t smem = (size_t)p.num_stages * stage + 1024;
+  static bool attr = false;
+  if (!attr) {
+    DY_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+    attr = true;
+  }
+  wgrad_tc_kernel<<<units * p.ksplit, kT, smem, st>>>(plan.x[0], plan.x[1], plan.z, p, g_wdbg[0], g_wdbg[1],
+                                                      g_wdbg[2], g_wdbg[3]);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+}  // namespace dy

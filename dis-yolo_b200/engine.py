@@ -254,7 +254,7 @@ class Engine(object):
                    'dy_forward_host_end')
         return raw, box, cnt, msk
 
-    # ---- training step (fp32 engine) ----------------------------------------------------------
+    # ---- training step (bf16 tensor-core engine or fp32 verification engine) ----------------------------------------------------------
     def train_init(self):
         """Allocate the training state; returns the number of trainable scalars."""
         _lib.check(self.lib.dy_train_init(self.h), 'dy_train_init')
@@ -273,11 +273,18 @@ class Engine(object):
         t = self.torch
         images = self._dev(images, t.float32)
         B = images.shape[0]
-        lab = [self._dev(np.ascontiguousarray(l, np.float32).reshape(B, -1), t.float32) for l in labels]
-        tb = self._dev(np.ascontiguousarray(true_boxes, np.float32).reshape(B, -1), t.float32)
-        tm = self._dev(np.ascontiguousarray(true_masks).astype(np.uint8), t.uint8)
-        pp = self._dev(np.ascontiguousarray(perm_prop, np.int32), t.int32)
-        pg = self._dev(np.ascontiguousarray(perm_gt, np.int32), t.int32)
+
+        def dev(x, np_dtype, dtype, flat=True):
+            # device tensors pass through untouched (inputs resident in HBM); host arrays are uploaded
+            if not isinstance(x, t.Tensor):
+                x = np.ascontiguousarray(x).astype(np_dtype, copy=False)
+            x = self._dev(x, dtype)
+            return x.reshape(B, -1) if flat else x
+        lab = [dev(l, np.float32, t.float32) for l in labels]
+        tb = dev(true_boxes, np.float32, t.float32)
+        tm = dev(true_masks, np.uint8, t.uint8, flat=False)
+        pp = dev(perm_prop, np.int32, t.int32, flat=False)
+        pg = dev(perm_gt, np.int32, t.int32, flat=False)
         if pp.shape != (B, self.max_detection) or pg.shape != (B, 20):
             raise ValueError('perm_prop must be [B,max_detection], perm_gt [B,20]')
         losses = np.zeros(8, np.float32)
@@ -413,3 +420,22 @@ def conv_layer(x, w, stride, scale, shift, act, alpha=0.1, residual=None, precis
                                      scale.ctypes.data_as(C.c_void_p), shift.ctypes.data_as(C.c_void_p),
                                      int(bool(act)), float(alpha), _ptr(residual), _ptr(out), st), 'dy_conv_layer')
     return out
+
+
+def conv_backward(x, dz, w, want_dx=True, want_dw=True):
+    """Backward of one stride-1 conv through the tensor-core training engine (dy_conv_backward).
+    x [B,H,W,cin], dz [B,H,W,cout] cuda fp32, w HWIO numpy -> (dx [B,H,W,cin], dw [k,k,cin,cout])."""
+    import torch
+    lib = _lib.lib()
+    _lib.require_gpu()
+    x, dz = x.contiguous().float(), dz.contiguous().float()
+    B, H, W, cin = x.shape
+    w = np.ascontiguousarray(w, np.float32)
+    k, cout = w.shape[0], w.shape[3]
+    dx = torch.empty_like(x) if want_dx else None
+    dw = torch.zeros((k, k, cin, cout), dtype=torch.float32, device=x.device) if want_dw else None
+    with torch.cuda.device(x.device):
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.dy_conv_backward(_ptr(x), _ptr(dz), B, H, W, cin, w.ctypes.data_as(C.c_void_p), k, cout,
+                                        _ptr(dx), _ptr(dw), st), 'dy_conv_backward')
+    return dx, dw

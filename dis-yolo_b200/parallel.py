@@ -66,7 +66,8 @@ class BucketedAllReduce(object):
 
 
 class DataParallelTrainer(object):
-    """engine: an fp32 Engine with load_weights() done.  Every rank must hold identical weights."""
+    """engine: an Engine (bf16 tensor-core or fp32) with load_weights() done.  Every rank must hold identical
+    weights."""
 
     def __init__(self, engine, bucket_mb=25, group=None):
         import torch

@@ -96,9 +96,10 @@ class YOLONet(object):
         self.evaluation = Handle('evaluation', 'fetch')
 
         if precision is None:
-            precision = 'fp32' if training else 'bf16'       # the training step runs on the fp32 engine
-        if training and precision != 'fp32':
-            raise ValueError('training=True needs precision="fp32" in this release')
+            # The tensor-core (bf16) training step differentiates layers 53..82 (the reference's stage 1:
+            # backbone locked, yolo3_net_pos.py:155-156); a net with unlocked backbone layers trains on
+            # the fp32 engine.
+            precision = 'bf16' if (not training or all(self.lock[:52])) else 'fp32'
         dev = int(cfg.GPU) if device is None else int(device)
         self.engine = Engine(image_size=self.image_size, max_batch=int(self.batchsize), precision=precision,
                              device=dev, anchors=self.anchors, num_classes=self.num_class, k_map=self.k,

@@ -23,6 +23,25 @@ IGNORE_THRESH = 0.5        # config.py:57
 L2_SCALE = 1e-4            # yolo3_net_pos.py:38
 MAX_BOX = 20               # config.py:69
 NP_DT = np.float32         # set to np.float64 to obtain a high-precision reference of the same graph
+EMULATE_BF16 = False       # True: round where the tensor-core engine stores bf16 (conv operands, z, y),
+                           # straight-through in the backward pass -- "identical inputs" oracle for the
+                           # mixed-precision training step (leaky masks then agree with the engine's)
+
+
+def _rb(x):
+    """bf16 round-to-nearest-even with a straight-through gradient."""
+    if not EMULATE_BF16:
+        return x
+    return x + (x.detach().float().bfloat16().to(x.dtype) - x.detach())
+
+
+# inputs of convolutional53..82: n -> (src0, src1); src1's output is 2x-upsampled and concatenated AFTER
+# src0's (yolo3_net_pos.py:258-412; concat order [skip, up], :291,326,387,402)
+TOPOLOGY_53_82 = {53: (52, 0), 54: (53, 0), 55: (54, 0), 56: (55, 0), 57: (56, 0), 58: (57, 0), 59: (58, 0),
+                  60: (57, 0), 61: (43, 60), 62: (61, 0), 63: (62, 0), 64: (63, 0), 65: (64, 0), 66: (65, 0),
+                  67: (66, 0), 68: (65, 0), 69: (26, 68), 70: (69, 0), 71: (70, 0), 72: (71, 0), 73: (72, 0),
+                  74: (73, 0), 75: (74, 0), 76: (73, 0), 77: (9, 76), 78: (77, 0), 79: (78, 0), 80: (4, 79),
+                  81: (80, 0), 82: (81, 0)}
 
 
 def _conv_same(x, w, stride):
@@ -33,7 +52,18 @@ def _conv_same(x, w, stride):
     return Fnn.conv2d(Fnn.pad(x, (pl, pr, pt, pb)), w.permute(3, 2, 0, 1), stride=stride)
 
 
-def forward_train(images, P, lock, stats_out=None, acts_out=None):
+def conv_backward(x, dz, w, stride=1):
+    """What TF's autodiff emits for tf.nn.conv2d (yolo3_net_pos.py:125,142): Conv2DBackpropInput and
+    Conv2DBackpropFilter.  x [B,H,W,cin], dz [B,Ho,Wo,cout], w HWIO (numpy) -> (dx NHWC, dw HWIO),
+    float64 on the CPU through torch.autograd of the same 'SAME'-padded convolution."""
+    xt = torch.from_numpy(np.ascontiguousarray(x, np.float64)).permute(0, 3, 1, 2).requires_grad_(True)
+    wt = torch.from_numpy(np.ascontiguousarray(w, np.float64)).requires_grad_(True)
+    y = _conv_same(xt, wt, stride)
+    y.backward(torch.from_numpy(np.ascontiguousarray(dz, np.float64)).permute(0, 3, 1, 2))
+    return xt.grad.permute(0, 2, 3, 1).numpy(), wt.grad.numpy()
+
+
+def forward_train(images, P, lock, stats_out=None, acts_out=None, z_out=None):
     """Training-mode forward.  images [B,H,W,3] numpy; P: dict name -> torch tensor (leaf tensors
     with requires_grad for trainables).  Unlocked BN layers use batch moments over (N,H,W)
     (yolo3_net_pos.py:88-98); locked ones the moving statistics (:76-81).
@@ -43,12 +73,15 @@ def forward_train(images, P, lock, stats_out=None, acts_out=None):
 
     def run(n, x, shortcut=None):
         L = t[n]
-        y = _conv_same(x, P[O.vname(n, 'w')], L['s'])
+        y = _conv_same(_rb(x) if n == 1 else x, _rb(P[O.vname(n, 'w')]), L['s'])
         if L['bn']:
             g, b = P[O.vname(n, 'gamma')].view(1, -1, 1, 1), P[O.vname(n, 'beta')].view(1, -1, 1, 1)
             if lock[n]:
                 m, v = P[O.vname(n, 'mean')].view(1, -1, 1, 1), P[O.vname(n, 'var')].view(1, -1, 1, 1)
             else:
+                y = _rb(y)                 # the engine keeps the pre-BN output z in bf16
+                if z_out is not None:
+                    z_out[n] = y.detach().permute(0, 2, 3, 1).numpy().copy()
                 m = y.mean(dim=(0, 2, 3), keepdim=True)
                 v = ((y - m) ** 2).mean(dim=(0, 2, 3), keepdim=True)
                 if stats_out is not None:
@@ -59,8 +92,11 @@ def forward_train(images, P, lock, stats_out=None, acts_out=None):
             y = y + P[O.vname(n, 'b')].view(1, -1, 1, 1)
         if L['res']:
             y = y + shortcut
-        if acts_out is not None and y.requires_grad:
-            y.retain_grad()
+        if L['bn']:
+            y = _rb(y)                     # bf16 activations; the biased linear heads stay fp32
+        if acts_out is not None:
+            if y.requires_grad:
+                y.retain_grad()
             acts_out[n] = y
         return y
 
@@ -258,7 +294,8 @@ def train_step(images, W, lock, labels, true_boxes, true_masks, perms, det_thres
         P[nm].requires_grad_(True)
     stats = {}
     acts = {}
-    yolos, mp = forward_train(images, P, lock, stats, acts)
+    zs = {}
+    yolos, mp = forward_train(images, P, lock, stats, acts, zs)
     ly = loss_yolo(yolos, true_boxes, labels)
     B = images.shape[0]
     if windows is None:
@@ -290,7 +327,8 @@ def train_step(images, W, lock, labels, true_boxes, true_masks, perms, det_thres
             newW[O.vname(n, 'mean')] = (W[O.vname(n, 'mean')] * O.BN_DECAY + m * (1 - O.BN_DECAY)).astype(np.float32)
             newW[O.vname(n, 'var')] = (W[O.vname(n, 'var')] * O.BN_DECAY + v * (1 - O.BN_DECAY)).astype(np.float32)
     act_grads = {n: a.grad.permute(0, 2, 3, 1).numpy().copy() for n, a in acts.items() if a.grad is not None}
-    return losses, grads, newW, adam, dict(stats=stats, detections=det, act_grads=act_grads,
+    return losses, grads, newW, adam, dict(stats=stats, detections=det, act_grads=act_grads, z=zs,
+                                           acts={n: a.detach().permute(0, 2, 3, 1).numpy().copy() for n, a in acts.items()},
                                            yolos=[y.detach().numpy() for y in yolos], mask_pos=mp.detach().numpy())
 
 

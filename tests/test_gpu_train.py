@@ -13,7 +13,7 @@ import pytest
 
 from oracle import dis_oracle as O
 from oracle import dis_oracle_train as T
-from tests.util import rel_err
+from tests.util import bf16_round, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -192,3 +192,193 @@ def test_data_parallel_two_gpus():
     assert res[0][1] < 1e-4 and res[1][1] < 1e-4            # all-reduced gradient == sum of rank gradients
     assert res[0][2] == res[1][2]                           # identical parameters after the step
     assert res[0][3] == res[1][3] and res[0][4] >= 2        # averaged losses agree; > 1 bucket
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (bf16) training engine
+# ---------------------------------------------------------------------------------------------
+def _grad_table(eng, g, og):
+    errs, cos = {}, {}
+    for layer in range(53, 83):
+        off, cnt = eng.layer_span(layer)
+        L = O.layer_table()[layer]
+        nw = L['k'] ** 2 * L['cin'] * L['cout']
+        names = ['w', 'gamma', 'beta'] if L['bn'] else ['w', 'b']
+        sizes = [nw] + [L['cout']] * (len(names) - 1)
+        o = off
+        for nm, sz in zip(names, sizes):
+            ref = og[O.vname(layer, nm)].reshape(-1).astype(np.float64)
+            got = g[o:o + sz].astype(np.float64)
+            errs['%d%s' % (layer, nm)] = rel_err(got, ref)
+            cos['%d%s' % (layer, nm)] = float(got @ ref / max(np.linalg.norm(got) * np.linalg.norm(ref), 1e-30))
+            o += sz
+    return errs, cos
+
+
+def _local_layer_oracle(n, x_in, w_bf, z_eng, dy_eng, gamma, beta, bias, bn):
+    """float64 restatement of ONE layer's training-mode forward and backward on the engine's own
+    inputs (x_in = the engine's input activations, z_eng = its stored pre-BN output, dy_eng = its
+    gradient w.r.t. the layer output).  Returns dict(z, y, dz, dw, dx, dgamma, dbeta / dbias)."""
+    import torch
+    out = {}
+    xt = torch.from_numpy(np.ascontiguousarray(x_in, np.float64)).permute(0, 3, 1, 2)
+    wt = torch.from_numpy(np.ascontiguousarray(w_bf, np.float64))
+    z = T._conv_same(xt, wt, 1)
+    out['z'] = z.permute(0, 2, 3, 1).numpy()
+    dy = torch.from_numpy(np.ascontiguousarray(dy_eng, np.float64)).permute(0, 3, 1, 2)
+    if bn:
+        ze = torch.from_numpy(np.ascontiguousarray(z_eng, np.float64)).permute(0, 3, 1, 2).requires_grad_(True)
+        g = torch.from_numpy(np.asarray(gamma, np.float64)).requires_grad_(True)
+        b = torch.from_numpy(np.asarray(beta, np.float64)).requires_grad_(True)
+        m = ze.mean(dim=(0, 2, 3), keepdim=True)
+        v = ((ze - m) ** 2).mean(dim=(0, 2, 3), keepdim=True)
+        y = (ze - m) * torch.rsqrt(v + O.BN_EPS) * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+        y = torch.maximum(O.ALPHA * y, y)
+        y.backward(dy)
+        out['y'] = y.detach().permute(0, 2, 3, 1).numpy()
+        out['dz'] = ze.grad.permute(0, 2, 3, 1).numpy()
+        out['dgamma'], out['dbeta'] = g.grad.numpy(), b.grad.numpy()
+        out['mean'], out['var'] = m.detach().reshape(-1).numpy(), v.detach().reshape(-1).numpy()
+    else:
+        out['y'] = out['z'] + np.asarray(bias, np.float64)
+        out['dz'] = np.ascontiguousarray(dy_eng, np.float64)
+        out['dbias'] = out['dz'].sum(axis=(0, 1, 2))
+    out['dx'], out['dw'] = T.conv_backward(x_in, out['dz'], w_bf)
+    return out
+
+
+def test_train_step_bf16_tensor_core_engine():
+    """The training step on the tcgen05 engine (bf16 operands / activations / activation gradients,
+    fp32 accumulation, fp32 BN statistics, master weights and Adam).
+
+    End to end only the LOSSES are comparable with the float64 oracle (3e-2): with batch-statistics
+    BN at random init the network is chaotic in its rounding -- two bf16 forwards that differ only
+    in fp32 accumulation order (this engine vs a float64 oracle rounding to bf16 at the same points,
+    T.EMULATE_BF16) agree to 2e-5 after conv1 and are fully decorrelated (5e-3, the bf16 noise
+    floor) by layer 40; that flips leaky-ReLU masks and moves weight gradients by 0.4-1.2 norm-wise
+    (measured between the two float64 oracles themselves).  The kernels are therefore checked layer
+    by layer on IDENTICAL inputs: for every trained layer the float64 oracle recomputes z, y, dz,
+    dW, d gamma / d beta / d bias and the input gradient from the engine's own x, z, dy.
+    Tolerances (norm-wise): z, y 4e-3 (one bf16 rounding); d gamma, d beta, d bias 1e-2; dW 2e-2 (bf16 dz);
+    input gradients 1.5e-2 (bf16 dz, bf16 weights, bf16 store, accumulation over consumers)."""
+    import disyolo_b200 as dy
+    W, img, labels, tb, tm, pp, pg, thresh = _setup()
+    B, size = img.shape[0], img.shape[1]
+    lock = O.default_lock_flags()
+    eng = dy.Engine(image_size=size, max_batch=B, precision='bf16')
+    eng.load_weights(W)
+    assert eng.train_init() == 21070737
+    perms = [(pp[b].tolist(), pg[b].tolist()) for b in range(B)]
+    keys = ('total', 'obj', 'noobj', 'cls', 'xy', 'wh', 'mask', 'l2')
+    T.NP_DT = np.float64
+    try:
+        losses = eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+        ol64 = T.train_step(img, W, lock, labels, tb, tm, perms, det_thresh=thresh, lr=1e-4, apply=False)[0]
+        print('bf16 losses', losses, 'float64 oracle', [ol64[k] for k in keys])
+        assert np.allclose(losses, [ol64[k] for k in keys], rtol=3e-2, atol=1e-4)
+        g = eng.train_backward(82, 1).cpu().numpy()
+        assert np.all(np.isfinite(g))
+        tab = O.layer_table()
+        topo = T.TOPOLOGY_53_82          # n -> (src0, src1)
+        act = {n: eng.activation(n, B).cpu().numpy() for n in list(range(53, 83)) + [52, 43, 26, 9, 4]}
+        dyt = {n: eng.train_tensor(n, 'dy').cpu().numpy() for n in range(53, 83)}
+        up2 = lambda a: a.repeat(2, axis=1).repeat(2, axis=2)
+        dx_sum, errs, stats = {}, {}, {}
+        for n in range(82, 52, -1):
+            L = tab[n]
+            s0, s1 = topo[n]
+            x_in = act[s0] if s1 == 0 else np.concatenate([act[s0], up2(act[s1])], axis=3)
+            w_bf = bf16_round(W[O.vname(n, 'w')])
+            z_eng = eng.train_tensor(n, 'z').cpu().numpy() if L['bn'] else None
+            r = _local_layer_oracle(n, x_in, w_bf, z_eng, dyt[n], W.get(O.vname(n, 'gamma')), W.get(O.vname(n, 'beta')),
+                                    W.get(O.vname(n, 'b')), L['bn'])
+            off, cnt = eng.layer_span(n)
+            nw = L['k'] ** 2 * L['cin'] * L['cout']
+            if L['bn']:
+                errs['%dz' % n] = rel_err(z_eng, r['z'])
+                errs['%dgamma' % n] = rel_err(g[off + nw:off + nw + L['cout']], r['dgamma'])
+                errs['%dbeta' % n] = rel_err(g[off + nw + L['cout']:off + cnt], r['dbeta'])
+                stats[n] = (r['mean'], r['var'])
+            else:
+                errs['%db' % n] = rel_err(g[off + nw:off + cnt], r['dbias'])
+            errs['%dy' % n] = rel_err(act[n], r['y'])
+            errs['%dw' % n] = rel_err(g[off:off + nw], r['dw'].reshape(-1))
+            c0 = act[s0].shape[3]
+            if s0 >= 53:
+                dx_sum[s0] = dx_sum.get(s0, 0) + r['dx'][..., :c0]
+            if s1 >= 53:
+                d1 = r['dx'][..., c0:]
+                dx_sum[s1] = dx_sum.get(s1, 0) + (d1[:, 0::2, 0::2] + d1[:, 1::2, 0::2] + d1[:, 0::2, 1::2] + d1[:, 1::2, 1::2])
+        for p_, ref in dx_sum.items():
+            errs['%ddy' % p_] = rel_err(dyt[p_], ref)
+        print('local rel errs:', ' '.join('%s:%.1e' % kv for kv in sorted(errs.items(), key=lambda kv: kv[0])))
+        for key, e in errs.items():
+            if key.endswith('dy'):
+                tol = 1.5e-2
+            elif key.endswith(('z', 'y')):
+                tol = 4e-3
+            elif key.endswith('w'):
+                tol = 2e-2       # sum_p x_p dz_p with sum_p dz_p = 0 (BN backward): the mean of x cancels in the
+                                 # signal but not in dz's bf16 rounding noise (measured: 1.3e-2 on conv61)
+            else:
+                tol = 1e-2
+            assert e < tol, 'layer tensor %s: rel err %.3g (tol %.1e)' % (key, e, tol)
+        # ---- Adam on the fp32 master weights, from the engine's own gradients ----
+        before = {n: eng.get_weights(O.vname(n, 'w'), W[O.vname(n, 'w')].shape) for n in (53, 58, 61, 75, 81, 82)}
+        eng.train_apply(1e-4)
+        lr_t = 1e-4 * np.sqrt(1 - 0.999) / (1 - 0.9)
+        for n, w0 in before.items():
+            off, cnt = eng.layer_span(n)
+            gw = g[off:off + w0.size].reshape(w0.shape).astype(np.float64) + 1e-4 * w0     # + L2 gradient (:38)
+            want = w0 - lr_t * (0.1 * gw) / (np.sqrt(0.001 * gw * gw) + 1e-8)
+            got = eng.get_weights(O.vname(n, 'w'), w0.shape)
+            assert np.abs(got - want).max() < 2e-6, (n, float(np.abs(got - want).max()))
+        for n in (53, 81):                           # moving averages (:92-95) from the batch moments of z
+            for nm, i in (('mean', 0), ('var', 1)):
+                name = O.vname(n, nm)
+                want = W[name] * O.BN_DECAY + stats[n][i] * (1 - O.BN_DECAY)
+                assert np.allclose(eng.get_weights(name, W[name].shape), want, rtol=1e-4, atol=1e-6), name
+        # ---- the next forward runs on the re-packed bf16 operands of the updated master weights ----
+        Wn = dict(W)
+        for n in range(53, 83):
+            for nm in (['w', 'gamma', 'beta', 'mean', 'var'] if tab[n]['bn'] else ['w', 'b']):
+                Wn[O.vname(n, nm)] = eng.get_weights(O.vname(n, nm), W[O.vname(n, nm)].shape)
+        l2 = eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+        o2 = T.train_step(img, Wn, lock, labels, tb, tm, perms, det_thresh=thresh, lr=1e-4, apply=False)[0]
+        print('step 2 losses', l2, [o2[k] for k in keys])
+        assert np.allclose(l2, [o2[k] for k in keys], rtol=3e-2, atol=1e-4)
+    finally:
+        T.NP_DT = np.float32
+        eng.close()
+
+
+def test_loss_decreases_bf16():
+    import disyolo_b200 as dy
+    W, img, labels, tb, tm, pp, pg, thresh = _setup(seed=3)
+    eng = dy.Engine(image_size=img.shape[1], max_batch=img.shape[0], precision='bf16')
+    eng.load_weights(W)
+    eng.train_init()
+    hist = []
+    for _ in range(6):
+        hist.append(float(eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)[0]))
+        eng.train_backward()
+        eng.train_apply(1e-3)
+    print('bf16 loss history', hist)
+    assert np.all(np.isfinite(hist)) and hist[-1] < hist[0]
+    # evaluation through the same net after training steps (validation loop, train_yolo3_mask.py:163-176)
+    import torch
+    out = eng.forward(torch.from_numpy(img).cuda(), torch.tensor([[0, 0, 1, 1.]] * img.shape[0]).cuda(), 0.1)
+    torch.cuda.synchronize()
+    assert out['det_count'].shape[0] == img.shape[0]
+    eng.close()
+
+
+def test_bf16_training_refuses_unlocked_backbone():
+    import disyolo_b200 as dy
+    from disyolo_b200 import _lib
+    W = O.make_weights('lively', 1)
+    eng = dy.Engine(image_size=64, max_batch=1, precision='bf16', lock=[0] * 82)
+    eng.load_weights(W)
+    with pytest.raises(_lib.DisYoloError, match='precision=fp32'):
+        eng.train_init()
+    eng.close()
