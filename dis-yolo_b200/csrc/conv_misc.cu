@@ -97,16 +97,35 @@ conv1_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio, co
 //                bf16 and writes its swizzled 64-byte row; fence.proxy.async + mbarrier arrive
 //   warp  4      MMA issuer: 2 x tcgen05.mma (M=128, N=32, K=16) per tile into 1 of 4 TMEM stages
 //   warp  5      TMEM allocator
-//   warps 8..11  epilogue: tcgen05.ld -> folded BN -> leaky -> bf16 -> space-to-depth (and/or P1) store
+//   warps 8..15  epilogue, two warpgroups on alternate tiles: tcgen05.ld -> folded BN -> leaky -> bf16 ->
+//                space-to-depth (TMA store from a double-buffered staging row) or P1 store
 // Tiles are 128 consecutive pixels in (n,y,x) raster order; W % 32 == 0 keeps a segment in one row.
 // ------------------------------------------------------------------------------------------
-constexpr int kC1Threads = 384;
+constexpr int kC1Threads = 512;
 constexpr int kC1Stages = 3;
 constexpr int kPatchW = 112;                 // pixels x0-4 .. x0+32 (37 x 3 = 111 floats): the TMA box must start 16-byte aligned
 constexpr int kPatchLead = 4;                // leading pixels before x0 inside the patch
 constexpr int kC1Patches = 4;                // patch prefetch depth per producer warp (TMA latency > 1 tile time)
 constexpr int kC1PatchFloats = 3 * kPatchW + 16;   // 1408 B, a multiple of 128 B
-constexpr size_t kC1SmemBytes = 3 * 8192 + 2048 + 4 * 2048 + 4 * kC1Patches * kC1PatchFloats * 4 + 1024;
+constexpr size_t kC1SmemBytes = 3 * 8192 + 2048 + 16 * 2048 + 4 * kC1Patches * kC1PatchFloats * 4 + 1024;
+
+// (n, y, x0) of a 32-pixel segment, advanced tile by tile without divisions: consecutive tiles of a CTA
+// are gridDim.x * 128 pixels apart = (sy rows, sx pixels)
+struct SegCoord {
+  int x0, y, n;
+  __device__ __forceinline__ void init(long long p0, int H, int W) {
+    x0 = (int)(p0 % W);
+    const long long t = p0 / W;
+    y = (int)(t % H);
+    n = (int)(t / H);
+  }
+  __device__ __forceinline__ void advance(int sx, int sy, int H, int W) {
+    x0 += sx;
+    if (x0 >= W) { x0 -= W; ++y; }
+    y += sy;
+    while (y >= H) { y -= H; ++n; }
+  }
+};
 
 // v2: the fp32 patches arrive by TMA (3-D map [N][H][W*3], out-of-bounds = zero padding for free),
 // double buffered per producer warp; the space-to-depth output leaves through per-warp TMA stores
@@ -116,14 +135,15 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
                 const float* __restrict__ w_hwio, const float* __restrict__ scale, const float* __restrict__ shift,
                 float alpha, int B, int H, int W, __nv_bfloat16* __restrict__ out_same) {
   // dynamic smem: [A tiles: kC1Stages x 8 KB, SWIZZLE_64B rows of 64 B][weights 2 KB, same layout]
-  // [per epilogue warp 2 KB: 16 pixel pairs x 128 B, SWIZZLE_128B][patches: 4 warps x kC1Patches x 1408 B]
+  // [per epilogue warp 2 x 2 KB: 16 pixel pairs x 128 B, SWIZZLE_128B, double buffered]
+  // [patches: 4 warps x kC1Patches x 1408 B]
   extern __shared__ uint8_t c1_smem_raw[];
   uint8_t* c1_smem = c1_smem_raw + ((1024u - (smem_u32(c1_smem_raw) & 1023u)) & 1023u);
   uint8_t (*sA)[128 * 64] = reinterpret_cast<uint8_t (*)[128 * 64]>(c1_smem);
   uint8_t* sB = c1_smem + kC1Stages * 8192;
-  uint8_t (*sOut)[2048] = reinterpret_cast<uint8_t (*)[2048]>(sB + 2048);
+  uint8_t (*sOut)[2][2048] = reinterpret_cast<uint8_t (*)[2][2048]>(sB + 2048);
   float (*patch)[kC1Patches][kC1PatchFloats] =
-      reinterpret_cast<float (*)[kC1Patches][kC1PatchFloats]>(sB + 2048 + 4 * 2048);
+      reinterpret_cast<float (*)[kC1Patches][kC1PatchFloats]>(sB + 2048 + 16 * 2048);
   __shared__ __align__(8) uint64_t full_bar[kC1Stages], empty_bar[kC1Stages], tfull_bar[4], tempty_bar[4];
   __shared__ __align__(8) uint64_t patch_bar[4][kC1Patches];
   __shared__ uint32_t tmem_base_smem;
@@ -171,24 +191,31 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
 
   if (warp < 4) {
     // ================================ im2col producers ================================
-    auto issue_patch = [&](int tile, int buf) {                    // lane 0 only
-      const long long p0 = (long long)tile * 128 + warp * 32;
-      const int x0 = (int)(p0 % W);
-      const long long t = p0 / W;
-      const int y = (int)(t % H), n = (int)(t / H);                 // n >= B for segments past the end: zero fill
+    // running coordinate of the NEXT patch to request (kC1Patches-1 tiles ahead of the one being built)
+    const int step_px = 128 * (int)gridDim.x, sx = step_px % W, sy = step_px / W;
+    SegCoord nx;
+    nx.init((long long)blockIdx.x * 128 + warp * 32, H, W);
+    auto issue_patch = [&](int buf) {                                // lane 0 only; n >= B past the end: zero fill
       mbar_expect_tx(&patch_bar[warp][buf], 3 * kPatchW * 4);
-      tma_load_3d(&patch[warp][buf][0], &mapImg, &patch_bar[warp][buf], (x0 - kPatchLead) * 3, y - 1, n);
+      tma_load_3d(&patch[warp][buf][0], &mapImg, &patch_bar[warp][buf], (nx.x0 - kPatchLead) * 3, nx.y - 1, nx.n);
     };
-    int it = 0;
-    if (lane == 0)
-      for (int d = 0; d < kC1Patches - 1; ++d)
-        if ((long long)blockIdx.x + (long long)d * gridDim.x < num_tiles) issue_patch(blockIdx.x + d * gridDim.x, d);
+    int it = 0, issued = blockIdx.x;                                 // tile index of the next patch to request
+    for (int d = 0; d < kC1Patches - 1; ++d) {
+      if (issued < num_tiles) {
+        if (lane == 0) issue_patch(d);
+        issued += gridDim.x;
+        nx.advance(sx, sy, H, W);
+      }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int stage = it % kC1Stages, buf = it % kC1Patches;
       const uint32_t ph = (uint32_t)(it / kC1Stages) & 1u;
       // refill the buffer that was consumed last iteration (all lanes passed the __syncwarp after reading it)
-      if (lane == 0 && (long long)tile + (long long)(kC1Patches - 1) * gridDim.x < num_tiles)
-        issue_patch(tile + (kC1Patches - 1) * gridDim.x, (it + kC1Patches - 1) % kC1Patches);
+      if (issued < num_tiles) {
+        if (lane == 0) issue_patch((it + kC1Patches - 1) % kC1Patches);
+        issued += gridDim.x;
+        nx.advance(sx, sy, H, W);
+      }
       mbar_wait(&patch_bar[warp][buf], (uint32_t)(it / kC1Patches) & 1u);
       const float* mp = &patch[warp][buf][0];
       // this lane's pixel: tap (kh,kw,c) = patch[kh][(lane + kw - 1 + kPatchLead)*3 + c], k = (kh*3+kw)*3 + c
@@ -236,7 +263,8 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
     }
   } else if (warp >= 8) {
     // ================================ epilogue ================================
-    const int q = warp & 3;
+    // two warpgroups (warps 8..11, 12..15) drain alternate tiles: group g owns TMEM stages g and g+2
+    const int q = warp & 3, grp = (warp - 8) >> 2;
     const int Hq = H / 2 + 1, Wq = W / 2 + 1;
     float sc[32], sh[32];
 #pragma unroll
@@ -244,16 +272,16 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
       sc[c] = __ldg(scale + c);
       sh[c] = __ldg(shift + c);
     }
-    uint8_t* so = &sOut[q][0];
     const bool use_tma = out_same == nullptr;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int step_px = 256 * (int)gridDim.x, sx = step_px % W, sy = step_px / W;
+    SegCoord sg;
+    sg.init((long long)(blockIdx.x + grp * gridDim.x) * 128 + q * 32, H, W);
+    int it = grp, nst = 0;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles;
+         tile += 2 * gridDim.x, it += 2, sg.advance(sx, sy, H, W)) {
       const int acc = it & 3;
-      const long long p0 = (long long)tile * 128 + q * 32;           // first pixel of this warp's segment
-      const bool seg_ok = p0 < total;                                // W % 32 == 0: all 32 pixels or none
-      const int x0 = (int)(p0 % W);
-      const long long t = p0 / W;
-      const int y = (int)(t % H), n = (int)(t / H);
+      const int x0 = sg.x0, y = sg.y, n = sg.n;                      // first pixel of this warp's segment
+      const bool seg_ok = n < B;                                     // W % 32 == 0: all 32 pixels or none
       mbar_wait(&tfull_bar[acc], (uint32_t)(it >> 2) & 1u);
       tc_fence_after();
       uint32_t r0[16], r1[16];
@@ -278,7 +306,9 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
       }
       if (use_tma) {
         // pixel pair (lane>>1) = one 128-byte row of the s2d tensor; SWIZZLE_128B chunk = c ^ (pair & 7)
-        if (lane == 0) bulk_wait_read<0>();                          // previous tile's store has read sOut
+        uint8_t* so = &sOut[warp - 8][nst & 1][0];
+        ++nst;
+        if (lane == 0) bulk_wait_read<1>();                          // the store two tiles ago has read this buffer
         __syncwarp();
         const int pair = lane >> 1, half = lane & 1;
 #pragma unroll

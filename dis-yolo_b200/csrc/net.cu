@@ -1186,6 +1186,59 @@ int dy_assemble_masks(dy_net* net, const float* score_dev, int32_t layout, int32
   return run_masks(net, score_dev, layout, B, det_count_dev, masks_dev, st);
 }
 
+int dy_postproc_profile(dy_net* net, const float* yolo8_dev, const float* yolo16_dev, const float* yolo32_dev,
+                        const float* score_dev, int32_t layout, int32_t B, const float* windows_dev, float det_thresh,
+                        float* masks_dev, int32_t reps, float* ms_host, void* stream) {
+  DY_CHECK(net && yolo8_dev && yolo16_dev && yolo32_dev && score_dev && windows_dev && masks_dev && ms_host,
+           "null argument");
+  DY_CHECK(B >= 1 && B <= net->cfg.max_batch && reps >= 1, "batch / reps");
+  DY_CHECK(layout == 0 || layout == 1, "layout: 0 = NHWC, 1 = planar");
+  cudaStream_t st = (cudaStream_t)stream;
+  DecodeArgs da;
+  memset(&da, 0, sizeof(da));
+  da.yolo[0] = yolo8_dev; da.yolo[1] = yolo16_dev; da.yolo[2] = yolo32_dev;
+  da.g[0] = net->S / 8; da.g[1] = net->S / 16; da.g[2] = net->S / 32;
+  da.B = B; da.num_class = net->cfg.num_classes; da.net = 32 * da.g[2];
+  memcpy(da.anchors, net->cfg.anchors, sizeof(da.anchors));
+  da.windows = windows_dev; da.thresh = det_thresh;
+  da.cand = net->cand; da.cand_count = net->cand_count; da.cap = net->cap;
+  NmsArgs na;
+  na.cand = net->cand; na.cand_count = net->cand_count; na.cap = net->cap;
+  na.B = B; na.num_class = net->cfg.num_classes; na.max_det = net->cfg.max_detection;
+  na.iou_thr = net->cfg.iou_threshold; na.sel = net->sel; na.sel_cnt = net->sel_cnt;
+  FinalizeArgs fa;
+  fa.cand = net->cand; fa.cap = net->cap; fa.B = B; fa.num_class = net->cfg.num_classes;
+  fa.max_det = net->cfg.max_detection; fa.sel = net->sel; fa.sel_cnt = net->sel_cnt;
+  fa.S = net->S / 2; fa.k = net->cfg.k_map;
+  fa.det_raw = net->det_raw_ws; fa.raw_count = net->raw_count; fa.det_box = net->det_box_ws;
+  fa.det_count = net->det_count_ws; fa.edges = net->edges;
+  cudaEvent_t ev[5];
+  for (int i = 0; i < 5; ++i) DY_CUDA(cudaEventCreate(&ev[i]));
+  int rc = DY_OK;
+  // each stage `reps` times back to back between two events; stages see the previous stage's output
+  DY_CUDA(cudaEventRecord(ev[0], st));
+  for (int r = 0; r < reps && rc == DY_OK; ++r) {
+    cudaMemsetAsync(net->cand_count, 0, (size_t)B * 4, st);
+    note_launch();
+    rc = launch_decode(da, st);
+  }
+  DY_CUDA(cudaEventRecord(ev[1], st));
+  for (int r = 0; r < reps && rc == DY_OK; ++r) { note_launch(); rc = launch_nms(na, st); }
+  DY_CUDA(cudaEventRecord(ev[2], st));
+  for (int r = 0; r < reps && rc == DY_OK; ++r) { note_launch(); rc = launch_finalize(fa, st); }
+  DY_CUDA(cudaEventRecord(ev[3], st));
+  for (int r = 0; r < reps && rc == DY_OK; ++r) rc = run_masks(net, score_dev, layout, B, net->det_count_ws, masks_dev, st);
+  DY_CUDA(cudaEventRecord(ev[4], st));
+  DY_CUDA(cudaEventSynchronize(ev[4]));
+  for (int i = 0; i < 4; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+    ms_host[i] = ms / (float)reps;
+  }
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
 int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
                   const float* w_host, int32_t k, int32_t stride, int32_t cout, const float* scale_host,
                   const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,

@@ -47,6 +47,9 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
   for (int c = 0; c < a.num_class; ++c) sum = __fadd_rn(sum, expf(__fsub_rn(t[5 + c], mx)));
   const float pmax = __fdiv_rn(1.f, sum);              // exp(0)/sum
   const float score = __fmul_rn(sigmoidf_(t[4]), pmax);
+  // below the threshold and no dense output requested: the box is never looked at (keep = score >
+  // thresh, :558) -- skip its two sigmoids, two exps and eight IEEE divisions
+  if (!a.dense_box && !(score > a.thresh)) return;
   // box (:487-505): xy = (cell + sigmoid(t_xy)) / grid ; wh = exp(t_wh) * anchor / net
   const float gf = (float)g, nf = (float)a.net;
   const float xc = __fdiv_rn(__fadd_rn((float)cx, sigmoidf_(t[0])), gf);
@@ -329,8 +332,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
 // ------------------------------------------------------------------------------------------
 constexpr int kMaskRowsPerCta = 32;
 
-// One warp per row at a time: the row's vertical bin is warp-uniform, rows above/below the box are a
-// pure 0.5 fill, and every warp store instruction writes 512 contiguous bytes (streaming stores).
+// One CTA per (32-row slab, detection, image).  Rows above / below the box are a pure 0.5 fill; the slab
+// is walked as a flat array of float4 so that every lane of every store instruction is busy and each
+// warp writes 512 contiguous bytes (streaming stores: the masks are consumed by the host).
 __global__ void __launch_bounds__(256) mask_kernel(MaskArgs a) {
   const int d = blockIdx.y, b = blockIdx.z;
   if (d >= a.det_count[b]) return;
@@ -342,44 +346,43 @@ __global__ void __launch_bounds__(256) mask_kernel(MaskArgs a) {
     gy[j] = (j <= a.k) ? __ldg(ed + kMaxK + 1 + j) : 0x7fffffff;
   }
   const int x_lo = gx[0], x_hi = gx[a.k], y_lo = gy[0], y_hi = gy[a.k];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qpr = a.S >> 2;
   const int y0 = blockIdx.x * kMaskRowsPerCta;
   const int y1 = min(a.S, y0 + kMaskRowsPerCta);
   const float* sbase = a.score + b * a.s_img;
-  float* obase = a.out + ((long long)b * a.max_det + d) * a.S * a.S;
+  float4* obase = reinterpret_cast<float4*>(a.out + (((long long)b * a.max_det + d) * a.S + y0) * a.S);
   const float4 half4 = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-  for (int y = y0 + warp; y < y1; y += 8) {
-    float4* orow = reinterpret_cast<float4*>(obase + (long long)y * a.S);
-    if (y < y_lo || y >= y_hi) {
-      for (int q = lane; q < qpr; q += 32) __stcs(orow + q, half4);
-      continue;
-    }
-    int by = 0;
+  const int nq = (y1 - y0) * qpr;
+  if (y1 <= y_lo || y0 >= y_hi) {          // slab entirely outside the box
+    for (int i = threadIdx.x; i < nq; i += 256) __stcs(obase + i, half4);
+    return;
+  }
+  for (int i = threadIdx.x; i < nq; i += 256) {
+    const int yy = i / qpr;
+    const int q = i - yy * qpr;
+    const int y = y0 + yy, x0 = q << 2;
+    float4 o = half4;
+    if (y >= y_lo && y < y_hi && x0 + 3 >= x_lo && x0 < x_hi) {
+      int by = 0;
 #pragma unroll
-    for (int j = 1; j < kMaxK; ++j)
-      if (j < a.k && y >= gy[j]) by = j;
-    const float* srow = sbase + (long long)(by * a.k) * a.s_ch + (long long)y * a.s_row;
-    for (int q = lane; q < qpr; q += 32) {
-      const int x0 = q << 2;
-      float4 o = half4;
-      if (x0 + 3 >= x_lo && x0 < x_hi) {
-        float v[4];
+      for (int j = 1; j < kMaxK; ++j)
+        if (j < a.k && y >= gy[j]) by = j;
+      const float* srow = sbase + (long long)(by * a.k) * a.s_ch + (long long)y * a.s_row;
+      float v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int x = x0 + i;
-          int bx = 0;
+      for (int t = 0; t < 4; ++t) {
+        const int x = x0 + t;
+        int bx = 0;
 #pragma unroll
-          for (int j = 1; j < kMaxK; ++j)
-            if (j < a.k && x >= gx[j]) bx = j;
-          float val = 0.5f;
-          if (x >= x_lo && x < x_hi) val = sigmoidf_(__ldg(srow + (long long)bx * a.s_ch + (long long)x * a.s_pix));
-          v[i] = val;
-        }
-        o = make_float4(v[0], v[1], v[2], v[3]);
+        for (int j = 1; j < kMaxK; ++j)
+          if (j < a.k && x >= gx[j]) bx = j;
+        float val = 0.5f;
+        if (x >= x_lo && x < x_hi) val = sigmoidf_(__ldg(srow + (long long)bx * a.s_ch + (long long)x * a.s_pix));
+        v[t] = val;
       }
-      __stcs(orow + q, o);
+      o = make_float4(v[0], v[1], v[2], v[3]);
     }
+    __stcs(obase + i, o);
   }
 }
 

@@ -42,46 +42,70 @@ static int grid_for(long long total, int cap = 148 * 8) {
 }
 
 // -------------------------------------------------------------------------------------------
-// per-channel reductions over a P1 matrix [rows, C]: thread (tx, ty) owns the 8 channels of vector
-// column tx for rows ty, ty+R, ...; fp32 partial sums are flushed to double every 32 rows
+// Elementwise / reduction kernels over a P1 matrix [rows, C] of bf16.  Thread t of a block owns the
+// 16-byte vector column v = t % (C/8) and the rows (t / (C/8)) + k*R of the block's row range: no
+// per-element index division, 32-bit row arithmetic (rows < 2^31), and kUnroll independent 16-byte
+// loads per operand in flight per thread -- these kernels are HBM-bound.
 // -------------------------------------------------------------------------------------------
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ bool p1_pixel(uint32_t r, uint32_t Hp, uint32_t Wp, int H, int W, int* n, int* y, int* x) {
+  const uint32_t t = r / Wp;
+  *x = (int)(r - t * Wp);
+  const uint32_t nn = t / Hp;
+  *n = (int)nn;
+  *y = (int)(t - nn * Hp);
+  return *x < W && *y < H;
+}
+
+// per-channel reductions: fp32 partial sums per thread are flushed to double every 8 row groups
 template <bool BWD>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
 p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ z,
                  const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
-                 const float* __restrict__ invstd, float alpha, int act, long long rows, int C, int rows_per_block,
+                 const float* __restrict__ invstd, float alpha, int act, uint32_t rows, int C,
                  double* __restrict__ o1, double* __restrict__ o2) {
   __shared__ double sm[16 * kT];
   const int cv = C >> 3;
-  const int tx = threadIdx.x % cv, ty = threadIdx.x / cv, R = kT / cv;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > rows) r1 = rows;
+  const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
+  const uint32_t G = gridDim.x * (uint32_t)R;
   double d1[8], d2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) d1[j] = d2[j] = 0.0;
   float fa[8], fb[8], fm[8], fi[8];
-  if (BWD && ty < R) {
-    load8f(a + tx * 8, fa);
-    load8f(b + tx * 8, fb);
-    load8f(mean + tx * 8, fm);
-    load8f(invstd + tx * 8, fi);
+  if (BWD) {
+    load8f(a + v * 8, fa);
+    load8f(b + v * 8, fb);
+    load8f(mean + v * 8, fm);
+    load8f(invstd + v * 8, fi);
   }
-  if (ty < R) {
-    long long r = r0 + ty;
-    while (r < r1) {
-      float p1[8], p2[8];
+  uint32_t r = blockIdx.x * (uint32_t)R + rl;
+  while (r < rows) {
+    float p1[8], p2[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) p1[j] = p2[j] = 0.f;
-      for (int it = 0; it < 32 && r < r1; ++it, r += R) {
+    for (int j = 0; j < 8; ++j) p1[j] = p2[j] = 0.f;
+    for (int it = 0; it < 8 && r < rows; ++it, r += kUnroll * G) {
+      uint4 qu[kUnroll], qz[kUnroll];
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        const uint32_t rr = r + k * G;
+        qu[k] = make_uint4(0, 0, 0, 0);
+        qz[k] = make_uint4(0, 0, 0, 0);
+        if (rr < rows) {
+          qu[k] = __ldg(reinterpret_cast<const uint4*>(u + (size_t)rr * C) + v);
+          if (BWD) qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)rr * C) + v);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
         float fu[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(u + r * C) + tx), fu);
+        unpack8(qu[k], fu);
         if (BWD) {
           float fz[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C) + tx), fz);
+          unpack8(qz[k], fz);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float g = fu[j];
+            float g = fu[j];               // rows beyond the end and pad pixels carry dy = 0
             if (act && !(fmaf(fz[j], fa[j], fb[j]) > 0.f)) g *= alpha;
             p1[j] += g;
             p2[j] += g * ((fz[j] - fm[j]) * fi[j]);
@@ -94,11 +118,11 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
           }
         }
       }
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        d1[j] += (double)p1[j];
-        d2[j] += (double)p2[j];
-      }
+    for (int j = 0; j < 8; ++j) {
+      d1[j] += (double)p1[j];
+      d2[j] += (double)p2[j];
     }
   }
 #pragma unroll
@@ -110,57 +134,61 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
   for (int o = threadIdx.x; o < 16 * cv; o += kT) {
     const int j = o / cv, x = o - j * cv;
     double t = 0.0;
-    for (int r = 0; r < R; ++r) t += sm[j * kT + r * cv + x];
+    for (int q = 0; q < R; ++q) t += sm[j * kT + q * cv + x];
     const int ch = x * 8 + (j & 7);
     if (j < 8) atomicAdd(o1 + ch, t);
     else if (o2) atomicAdd(o2 + ch, t);
   }
 }
 
-__device__ __forceinline__ bool p1_pixel(long long r, int Hp, int Wp, int H, int W, int* n, int* y, int* x) {
-  const long long t = r / Wp;
-  *x = (int)(r - t * Wp);
-  *n = (int)(t / Hp);
-  *y = (int)(t - (long long)(*n) * Hp);
-  return *x < W && *y < H;
-}
-
 __global__ void __launch_bounds__(kT)
 bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
-                 const __nv_bfloat16* __restrict__ residual, long long rows, int H, int W, int C, float alpha, int act,
+                 const __nv_bfloat16* __restrict__ residual, uint32_t rows, int H, int W, int C, float alpha, int act,
                  __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up) {
-  const int cv = C >> 3, Hp = H + 1, Wp = W + 1;
-  const long long total = rows * cv;
-  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-    const long long r = i / cv;
-    const int v = (int)(i - r * cv);
-    int n, y, x;
-    if (!p1_pixel(r, Hp, Wp, H, W, &n, &y, &x)) continue;
-    float fz[8], fa[8], fb[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C) + v), fz);
-    load8f(a + v * 8, fa);
-    load8f(b + v * 8, fb);
+  const int cv = C >> 3;
+  const uint32_t Hp = H + 1, Wp = W + 1;
+  const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
+  const uint32_t G = gridDim.x * (uint32_t)R;
+  float fa[8], fb[8];
+  load8f(a + v * 8, fa);
+  load8f(b + v * 8, fb);
+  for (uint32_t r = blockIdx.x * (uint32_t)R + rl; r < rows; r += kUnroll * G) {
+    uint4 qz[kUnroll], qr[kUnroll];
+    int pn[kUnroll], py[kUnroll], px[kUnroll];
+    bool ok[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(fz[j], fa[j], fb[j]);
-      if (act) t = fmaxf(alpha * t, t);
-      fz[j] = t;
+    for (int k = 0; k < kUnroll; ++k) {
+      const uint32_t rr = r + k * G;
+      ok[k] = rr < rows && p1_pixel(rr, Hp, Wp, H, W, &pn[k], &py[k], &px[k]);
+      qr[k] = make_uint4(0, 0, 0, 0);
+      if (ok[k]) {
+        qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)rr * C) + v);
+        if (residual) qr[k] = __ldg(reinterpret_cast<const uint4*>(residual + (size_t)rr * C) + v);
+      }
     }
-    if (residual) {
-      float fr[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(residual + r * C) + v), fr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) fz[j] += fr[j];
-    }
-    const uint4 q = pack8(fz);
-    if (out_same) reinterpret_cast<uint4*>(out_same + r * C)[v] = q;
-    if (out_up) {
-      const long long Wu = 2 * W + 1, Hu = 2 * H + 1;
-      const long long ru = ((long long)n * Hu + 2 * y) * Wu + 2 * x;
-      reinterpret_cast<uint4*>(out_up + ru * C)[v] = q;
-      reinterpret_cast<uint4*>(out_up + (ru + 1) * C)[v] = q;
-      reinterpret_cast<uint4*>(out_up + (ru + Wu) * C)[v] = q;
-      reinterpret_cast<uint4*>(out_up + (ru + Wu + 1) * C)[v] = q;
+    for (int k = 0; k < kUnroll; ++k) {
+      if (!ok[k]) continue;
+      const uint32_t rr = r + k * G;
+      float fz[8], fr[8];
+      unpack8(qz[k], fz);
+      unpack8(qr[k], fr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(fz[j], fa[j], fb[j]);
+        if (act) t = fmaxf(alpha * t, t);
+        fz[j] = t + fr[j];
+      }
+      const uint4 q = pack8(fz);
+      if (out_same) reinterpret_cast<uint4*>(out_same + (size_t)rr * C)[v] = q;
+      if (out_up) {
+        const size_t Wu = 2 * W + 1, Hu = 2 * H + 1;
+        const size_t ru = ((size_t)pn[k] * Hu + 2 * py[k]) * Wu + 2 * px[k];
+        reinterpret_cast<uint4*>(out_up + ru * C)[v] = q;
+        reinterpret_cast<uint4*>(out_up + (ru + 1) * C)[v] = q;
+        reinterpret_cast<uint4*>(out_up + (ru + Wu) * C)[v] = q;
+        reinterpret_cast<uint4*>(out_up + (ru + Wu + 1) * C)[v] = q;
+      }
     }
   }
 }
@@ -170,44 +198,64 @@ bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
                        const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                        const double* __restrict__ s1, const double* __restrict__ s2, float alpha, int act, int mode,
-                       long long rows, long long rows_out, long long mvalid, int H, int W, int C,
+                       uint32_t rows, uint32_t rows_out, long long mvalid, int H, int W, int C,
                        __nv_bfloat16* __restrict__ dz) {
-  const int cv = C >> 3, Hp = H + 1, Wp = W + 1;
-  const long long total = rows_out * cv;
+  const int cv = C >> 3;
+  const uint32_t Hp = H + 1, Wp = W + 1;
+  const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
+  const uint32_t G = gridDim.x * (uint32_t)R;
   const float invM = 1.f / (float)mvalid;
-  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-    const long long r = i / cv;
-    const int v = (int)(i - r * cv);
-    int n, y, x;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (r < rows && p1_pixel(r, Hp, Wp, H, W, &n, &y, &x)) {
-      float fg[8], fz[8], fa[8], fb[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + r * C) + v), fg);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(z + r * C) + v), fz);
-      load8f(a + v * 8, fa);
-      load8f(b + v * 8, fb);
-      if (act) {
+  // per-channel constants of this thread's 8 channels: dz = g*k0 - k1 - xhat*k2 (mode 0) or g*k0 (mode 1)
+  float fa[8], fb[8], k0[8], k1[8], k2[8], fm[8], fi[8];
+  load8f(a + v * 8, fa);
+  load8f(b + v * 8, fb);
+  if (mode == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (!(fmaf(fz[j], fa[j], fb[j]) > 0.f)) fg[j] *= alpha;
+    for (int j = 0; j < 8; ++j) { k0[j] = fa[j]; k1[j] = k2[j] = fm[j] = fi[j] = 0.f; }
+  } else {
+    float fg[8];
+    load8f(mean + v * 8, fm);
+    load8f(invstd + v * 8, fi);
+    load8f(gamma + v * 8, fg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      k0[j] = fg[j] * fi[j];
+      k1[j] = k0[j] * ((float)s1[v * 8 + j] * invM);
+      k2[j] = k0[j] * ((float)s2[v * 8 + j] * invM);
+    }
+  }
+  for (uint32_t r = blockIdx.x * (uint32_t)R + rl; r < rows_out; r += kUnroll * G) {
+    uint4 qg[kUnroll], qz[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k) {
+      const uint32_t rr = r + k * G;
+      int n, y, x;
+      ok[k] = rr < rows && p1_pixel(rr, Hp, Wp, H, W, &n, &y, &x);
+      if (ok[k]) {
+        qg[k] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)rr * C) + v);
+        qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)rr * C) + v);
       }
-      if (mode == 1) {
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) fg[j] *= fa[j];
-      } else {
-        float fm[8], fi[8], fgm[8];
-        load8f(mean + v * 8, fm);
-        load8f(invstd + v * 8, fi);
-        load8f(gamma + v * 8, fgm);
+    for (int k = 0; k < kUnroll; ++k) {
+      const uint32_t rr = r + k * G;
+      if (rr >= rows_out) continue;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (ok[k]) {
+        float fg[8], fz[8];
+        unpack8(qg[k], fg);
+        unpack8(qz[k], fz);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (fz[j] - fm[j]) * fi[j];
-          fg[j] = fgm[j] * fi[j] * (fg[j] - (float)s1[v * 8 + j] * invM - xh * (float)s2[v * 8 + j] * invM);
+          float g = fg[j];
+          if (act && !(fmaf(fz[j], fa[j], fb[j]) > 0.f)) g *= alpha;
+          fg[j] = mode == 1 ? g * k0[j] : g * k0[j] - k1[j] - ((fz[j] - fm[j]) * fi[j]) * k2[j];
         }
+        q = pack8(fg);
       }
-      q = pack8(fg);
+      reinterpret_cast<uint4*>(dz + (size_t)rr * C)[v] = q;
     }
-    reinterpret_cast<uint4*>(dz + r * C)[v] = q;
   }
 }
 
@@ -221,7 +269,7 @@ f32_to_p1_kernel(const float* __restrict__ src, long long rows, long long rows_o
     const int v = (int)(i - r * cv);
     int n, y, x;
     uint4 q = make_uint4(0, 0, 0, 0);
-    if (r < rows && p1_pixel(r, Hp, Wp, H, W, &n, &y, &x)) {
+    if (r < rows && p1_pixel((uint32_t)r, (uint32_t)Hp, (uint32_t)Wp, H, W, &n, &y, &x)) {
       const float* s = src + (((long long)n * H + y) * W + x) * C;
       float f[8];
 #pragma unroll
@@ -243,7 +291,7 @@ pool2x2_p1_kernel(const __nv_bfloat16* __restrict__ src, long long rows, long lo
     const int v = (int)(i - r * cv);
     int n, y, x;
     uint4 q = make_uint4(0, 0, 0, 0);
-    if (r < rows && p1_pixel(r, Hp, Wp, h, w, &n, &y, &x)) {
+    if (r < rows && p1_pixel((uint32_t)r, (uint32_t)Hp, (uint32_t)Wp, h, w, &n, &y, &x)) {
       const long long ru = ((long long)n * Hu + 2 * y) * Wu + 2 * x;
       float f0[8], f1[8], f2[8], f3[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(src + ru * C) + v), f0);
@@ -452,7 +500,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int co = n0 + c0 + j;
-          if (co < p.cout) atomicAdd(drow + co, __uint_as_float(r[j]));
+          if (co < p.cout) {
+            if (p.ksplit > 1) atomicAdd(drow + co, __uint_as_float(r[j]));
+            else drow[co] = __uint_as_float(r[j]);
+          }
         }
       }
     }
@@ -473,17 +524,29 @@ void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
   g_wdbg[0] = lbo_a; g_wdbg[1] = sbo_a; g_wdbg[2] = lbo_b; g_wdbg[3] = sbo_b;
 }
 
-int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* sum, double* sumsq, cudaStream_t st) {
-  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT, "channel count");
+// grid for the row-strided kernels: enough 256-thread blocks to keep ~8 independent 16-byte loads per
+// thread in flight on every SM, never more blocks than row groups
+static int row_grid(long long rows, int C) {
   const int R = kT / (C / 8);
-  int rpb = R * 64;
-  long long blocks = (rows + rpb - 1) / rpb;
-  if (blocks > 148 * 4) {
-    blocks = 148 * 4;
-    rpb = (int)((rows + blocks - 1) / blocks);
-  }
-  p1_reduce_kernel<false><<<(int)blocks, kT, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0, rows, C,
-                                                      rpb, sum, sumsq);
+  long long g = (rows + (long long)R * kUnroll - 1) / ((long long)R * kUnroll);
+  if (g > 148 * 6) g = 148 * 6;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// reductions end with 2*C double atomics per block: cap the grid so that a launch issues at most ~256K of
+// them (a wide, low-resolution layer would otherwise spend its time serialising atomics in L2)
+static int reduce_grid(long long rows, int C) {
+  int g = row_grid(rows, C);
+  const int cap = (256 * 1024) / (2 * C);
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : g;
+}
+
+int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* sum, double* sumsq, cudaStream_t st) {
+  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
+  p1_reduce_kernel<false><<<reduce_grid(rows, C), kT, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0,
+                                                            (uint32_t)rows, C, sum, sumsq);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -491,15 +554,9 @@ int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* su
 int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
                             const float* mean, const float* invstd, float alpha, int act, long long rows, int C,
                             double* s1, double* s2, cudaStream_t st) {
-  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT, "channel count");
-  const int R = kT / (C / 8);
-  int rpb = R * 64;
-  long long blocks = (rows + rpb - 1) / rpb;
-  if (blocks > 148 * 4) {
-    blocks = 148 * 4;
-    rpb = (int)((rows + blocks - 1) / blocks);
-  }
-  p1_reduce_kernel<true><<<(int)blocks, kT, 0, st>>>(dy, z, a, b, mean, invstd, alpha, act, rows, C, rpb, s1, s2);
+  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
+  p1_reduce_kernel<true><<<reduce_grid(rows, C), kT, 0, st>>>(dy, z, a, b, mean, invstd, alpha, act, (uint32_t)rows, C,
+                                                           s1, s2);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -507,10 +564,10 @@ int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, con
 int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, const __nv_bfloat16* residual, int B,
                      int H, int W, int C, float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up,
                      cudaStream_t st) {
-  DY_CHECK(C % 8 == 0, "channel count");
   const long long rows = (long long)B * (H + 1) * (W + 1);
-  bn_act_p1_kernel<<<grid_for(rows * (C / 8)), kT, 0, st>>>(z, a, b, residual, rows, H, W, C, alpha, act, out_same,
-                                                            out_up);
+  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
+  bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, a, b, residual, (uint32_t)rows, H, W, C, alpha, act, out_same,
+                                                     out_up);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -524,8 +581,10 @@ int launch_bn_bwd_apply_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, cons
   DY_CHECK(C % 8 == 0, "channel count");
   const long long rows = (long long)B * (H + 1) * (W + 1);
   const long long ro = round_up64(rows);
-  bn_bwd_apply_p1_kernel<<<grid_for(ro * (C / 8)), kT, 0, st>>>(dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act,
-                                                                mode, rows, ro, (long long)B * H * W, H, W, C, dz);
+  DY_CHECK(kT % (C / 8) == 0 && C <= 8 * kT && ro < (1ll << 31), "channel count / rows");
+  bn_bwd_apply_p1_kernel<<<row_grid(ro, C), kT, 0, st>>>(dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act, mode,
+                                                         (uint32_t)rows, (uint32_t)ro, (long long)B * H * W, H, W, C,
+                                                         dz);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -622,7 +681,9 @@ int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream
   p.M = (int)M;
   p.total_chunks = (int)((M + kWgradRows - 1) / kWgradRows);
   const int units = p.ntap * (p.src_blk[0] + (p.nsrc > 1 ? p.src_blk[1] : 0)) * p.n_tiles_n;
-  int ksplit = (2 * num_sms + units - 1) / units;
+  // split K only when the (tap, channel block, N tile) units alone leave SMs idle: every split costs a
+  // pipeline fill and turns the epilogue's stores into atomics
+  int ksplit = units * 4 >= num_sms * 3 ? 1 : (num_sms + units - 1) / units;
   if (ksplit < 1) ksplit = 1;
   // keep at least 8 chunks (512 pixel rows) per CTA so that the pipeline fill is amortised
   const int max_split = (p.total_chunks + 7) / 8;

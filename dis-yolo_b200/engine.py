@@ -392,6 +392,18 @@ class Engine(object):
                    'dy_assemble_masks')
         return out
 
+    def postproc_profile(self, yolos, score_maps, windows, det_thresh, masks_out, layout='nhwc', reps=20):
+        """Device ms per launch of (decode, nms, finalize, mask assembly); see dy_postproc_profile."""
+        t = self.torch
+        y = [self._dev(v, t.float32) for v in yolos]
+        score_maps, windows = self._dev(score_maps, t.float32), self._dev(windows, t.float32)
+        ms = np.zeros(4, np.float32)
+        _lib.check(self.lib.dy_postproc_profile(self.h, _ptr(y[0]), _ptr(y[1]), _ptr(y[2]), _ptr(score_maps),
+                                                0 if layout == 'nhwc' else 1, y[0].shape[0], _ptr(windows),
+                                                float(det_thresh), _ptr(masks_out), int(reps),
+                                                ms.ctypes.data_as(C.c_void_p), self._stream()), 'dy_postproc_profile')
+        return dict(decode=float(ms[0]), nms=float(ms[1]), finalize=float(ms[2]), masks=float(ms[3]))
+
 
 def set_option(name, value):
     """dy_set_option: planning overrides of the conv engine ('tc_resident', 'tc_halo'; -1 = auto)."""

@@ -149,6 +149,14 @@ int dy_nms(dy_net* net, const float* box_dev, const int32_t* cls_dev, const floa
 int dy_assemble_masks(dy_net* net, const float* score_dev, int32_t layout, int32_t B, const float* det_box_dev,
                       const int32_t* det_count_dev, float* masks_dev, void* stream);
 
+/* Measurement aid for bench.py: device milliseconds of each post-processing kernel (decode+threshold,
+ * per-class NMS, top-k/finalize, mask assembly), each launched `reps` times back to back between two
+ * CUDA events on `stream`; ms_host[4] receives the per-launch averages.  Same inputs as dy_detect +
+ * dy_assemble_masks (score maps: layout 0 = NHWC, 1 = planar). */
+int dy_postproc_profile(dy_net* net, const float* yolo8_dev, const float* yolo16_dev, const float* yolo32_dev,
+                        const float* score_dev, int32_t layout, int32_t B, const float* windows_dev, float det_thresh,
+                        float* masks_dev, int32_t reps, float* ms_host, void* stream);
+
 /* One convolution of the reference's builders through the same engine the network uses
  * (conv / conv_bn / res_conv_bn, yolo3_net_pos.py:109-151): x [B,H,W,cin] fp32 NHWC (device),
  * w HWIO [k,k,cin,cout] fp32 (host), per-channel scale/shift (host; folded BN or 1/bias),
