@@ -498,7 +498,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int nslab = p.block_n / p.slab;
         const bool elected = wg_tid == 0;
         const bool dual = p.out[1].mode != OUT_NONE;
-        if (dual) s_dst[wg][1][row] = dest_offset(p, p.out[1], px, m);
+        // Double buffered by tile parity: a warp that has finished this tile's cooperative stores writes
+        // the NEXT tile's offsets while slower warps of the warpgroup are still reading this tile's (there
+        // is no warpgroup barrier between two tiles; within a tile every slab has one, so nobody can be
+        // two tiles ahead).
+        // (the TMA path needs no table for out[0], so s_dst[wg][0..1] serve as the two parities)
+        long long* dst2 = s_dst[wg][(it >> 1) & 1];
+        if (dual) dst2[row] = dest_offset(p, p.out[1], px, m);
         if (elected && has_res && !res_primed) {
           // very first slab of this warpgroup: nothing has used the buffers yet
           mbar_expect_tx(&res_full[wg][sc & 1], buf_bytes);
@@ -567,7 +573,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // second destination form (space-to-depth / upsampled): cooperative vector stores
             for (int idx = wg_tid; idx < kBlockM * vpr; idx += 128) {
               const int rr = idx >> vsh, cj = idx & (vpr - 1);
-              const long long d1 = s_dst[wg][1][rr];
+              const long long d1 = dst2[rr];
               if (d1 < 0) continue;
               const int sw = (p.slab == 64) ? (rr & 7) : ((rr >> 1) & 3);
               const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + ((cj ^ sw) << 4));

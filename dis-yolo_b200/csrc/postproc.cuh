@@ -66,5 +66,6 @@ int launch_decode(const DecodeArgs& a, cudaStream_t st);
 int launch_nms(const NmsArgs& a, cudaStream_t st);
 int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
 int launch_masks(const MaskArgs& a, cudaStream_t st);
+void masks_set_streaming(int on);   // 1 (default): st.global.cs streaming stores, 0: plain stores
 
 }  // namespace dy
