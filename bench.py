@@ -313,7 +313,8 @@ def run_ours(args):
     # latency-bound (reported as times only).
     yol = [eng.yolo(s, B) for s in range(3)]
     mp = eng.mask_pos(B)
-    pp_ms = eng.postproc_profile(yol, mp, win, THRESH, out['masks'], layout='nhwc', reps=20)
+    mp = mp.permute(0, 3, 1, 2).contiguous()       # the engine's own score-map layout: planar [B,9,S,S]
+    pp_ms = eng.postproc_profile(yol, mp, win, THRESH, out['masks'], layout='planar', reps=20)
     n0 = eng.num_candidates
     decode_bytes = B * n0 * 8 * 4
     mask_bytes = dets * sm * sm * 4

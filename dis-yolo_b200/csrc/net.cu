@@ -447,6 +447,11 @@ struct dy_net {
   __nv_bfloat16* dzb_scratch = nullptr;   // bf16 engine: dz of the layer being differentiated (P1)
   __nv_bfloat16* pool_scratch = nullptr;  // bf16 engine: 2x2-pooled dz of a concat consumer (P1, low resolution)
   long long adam_step = 0;
+  // device tables for the one-launch multi-tensor kernels (Adam / L2, BN moving averages + fold, repacking)
+  ParamSeg* pseg_dev = nullptr;
+  BnSeg* bseg_dev = nullptr;
+  PackSeg* kseg_dev = nullptr;
+  int n_pseg = 0, n_bseg = 0, n_kseg = 0, max_pack_tiles = 0;
 };
 
 namespace dy {
@@ -1523,6 +1528,36 @@ static int train_init(dy_net* net) {
   for (int b = 0; b < B; ++b) { w[4 * b] = 0; w[4 * b + 1] = 0; w[4 * b + 2] = 1; w[4 * b + 3] = 1; }
   DY_CUDA(cudaMemcpy(net->train_windows, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
   if (bf16) DY_TRY(train_init_tc(net));
+  // segment tables of the multi-tensor kernels
+  std::vector<ParamSeg> ps;
+  std::vector<BnSeg> bs;
+  std::vector<PackSeg> ks;
+  for (int n = 1; n <= 82; ++n) {
+    LayerState& s = L[n];
+    const LayerDef& d = s.def;
+    if (!s.unlocked) continue;
+    const int C = d.cout;
+    ps.push_back(ParamSeg{s.d_w_f32, s.off_w, (long long)s.K * C, kL2, 0});
+    if (d.bn) {
+      ps.push_back(ParamSeg{s.d_gamma, s.off_g, C, 0.f, 0});
+      ps.push_back(ParamSeg{s.d_beta, s.off_b, C, 0.f, 0});
+      bs.push_back(BnSeg{s.d_mean, s.d_var, s.bmean, s.bvar, s.d_gamma, s.d_beta, s.d_scale, s.d_shift, C, 0});
+    } else {
+      ps.push_back(ParamSeg{s.d_bias, s.off_b, C, kL2, 0});
+    }
+    if (bf16) {
+      ks.push_back(PackSeg{s.d_w_f32, s.d_wpk, s.wdg0, s.wdg1, s.K, C, s.cout_pad, d.k, d.cin0, d.cin1, s.Cg, 0});
+      const int tiles = ((s.K + 31) / 32) * ((s.cout_pad + 31) / 32);
+      if (tiles > net->max_pack_tiles) net->max_pack_tiles = tiles;
+    }
+  }
+  net->n_pseg = (int)ps.size(); net->n_bseg = (int)bs.size(); net->n_kseg = (int)ks.size();
+  DY_TRY(dev_alloc(net, (void**)&net->pseg_dev, ps.size() * sizeof(ParamSeg)));
+  DY_TRY(dev_alloc(net, (void**)&net->bseg_dev, bs.size() * sizeof(BnSeg)));
+  DY_TRY(dev_alloc(net, (void**)&net->kseg_dev, ks.size() * sizeof(PackSeg)));
+  if (!ps.empty()) DY_CUDA(cudaMemcpy(net->pseg_dev, ps.data(), ps.size() * sizeof(ParamSeg), cudaMemcpyHostToDevice));
+  if (!bs.empty()) DY_CUDA(cudaMemcpy(net->bseg_dev, bs.data(), bs.size() * sizeof(BnSeg), cudaMemcpyHostToDevice));
+  if (!ks.empty()) DY_CUDA(cudaMemcpy(net->kseg_dev, ks.data(), ks.size() * sizeof(PackSeg), cudaMemcpyHostToDevice));
   net->train_ready = true;
   return DY_OK;
 }
@@ -1901,12 +1936,8 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   note_launch(2);
   DY_TRY(launch_mask_loss(ma, st));
   // L2 regulariser over unlocked weights and biases (:38,118-123,138-140)
-  for (int n = 1; n <= 82; ++n) {
-    if (!L[n].unlocked) continue;
-    note_launch();
-    DY_TRY(launch_sumsq(L[n].d_w_f32, (long long)L[n].K * L[n].def.cout, 0.5 * kL2, net->loss_acc + 6, st));
-    if (!L[n].def.bn) DY_TRY(launch_sumsq(L[n].d_bias, L[n].def.cout, 0.5 * kL2, net->loss_acc + 6, st));
-  }
+  note_launch();
+  DY_TRY(launch_sumsq_multi(net->pseg_dev, net->n_pseg, net->loss_acc + 6, st));
   double acc[8];
   DY_CUDA(cudaMemcpyAsync(acc, net->loss_acc, 8 * 8, cudaMemcpyDeviceToHost, st));
   DY_CUDA(cudaStreamSynchronize(st));
@@ -1936,28 +1967,20 @@ int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad
   net->adam_step += 1;
   const double t = (double)net->adam_step;
   const float lr_t = (float)(lr * sqrt(1.0 - pow((double)kAdamB2, t)) / (1.0 - pow((double)kAdamB1, t)));
+  // one launch each: Adam over every trainable tensor, moving averages + inference fold of every trained
+  // BatchNorm, bf16 re-packing of the forward / dgrad operands
+  note_launch(2);
+  DY_TRY(launch_adam_multi(net->pseg_dev, net->n_pseg, grad_flat_dev, net->adam_m, net->adam_v, lr_t, kAdamB1, kAdamB2,
+                           kAdamEps, grad_scale, st));
+  DY_TRY(launch_bn_post_multi(net->bseg_dev, net->n_bseg, kBnDecay, net->cfg.bn_eps, st));
   for (int n = 1; n <= 82; ++n) {
     LayerState& s = L[n];
-    if (!s.unlocked) continue;
-    const int C = s.def.cout;
-    const long long nw = (long long)s.K * C;
-    note_launch(3);
-    DY_TRY(launch_adam(s.d_w_f32, grad_flat_dev + s.off_w, net->adam_m + s.off_w, net->adam_v + s.off_w, nw, lr_t,
-                       kAdamB1, kAdamB2, kAdamEps, kL2, grad_scale, st));
-    if (s.def.bn) {
-      DY_TRY(launch_adam(s.d_gamma, grad_flat_dev + s.off_g, net->adam_m + s.off_g, net->adam_v + s.off_g, C, lr_t,
-                         kAdamB1, kAdamB2, kAdamEps, 0.f, grad_scale, st));
-      DY_TRY(launch_adam(s.d_beta, grad_flat_dev + s.off_b, net->adam_m + s.off_b, net->adam_v + s.off_b, C, lr_t,
-                         kAdamB1, kAdamB2, kAdamEps, 0.f, grad_scale, st));
-      DY_TRY(launch_moving_update(s.d_mean, s.d_var, s.bmean, s.bvar, C, kBnDecay, st));
-      DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, C, s.d_scale, s.d_shift, st));
-    } else {
-      DY_TRY(launch_adam(s.d_bias, grad_flat_dev + s.off_b, net->adam_m + s.off_b, net->adam_v + s.off_b, C, lr_t,
-                         kAdamB1, kAdamB2, kAdamEps, kL2, grad_scale, st));
-      DY_CUDA(cudaMemcpyAsync(s.d_shift, s.d_bias, C * 4, cudaMemcpyDeviceToDevice, st));
-    }
-    // tensor-core engine: refresh the bf16 GEMM operands (forward and dgrad) from the fp32 master weights
-    if (net->cfg.precision == DY_PRECISION_BF16) DY_TRY(repack_tc(net, n, st));
+    if (s.unlocked && !s.def.bn)
+      DY_CUDA(cudaMemcpyAsync(s.d_shift, s.d_bias, s.def.cout * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  if (net->cfg.precision == DY_PRECISION_BF16) {
+    note_launch(2);
+    DY_TRY(launch_pack_multi(net->kseg_dev, net->n_kseg, net->max_pack_tiles, st));
   }
   return DY_OK;
 }

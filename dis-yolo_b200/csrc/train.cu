@@ -529,6 +529,55 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+__global__ void __launch_bounds__(kT)
+adam_multi_kernel(const ParamSeg* __restrict__ segs, const float* __restrict__ g, float* __restrict__ m,
+                  float* __restrict__ v, float lr_t, float b1, float b2, float eps, float grad_scale) {
+  const ParamSeg sg = segs[blockIdx.y];
+  float* __restrict__ p = sg.p;
+  const float* __restrict__ gs = g + sg.off;
+  float* __restrict__ ms = m + sg.off;
+  float* __restrict__ vs = v + sg.off;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < sg.n; i += (long long)gridDim.x * kT) {
+    const float pv = p[i];
+    const float gg = gs[i] * grad_scale + sg.l2 * pv;
+    const float mm = b1 * ms[i] + (1.f - b1) * gg;
+    const float vv = b2 * vs[i] + (1.f - b2) * gg * gg;
+    ms[i] = mm;
+    vs[i] = vv;
+    p[i] = pv - lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(kT) sumsq_multi_kernel(const ParamSeg* __restrict__ segs, double* out) {
+  __shared__ double red[kT / 32];
+  const ParamSeg sg = segs[blockIdx.y];
+  if (!(sg.l2 > 0.f)) return;
+  double s = 0;
+  for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < sg.n; i += (long long)gridDim.x * kT)
+    s += (double)sg.p[i] * (double)sg.p[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < kT / 32; ++w) t += red[w];
+    if (t != 0.0) atomicAdd(out, t * 0.5 * (double)sg.l2);
+  }
+}
+
+__global__ void bn_post_multi_kernel(const BnSeg* __restrict__ segs, float decay, float eps) {
+  const BnSeg sg = segs[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= sg.C) return;
+  const float mm = sg.mean[c] * decay + sg.bmean[c] * (1.f - decay);
+  const float mv = sg.var[c] * decay + sg.bvar[c] * (1.f - decay);
+  sg.mean[c] = mm;
+  sg.var[c] = mv;
+  const float inv = sg.gamma[c] / sqrtf(mv + eps);
+  sg.scale[c] = inv;
+  sg.shift[c] = sg.beta[c] - mm * inv;
+}
+
 __global__ void moving_update_kernel(float* mm, float* mv, const float* bm, const float* bv, int C, float decay) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -645,6 +694,22 @@ int launch_mask_loss(const MaskLossArgs& a, cudaStream_t st) {
   mask_roi_kernel<<<a.B, 32, 0, st>>>(a);
   DY_CUDA(cudaGetLastError());
   mask_loss_kernel<<<dim3(10, a.B), kT, 0, st>>>(a);
+  DY_LAUNCH_OK();
+}
+int launch_adam_multi(const ParamSeg* segs_dev, int nseg, const float* g, float* m, float* v, float lr_t, float b1,
+                      float b2, float eps, float grad_scale, cudaStream_t st) {
+  if (nseg <= 0) return DY_OK;
+  adam_multi_kernel<<<dim3(148, nseg), kT, 0, st>>>(segs_dev, g, m, v, lr_t, b1, b2, eps, grad_scale);
+  DY_LAUNCH_OK();
+}
+int launch_sumsq_multi(const ParamSeg* segs_dev, int nseg, double* out, cudaStream_t st) {
+  if (nseg <= 0) return DY_OK;
+  sumsq_multi_kernel<<<dim3(32, nseg), kT, 0, st>>>(segs_dev, out);
+  DY_LAUNCH_OK();
+}
+int launch_bn_post_multi(const BnSeg* segs_dev, int nseg, float decay, float eps, cudaStream_t st) {
+  if (nseg <= 0) return DY_OK;
+  bn_post_multi_kernel<<<dim3(4, nseg), 256, 0, st>>>(segs_dev, decay, eps);
   DY_LAUNCH_OK();
 }
 int launch_sumsq(const float* p, long long n, double scale, double* out, cudaStream_t st) {

@@ -82,6 +82,26 @@ int launch_sumsq(const float* p, long long n, double scale, double* out, cudaStr
 // g' = g*grad_scale + l2*p ; m,v update ; p -= lr_t*m/(sqrt(v)+eps)      (tf.train.AdamOptimizer)
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
                 float l2, float grad_scale, cudaStream_t st);
+// ---- multi-tensor forms: ONE launch over a device table of segments (blockIdx.y = segment) ------------
+struct ParamSeg {      // one trainable tensor
+  float* p;            // fp32 master parameter
+  long long off;       // offset into the flat gradient / Adam m / Adam v vectors
+  long long n;
+  float l2;            // 1e-4 for conv weights and biases, 0 for BatchNorm gamma / beta (:38,83-84)
+  int pad_;
+};
+struct BnSeg {         // one unlocked BatchNorm layer: moving averages (:92-95) + inference fold
+  float *mean, *var;
+  const float *bmean, *bvar, *gamma, *beta;
+  float *scale, *shift;
+  int C, pad_;
+};
+int launch_adam_multi(const ParamSeg* segs_dev, int nseg, const float* g, float* m, float* v, float lr_t, float b1,
+                      float b2, float eps, float grad_scale, cudaStream_t st);
+// out += sum over segments with l2 > 0 of 0.5 * l2 * sum p^2
+int launch_sumsq_multi(const ParamSeg* segs_dev, int nseg, double* out, cudaStream_t st);
+int launch_bn_post_multi(const BnSeg* segs_dev, int nseg, float decay, float eps, cudaStream_t st);
+
 int launch_moving_update(float* mov_mean, float* mov_var, const float* bmean, const float* bvar, int C, float decay,
                          cudaStream_t st);
 int launch_refold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int C,

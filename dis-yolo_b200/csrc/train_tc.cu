@@ -356,6 +356,43 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, int k, int cin_to
   }
 }
 
+__global__ void pack_fwd_multi_kernel(const PackSeg* __restrict__ segs) {
+  __shared__ float tile[32][33];
+  const PackSeg sg = segs[blockIdx.y];
+  const int tiles_k = (sg.K + 31) / 32, tiles_c = (sg.cout_pad + 31) / 32;
+  if ((int)blockIdx.x >= tiles_k * tiles_c) return;
+  const int k0 = ((int)blockIdx.x % tiles_k) * 32, c0 = ((int)blockIdx.x / tiles_k) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int kk = k0 + i, co = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (kk < sg.K && co < sg.cout) ? sg.w[(size_t)kk * sg.cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int co = c0 + i, kk = k0 + threadIdx.x;
+    if (co < sg.cout_pad && kk < sg.K) sg.wpk[(size_t)co * sg.K + kk] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void pack_dgrad_multi_kernel(const PackSeg* __restrict__ segs) {
+  const PackSeg sg = segs[blockIdx.y >> 1];
+  const int which = blockIdx.y & 1;
+  __nv_bfloat16* out = which ? sg.wdg1 : sg.wdg0;
+  if (out == nullptr) return;
+  const int kk = sg.k * sg.k, cin_total = sg.cin0 + sg.cin1;
+  const int ci0 = which ? sg.cin0 : 0, cin_sel = which ? sg.cin1 : sg.cin0;
+  const long long total = (long long)cin_sel * kk * sg.Cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % sg.Cg);
+    const long long t = i / sg.Cg;
+    const int tp = (int)(t % kk);
+    const int ci = (int)(t / kk);
+    float v = 0.f;
+    if (co < sg.cout) v = sg.w[((size_t)(kk - 1 - tp) * cin_total + ci0 + ci) * sg.cout + co];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // wgrad: one CTA per (tap, 128-input-channel block, N tile, K split).  256 threads:
 //   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue.
@@ -632,6 +669,15 @@ int launch_pack_dgrad_bf16(const float* w, int k, int cin_total, int ci0, int ci
                            __nv_bfloat16* out, cudaStream_t st) {
   pack_dgrad_kernel<<<grid_for((long long)cin_sel * k * k * Cg), kT, 0, st>>>(w, k, cin_total, ci0, cin_sel, cout, Cg,
                                                                                out);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_pack_multi(const PackSeg* segs_dev, int nseg, int max_tiles, cudaStream_t st) {
+  if (nseg <= 0) return DY_OK;
+  pack_fwd_multi_kernel<<<dim3(max_tiles, nseg), dim3(32, 8), 0, st>>>(segs_dev);
+  DY_CUDA(cudaGetLastError());
+  pack_dgrad_multi_kernel<<<dim3(148, 2 * nseg), kT, 0, st>>>(segs_dev);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

@@ -48,6 +48,16 @@ int launch_pack_fwd_bf16(const float* w, int K, int cout, int cout_pad, __nv_bfl
 int launch_pack_dgrad_bf16(const float* w, int k, int cin_total, int ci0, int cin_sel, int cout, int Cg,
                            __nv_bfloat16* out, cudaStream_t st);
 
+// all trained layers in ONE launch each (blockIdx.y = layer): forward operand and dgrad operands
+struct PackSeg {
+  const float* w;          // fp32 master HWIO
+  __nv_bfloat16* wpk;      // [cout_pad][K]
+  __nv_bfloat16* wdg0;     // dgrad operand towards src0 or null
+  __nv_bfloat16* wdg1;     // dgrad operand towards src1 or null
+  int K, cout, cout_pad, k, cin0, cin1, Cg, pad_;
+};
+int launch_pack_multi(const PackSeg* segs_dev, int nseg, int max_tiles, cudaStream_t st);
+
 // ---- wgrad on tcgen05 -------------------------------------------------------------------------
 struct WgradParams {
   int M;               // pixel rows to contract over = B*(H+1)*(W+1)
