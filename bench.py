@@ -529,6 +529,11 @@ def main():
         rank, _, _ = dist_env()
         if rank == 0:
             g.build()
+        if os.environ.get('DY_OPTS'):          # A/B aid: DY_OPTS="wgrad_fuse_kw=0,tc_halo=0" -> dy_set_option
+            from disyolo_b200.engine import set_option
+            for kv in os.environ['DY_OPTS'].split(','):
+                k, v = kv.split('=')
+                set_option(k.strip(), int(v))
         if args.workload == 'train':
             run_train(args)
         else:

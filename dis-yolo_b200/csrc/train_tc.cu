@@ -402,6 +402,7 @@ __global__ void pack_dgrad_multi_kernel(const PackSeg* __restrict__ segs) {
 // "stride" offset = 8 pixel rows; one K=16 step advances the start address by 16 rows.
 // -------------------------------------------------------------------------------------------
 constexpr int kWgradRows = 64;     // pixel rows (K) per pipeline stage
+constexpr int kWgradHaloRows = 72; // fused 3x3 mode: 64 + 2 halo rows, rounded up to the 8-row swizzle group
 constexpr int kWgradMaxStages = 6;
 
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -426,7 +427,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   const int nt = u % p.n_tiles_n; u /= p.n_tiles_n;
   const int blk_total = p.src_blk[0] + (p.nsrc > 1 ? p.src_blk[1] : 0);
   const int cb = u % blk_total;
-  const int tap = u / blk_total;
+  const int tap = u / blk_total;                 // fused mode: the kernel ROW kh (taps kh*3 .. kh*3+2)
+  const int nacc = p.fuse_kw ? 3 : 1;            // accumulators = taps sharing this CTA's dz boxes
+  const int a_rows = p.fuse_kw ? kWgradHaloRows : kWgradRows;
   const int src = cb >= p.src_blk[0] ? 1 : 0;
   const int ci0 = (src ? cb - p.src_blk[0] : cb) * 128;
   const int c_src = p.src_c[src], aw = p.src_aw[src];
@@ -438,9 +441,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   if (c_end > p.total_chunks) c_end = p.total_chunks;
   const int nchunks = c_end - c_begin;
 
-  const uint32_t a_box = (uint32_t)kWgradRows * aw * 2;          // bytes of one A box
+  const uint32_t a_box = (uint32_t)a_rows * aw * 2;              // bytes of one A box
   const uint32_t b_box = (uint32_t)kWgradRows * p.z_aw * 2;
-  const uint32_t a_bytes = 128u * kWgradRows * 2;                // 16 KB: all 128 channels
+  const uint32_t a_bytes = 128u * (uint32_t)a_rows * 2;          // 16 KB (18 KB with the halo): all 128 channels
   const uint32_t stage_bytes = a_bytes + (uint32_t)p.block_n * kWgradRows * 2;
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -465,7 +468,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_smem, 256u);
+    tmem_alloc(&tmem_base_smem, p.fuse_kw ? 512u : 256u);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -477,7 +480,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     if (elect_one() && nchunks > 0) {
       const CUtensorMap* xm = src ? &mapX1 : &mapX0;
       const uint32_t tx = (uint32_t)a_valid * a_box + (uint32_t)b_boxes * b_box;
-      const int shift = p.tap_shift[tap];
+      // fused: one (64+8)-row X box starting one pixel left of the kernel row's centre tap feeds kw = 0, 1, 2
+      const int shift = p.fuse_kw ? p.tap_shift[tap * 3] : p.tap_shift[tap];
       uint32_t stage = 0, phase = 0;
       for (int c = c_begin; c < c_end; ++c) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -508,9 +512,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
         const uint32_t sa = smem_base + stage * stage_bytes;
 #pragma unroll
         for (int k = 0; k < kWgradRows / 16; ++k) {
-          const uint64_t adesc = mn_desc(sa + k * kstep_a, lbo_a, sbo_a, lay_a);
           const uint64_t bdesc = mn_desc(sa + a_bytes + k * kstep_b, lbo_b, sbo_b, lay_b);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
+          // tap kw = the same box read kw pixel rows further down: the K (row) offset of an MN-major operand is
+          // linear in the start address (SBO = 8 rows), and the swizzle is a function of the smem address
+          for (int t = 0; t < nacc; ++t) {
+            const uint64_t adesc = mn_desc(sa + k * kstep_a + (uint32_t)t * aw * 2, lbo_a, sbo_a, lay_a);
+            umma_bf16(tmem_base + (uint32_t)(t * p.block_n), adesc, bdesc, idesc, acc);
+          }
           acc = 1u;
         }
         umma_commit(&empty_bar[stage]);
@@ -525,21 +533,43 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
     const int q = warp & 3;
     const int row = q * 32 + lane;                 // input channel inside the block == TMEM lane
     const bool valid = ci0 + row < c_src;
-    float* drow = p.dw + ((size_t)tap * p.cin_total + p.src_koff[src] + ci0 + row) * p.cout;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool vec4 = (p.cout & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw) & 15) == 0;
     uint32_t r[16];
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      tmem_ld16(taddr + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (valid) {
+    for (int t = 0; t < nacc; ++t) {
+      const int tp = p.fuse_kw ? tap * 3 + t : tap;
+      float* drow = p.dw + ((size_t)tp * p.cin_total + p.src_koff[src] + ci0 + row) * p.cout;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        tmem_ld16(taddr + (uint32_t)(t * p.block_n + c0), r);
+        tmem_ld_wait();
+        if (valid) {
+          const int co0 = n0 + c0;
+          if (vec4 && co0 + 16 <= p.cout) {
+            // 16 consecutive fp32 of one dW row: four 16-byte reductions / stores instead of sixteen scalar ones
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = n0 + c0 + j;
-          if (co < p.cout) {
-            if (p.ksplit > 1) atomicAdd(drow + co, __uint_as_float(r[j]));
-            else drow[co] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; j += 4) {
+              float* d = drow + co0 + j;
+              if (p.ksplit > 1) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(r[j])),
+                             "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])),
+                             "f"(__uint_as_float(r[j + 3]))
+                             : "memory");
+              } else {
+                *reinterpret_cast<float4*>(d) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = co0 + j;
+              if (co < p.cout) {
+                if (p.ksplit > 1) atomicAdd(drow + co, __uint_as_float(r[j]));
+                else drow[co] = __uint_as_float(r[j]);
+              }
+            }
           }
         }
       }
@@ -549,13 +579,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256u);
+    tmem_dealloc(tmem_base, p.fuse_kw ? 512u : 256u);
   }
 }
 
 int g_wdbg[4] = {0, 0, 0, 0};
+int g_wgrad_fuse = 1;
 
 }  // namespace
+
+void wgrad_set_fuse(int on) { g_wgrad_fuse = on; }
 
 void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
   g_wdbg[0] = lbo_a; g_wdbg[1] = sbo_a; g_wdbg[2] = lbo_b; g_wdbg[3] = sbo_b;
@@ -705,16 +738,23 @@ int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, i
   p.cout = cout;
   p.zc = zc;
   p.z_aw = zc % 64 == 0 ? 64 : 32;
-  p.block_n = zc >= 256 ? 256 : zc;          // zc in {32, 64, 128, 256, 512, 1024}
+  // 3x3: the three horizontal taps of a kernel row share one dz box and one halo'd X box (three
+  // accumulators, 3 * block_n <= 512 TMEM columns) -- X and dz are read from L2 3 times instead of 9
+  // Measured (ncu, batch 16): fusing wins where it keeps the N tile (dz <= 128 channels: conv81 912 -> 567 us,
+  // conv78 248 -> 154 us) and loses where it would halve it (dz >= 256 channels); option value 2 forces it.
+  p.fuse_kw = (k == 3 && (g_wgrad_fuse == 2 || (g_wgrad_fuse == 1 && zc <= 128))) ? 1 : 0;
+  const int bn_max = p.fuse_kw ? 128 : 256;
+  p.block_n = zc >= bn_max ? bn_max : zc;    // zc in {32, 64, 128, 256, 512, 1024}
   DY_CHECK(zc % p.block_n == 0 && p.block_n % p.z_aw == 0 && p.block_n % 16 == 0, "dz channel tiling");
   p.n_tiles_n = zc / p.block_n;
-  const size_t stage = 128 * (size_t)kWgradRows * 2 + (size_t)p.block_n * kWgradRows * 2;
+  const int a_rows = p.fuse_kw ? kWgradHaloRows : kWgradRows;
+  const size_t stage = 128 * (size_t)a_rows * 2 + (size_t)p.block_n * kWgradRows * 2;
   int ns = (int)((200 * 1024) / stage);
   if (ns > kWgradMaxStages) ns = kWgradMaxStages;
   p.num_stages = ns;
   p.dw = dw;
-  DY_TRY(make_tmap_2d(&plan->x[0], x0, rows_max, c0, c0, p.src_aw[0], kWgradRows));
-  if (c1 > 0) DY_TRY(make_tmap_2d(&plan->x[1], x1, rows_max, c1, c1, p.src_aw[1], kWgradRows));
+  DY_TRY(make_tmap_2d(&plan->x[0], x0, rows_max, c0, c0, p.src_aw[0], a_rows));
+  if (c1 > 0) DY_TRY(make_tmap_2d(&plan->x[1], x1, rows_max, c1, c1, p.src_aw[1], a_rows));
   else plan->x[1] = plan->x[0];
   DY_TRY(make_tmap_2d(&plan->z, dz, rows_max, zc, zc, p.z_aw, kWgradRows));
   return DY_OK;
@@ -726,18 +766,19 @@ int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream
   DY_CHECK(M < (1ll << 31) - 256, "too many rows");
   p.M = (int)M;
   p.total_chunks = (int)((M + kWgradRows - 1) / kWgradRows);
-  const int units = p.ntap * (p.src_blk[0] + (p.nsrc > 1 ? p.src_blk[1] : 0)) * p.n_tiles_n;
+  const int units = (p.fuse_kw ? 3 : p.ntap) * (p.src_blk[0] + (p.nsrc > 1 ? p.src_blk[1] : 0)) * p.n_tiles_n;
   // split K only when the (tap, channel block, N tile) units alone leave SMs idle: every split costs a
   // pipeline fill and turns the epilogue's stores into atomics
-  int ksplit = units * 4 >= num_sms * 3 ? 1 : (num_sms + units - 1) / units;
+  // (floor: units * ksplit must not exceed the SM count, or two CTAs would queue for a second wave)
+  int ksplit = units * 4 >= num_sms * 3 ? 1 : num_sms / units;
   if (ksplit < 1) ksplit = 1;
   // keep at least 8 chunks (512 pixel rows) per CTA so that the pipeline fill is amortised
   const int max_split = (p.total_chunks + 7) / 8;
   if (ksplit > max_split) ksplit = max_split;
   if (ksplit < 1) ksplit = 1;
   p.chunks_per_split = (p.total_chunks + ksplit - 1) / ksplit;
-  p.ksplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
-  const size_t stage = 128 * (size_t)kWgradRows * 2 + (size_t)p.block_n * kWgradRows * 2;
+  p.ksplit = (p.total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;     // <= ksplit
+  const size_t stage = 128 * (size_t)(p.fuse_kw ? kWgradHaloRows : kWgradRows) * 2 + (size_t)p.block_n * kWgradRows * 2;
   const size_t smem = (size_t)p.num_stages * stage + 1024;
   static bool attr = false;
   if (!attr) {

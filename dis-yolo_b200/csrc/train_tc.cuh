@@ -66,6 +66,7 @@ struct WgradParams {
   int src_aw[2];       // TMA box width of each source: 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
   int src_koff[2];     // first dW row of each source inside a tap
   int src_blk[2];      // ceil(c / 128)
+  int fuse_kw;         // 3x3 only: 1 = one CTA per kernel ROW, three accumulators (kw = 0,1,2) share the dz boxes
   int ntap;            // 1 or 9
   int tap_shift[9];    // pixel-row shift of X for each tap: (kh-1)*(W+1)+(kw-1)
   int cin_total;       // dW rows per tap
@@ -87,5 +88,6 @@ int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, i
 int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream_t st);
 // measurement / bring-up aid: descriptor field overrides (0 = computed value)
 void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b);
+void wgrad_set_fuse(int on);   // A/B aid: 0 = one CTA per tap (no sharing), 1 (default) = fused kernel rows
 
 }  // namespace dy
