@@ -417,6 +417,7 @@ struct dy_net {
   int* det_count_ws = nullptr;
   // dy_forward_host*: two device-side slots so that the copies of one step overlap the compute of
   // the next (H2D, compute and D2H each on their own stream)
+  static constexpr int kHostSlots = 3;
   struct HostSlot {
     float* images = nullptr;
     float* windows = nullptr;
@@ -427,7 +428,7 @@ struct dy_net {
     cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr;
     int B = 0;
     bool busy = false, want_masks = false;
-  } slot[2];
+  } slot[kHostSlots];
   int next_slot = 0;
   cudaStream_t h2d_stream = nullptr, comp_stream = nullptr, d2h_stream = nullptr;
   // ---- training ----
@@ -1030,7 +1031,7 @@ int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, cons
   DY_TRY(host_slots_init(net));
   const int id = net->next_slot;
   auto& sl = net->slot[id];
-  DY_CHECK(!sl.busy, "both pipeline slots are in flight: call dy_forward_host_end first");
+  DY_CHECK(!sl.busy, "all three pipeline slots are in flight: call dy_forward_host_end first");
   const int S = net->S;
   DY_CUDA(cudaMemcpyAsync(sl.images, images_host, (size_t)B * S * S * 3 * 4, cudaMemcpyHostToDevice, net->h2d_stream));
   DY_CUDA(cudaMemcpyAsync(sl.windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, net->h2d_stream));
@@ -1042,7 +1043,7 @@ int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, cons
   sl.B = B;
   sl.busy = true;
   sl.want_masks = want_masks != 0;
-  net->next_slot = id ^ 1;
+  net->next_slot = (id + 1) % dy_net::kHostSlots;
   *ticket = id;
   return DY_OK;
 }
@@ -1050,7 +1051,7 @@ int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, cons
 int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
                         int32_t* det_count_host, float* masks_host) {
   DY_CHECK(net && det_box_host && det_count_host, "null argument");
-  DY_CHECK(ticket == 0 || ticket == 1, "bad ticket");
+  DY_CHECK(ticket >= 0 && ticket < dy_net::kHostSlots, "bad ticket");
   auto& sl = net->slot[ticket];
   DY_CHECK(sl.busy, "ticket is not in flight");
   DY_CHECK(!masks_host || sl.want_masks, "masks were not requested at dy_forward_host_begin");

@@ -233,13 +233,17 @@ class Engine(object):
             buf = self.pinned(key, shape, t.float32)
             buf.copy_(x if isinstance(x, t.Tensor) else t.from_numpy(np.ascontiguousarray(x, np.float32)))
             return buf
+        if getattr(self, '_inflight', 0) >= 3:
+            # refuse BEFORE touching a staging buffer: all three belong to batches whose H2D may still run
+            raise _lib.DisYoloError('all three pipeline slots are in flight: call forward_host_end first')
         n = getattr(self, '_begin_count', 0)
-        self._begin_count = n + 1
-        img = stage('img%d' % (n & 1), images, (B, S, S, 3))
-        win = stage('win%d' % (n & 1), windows, (B, 4))
+        img = stage('img%d' % (n % 3), images, (B, S, S, 3))
+        win = stage('win%d' % (n % 3), windows, (B, 4))
         ticket = C.c_int32(-1)
         _lib.check(self.lib.dy_forward_host_begin(self.h, _ptr(img), B, _ptr(win), float(det_thresh),
                                                   int(bool(want_masks)), C.byref(ticket)), 'dy_forward_host_begin')
+        self._begin_count = n + 1
+        self._inflight = getattr(self, '_inflight', 0) + 1
         return (ticket.value, B, bool(want_masks), (img, win))
 
     def forward_host_end(self, ticket):
@@ -252,6 +256,7 @@ class Engine(object):
         msk = self.pinned('msk%d' % tid, (B, md, sm, sm), t.float32) if want_masks else None
         _lib.check(self.lib.dy_forward_host_end(self.h, tid, _ptr(raw), _ptr(box), _ptr(cnt), _ptr(msk)),
                    'dy_forward_host_end')
+        self._inflight = max(0, getattr(self, '_inflight', 0) - 1)
         return raw, box, cnt, msk
 
     # ---- training step (bf16 tensor-core engine or fp32 verification engine) ----------------------------------------------------------

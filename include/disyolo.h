@@ -99,10 +99,12 @@ int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const floa
 
 /* The pipelined form of dy_forward_host for back-to-back batches: _begin enqueues H2D + forward
  * for one batch and returns a ticket immediately; _end performs the D2H of that batch and blocks
- * until the host buffers are filled.  Two tickets may be in flight, so
- *     t0 = begin(batch0); loop { t1 = begin(next); end(t0); t0 = t1; }
- * overlaps the copies of one batch with the convolutions of the next (three streams, two device
- * slots).  dy_forward_host == begin + end. */
+ * until the host buffers are filled.  Up to three tickets may be in flight (three streams, three
+ * device slots), so
+ *     t0 = begin(b0); t1 = begin(b1); loop { t2 = begin(next); end(t0); t0 = t1; t1 = t2; }
+ * overlaps the H2D of batch k+2 and the D2H of batch k with the convolutions of batch k+1 without a
+ * bubble (with two slots the next H2D could only start after the previous D2H had finished).
+ * dy_forward_host == begin + end. */
 int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, const float* windows_host,
                           float det_thresh, int32_t want_masks, int32_t* ticket);
 int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,

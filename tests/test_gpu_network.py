@@ -132,27 +132,32 @@ def test_session_facade_matches_oracle():
 
 
 def test_pipelined_host_forward_matches_sync():
-    """dy_forward_host_begin/_end with two batches in flight returns exactly what the synchronous
-    dy_forward_host returns for each batch."""
+    """dy_forward_host_begin/_end with three batches in flight returns exactly what the synchronous
+    dy_forward_host returns for each batch; a fourth begin without an end is refused."""
     import torch
     import disyolo_b200 as dy
+    from collections import deque
     B, size = 2, 160
     eng = dy.Engine(image_size=size, max_batch=B, precision='bf16')
     eng.load_weights(O.make_weights('lively', 0))
-    batches = [_inputs(B, size, s) for s in (11, 12, 13)]
+    batches = [_inputs(B, size, s) for s in (11, 12, 13, 14, 15)]
     want = []
     for img, win in batches:
         raw, box, cnt, msk = eng.forward_host(img, win, 0.2)
         want.append((raw.numpy().copy(), box.numpy().copy(), cnt.numpy().copy(),
                      [msk[b, :cnt[b]].numpy().copy() for b in range(B)]))
-    tk = eng.forward_host_begin(batches[0][0], batches[0][1], 0.2)
-    for i in range(3):
-        nxt = eng.forward_host_begin(batches[i + 1][0], batches[i + 1][1], 0.2) if i < 2 else None
-        raw, box, cnt, msk = eng.forward_host_end(tk)
+    flight = deque(eng.forward_host_begin(batches[i][0], batches[i][1], 0.2) for i in range(3))
+    with pytest.raises(Exception):
+        eng.forward_host_begin(batches[3][0], batches[3][1], 0.2)      # all three slots busy
+    begun = 3
+    for i in range(len(batches)):
+        raw, box, cnt, msk = eng.forward_host_end(flight.popleft())
         assert np.array_equal(raw.numpy(), want[i][0]) and np.array_equal(cnt.numpy(), want[i][2])
         for b in range(B):
             assert np.array_equal(msk[b, :cnt[b]].numpy(), want[i][3][b])
-        tk = nxt
+        if begun < len(batches):
+            flight.append(eng.forward_host_begin(batches[begun][0], batches[begun][1], 0.2))
+            begun += 1
     with pytest.raises(Exception):
         eng.forward_host_end((0, B, True, None))        # nothing in flight any more
     eng.close()
