@@ -100,6 +100,35 @@ def test_end_to_end_576(precision):
     eng.close()
 
 
+def test_end_to_end_1152_bf16():
+    """BASELINE configs[4] geometry through the whole tensor-core path: 1152 x 1152 input (81,648
+    candidates, 576 x 576 score maps), low threshold; decode / NMS / top-k / mask assembly checked
+    against the oracle on the engine's own head and score maps."""
+    import torch
+    import disyolo_b200 as dy
+    B, size, thr = 1, 1152, 0.15
+    W = O.make_weights('lively', 0)
+    img, win = _inputs(B, size, 4)
+    eng = dy.Engine(image_size=size, max_batch=B, precision='bf16', max_detection=100)
+    eng.load_weights(W)
+    out = eng.forward(torch.from_numpy(img).cuda(), torch.from_numpy(win).cuda(), thr)
+    torch.cuda.synchronize()
+    yol = [eng.yolo(s, B).cpu().numpy() for s in range(3)]
+    assert [y.shape[1] for y in yol] == [144, 72, 36] and all(np.isfinite(y).all() for y in yol)
+    mp = eng.mask_pos(B).cpu().numpy()
+    assert mp.shape == (B, 576, 576, 9)
+    want = O.filter_detections(O.interpret_output(yol), win, thr, max_detection=100)
+    raw = out['det_raw'].cpu().numpy()
+    assert np.array_equal(raw[..., 4], want[..., 4])
+    assert np.max(np.abs(raw[..., :4] - want[..., :4])) * size < 0.5
+    db, dm = O.val_test(want, mp)
+    cnt = out['det_count'].cpu().numpy()
+    assert cnt[0] == len(db[0]) and cnt[0] > 0
+    for d in range(min(int(cnt[0]), 8)):
+        assert mask_iou(out['masks'][0, d].cpu().numpy(), dm[0][d]) >= 0.99
+    eng.close()
+
+
 def test_session_facade_matches_oracle():
     """The reference's calling convention (calculate_test_map.py:214-229) end to end."""
     import disyolo_b200.yolo.config as cfg
