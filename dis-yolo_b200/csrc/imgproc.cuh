@@ -1,0 +1,36 @@
+// Pre- / post-processing on either side of the hot path: interface.
+//   letterbox   = image_read (calculate_test_map.py:149-176, utils/val_data.py:36-63): bilinear resize of the
+//                 RGB image to fit image_size, 127-padding, /255
+//   postprocess = the per-detection loop of calculate_test_map.py:233-269 / utils/validation_map.py:137-166:
+//                 correct_yolo_boxes (:121-138), crop of the [S,S] sigmoid map, cv2.resize INTER_LINEAR to
+//                 the box size in the original image, > 0.5, paste; merged semantic mask
+#pragma once
+#include "common.cuh"
+
+namespace dy {
+
+// geometry image_read computes on the host (integer arithmetic of the reference, :152-158, :167-168)
+struct LetterboxGeom {
+  int src_h, src_w;   // original image
+  int new_h, new_w;   // resized extent
+  int top, left;      // (size - new) // 2
+  int size;
+};
+LetterboxGeom letterbox_geom(int src_h, int src_w, int size);
+
+// rgb [src_h, src_w, 3] uint8 (device) -> out [size, size, 3] fp32 (device), one image
+int launch_letterbox(const unsigned char* rgb, const LetterboxGeom& g, float* out, cudaStream_t st);
+
+struct PostDet {        // one detection in original-image coordinates
+  int x1, y1, x2, y2;   // corrected box (correct_yolo_boxes)
+  int cx1, cy1, cx2, cy2;   // crop of the [S,S] map: np.around(norm * S)
+  int cls;
+  int valid;            // 0: (y2-y1)*(x2-x1) <= 0 or empty crop -> skipped like the reference's `continue`
+  double scale_x, scale_y;   // cv2.resize source step per destination pixel
+};
+// det_box [n_max,6] = (y1,x1,y2,x2 normalised, class, score), count on the device
+int launch_postprocess(const float* det_box, const int* count, int n_max, const float* masks, int S, int image_h,
+                       int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
+                       unsigned char* full_masks, unsigned char* merged, cudaStream_t st);
+
+}  // namespace dy

@@ -16,6 +16,7 @@
 #include "postproc.cuh"
 #include "train.cuh"
 #include "train_tc.cuh"
+#include "imgproc.cuh"
 
 namespace dy {
 
@@ -1244,6 +1245,36 @@ int dy_postproc_profile(dy_net* net, const float* yolo8_dev, const float* yolo16
     ms_host[i] = ms / (float)reps;
   }
   for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
+int dy_letterbox(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_size, float* out_dev, float* window_host,
+                 void* stream) {
+  DY_CHECK(rgb_dev && out_dev, "null argument");
+  DY_CHECK(h >= 1 && w >= 1 && image_size >= 1, "image geometry");
+  const LetterboxGeom g = letterbox_geom(h, w, image_size);
+  if (window_host) {     // clip window for filter_detections (calculate_test_map.py:163-168)
+    window_host[0] = (float)((double)g.top / image_size);
+    window_host[1] = (float)((double)g.left / image_size);
+    window_host[2] = (float)((double)(g.new_h + g.top) / image_size);
+    window_host[3] = (float)((double)(g.new_w + g.left) / image_size);
+  }
+  note_launch();
+  return launch_letterbox(rgb_dev, g, out_dev, (cudaStream_t)stream);
+}
+
+int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32_t max_det, const float* masks_dev,
+                   int32_t S, int32_t image_h, int32_t image_w, int32_t net_size, int32_t* boxes_out_dev,
+                   uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev, void* stream) {
+  DY_CHECK(det_box_dev && det_count_dev && masks_dev && boxes_out_dev && valid_out_dev, "null argument");
+  DY_CHECK(max_det >= 1 && max_det <= 65535, "max_det");
+  cudaStream_t st = (cudaStream_t)stream;
+  PostDet* ws = nullptr;
+  DY_CUDA(cudaMallocAsync((void**)&ws, (size_t)max_det * sizeof(PostDet), st));
+  note_launch(2);
+  const int rc = launch_postprocess(det_box_dev, det_count_dev, max_det, masks_dev, S, image_h, image_w, net_size, ws,
+                                    boxes_out_dev, valid_out_dev, full_masks_dev, merged_dev, st);
+  cudaFreeAsync(ws, st);
   return rc;
 }
 

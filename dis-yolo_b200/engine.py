@@ -409,6 +409,39 @@ class Engine(object):
                                                 ms.ctypes.data_as(C.c_void_p), self._stream()), 'dy_postproc_profile')
         return dict(decode=float(ms[0]), nms=float(ms[1]), finalize=float(ms[2]), masks=float(ms[3]))
 
+    # ---- either side of the hot path ---------------------------------------
+    def letterbox(self, image_rgb, out=None):
+        """image_read (calculate_test_map.py:149-176) on the GPU: image_rgb [h,w,3] uint8 (numpy or cuda
+        tensor) -> (new_image [S,S,3] fp32 cuda, window [4] float32 numpy)."""
+        t = self.torch
+        img = image_rgb if isinstance(image_rgb, t.Tensor) else t.from_numpy(np.ascontiguousarray(image_rgb, np.uint8))
+        img = img.to(self.device).contiguous()
+        h, w = int(img.shape[0]), int(img.shape[1])
+        S = self.image_size
+        if out is None:
+            out = t.empty((S, S, 3), dtype=t.float32, device=self.device)
+        window = np.zeros(4, np.float32)
+        _lib.check(self.lib.dy_letterbox(_ptr(img), h, w, S, _ptr(out), window.ctypes.data_as(C.c_void_p),
+                                         self._stream()), 'dy_letterbox')
+        return out, window
+
+    def postprocess(self, det_box, det_count, masks, image_h, image_w, want_full=True):
+        """The per-detection loop of calculate_test_map.py:233-269 for one image: det_box [max_det,6],
+        det_count [1] / scalar tensor, masks [max_det,S,S] (cuda) -> dict(boxes [max_det,4] int32 (x1,y1,x2,y2),
+        valid [max_det] uint8, full_masks [max_det,h,w] uint8 or None, merged [h,w] uint8)."""
+        t = self.torch
+        md, S = int(masks.shape[0]), int(masks.shape[1])
+        det_box, masks = self._dev(det_box, t.float32), self._dev(masks, t.float32)
+        det_count = self._dev(det_count, t.int32).reshape(-1)
+        boxes = t.empty((md, 4), dtype=t.int32, device=self.device)
+        valid = t.empty((md,), dtype=t.uint8, device=self.device)
+        full = t.empty((md, image_h, image_w), dtype=t.uint8, device=self.device) if want_full else None
+        merged = t.empty((image_h, image_w), dtype=t.uint8, device=self.device)
+        _lib.check(self.lib.dy_postprocess(_ptr(det_box), _ptr(det_count), md, _ptr(masks), S, int(image_h),
+                                           int(image_w), self.image_size, _ptr(boxes), _ptr(valid), _ptr(full),
+                                           _ptr(merged), self._stream()), 'dy_postprocess')
+        return dict(boxes=boxes, valid=valid, full_masks=full, merged=merged)
+
 
 def set_option(name, value):
     """dy_set_option: planning overrides of the conv engine ('tc_resident', 'tc_halo'; -1 = auto)."""

@@ -151,6 +151,25 @@ int dy_nms(dy_net* net, const float* box_dev, const int32_t* cls_dev, const floa
 int dy_assemble_masks(dy_net* net, const float* score_dev, int32_t layout, int32_t B, const float* det_box_dev,
                       const int32_t* det_count_dev, float* masks_dev, void* stream);
 
+/* ---- either side of the hot path ----------------------------
+ * Replaces image_read (calculate_test_map.py:149-176, utils/val_data.py:36-63): the RGB uint8 image
+ * [h,w,3] (device) is resized with cv2.INTER_LINEAR semantics to fit image_size, embedded in a
+ * 127-filled square and divided by 255 -> out_dev [image_size,image_size,3] fp32; window_host[4]
+ * (may be NULL) receives the clip window (top, left, bottom, right) / image_size. */
+int dy_letterbox(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_size, float* out_dev, float* window_host,
+                 void* stream);
+/* Replaces the per-detection loop of calculate_test_map.py:233-269 (utils/validation_map.py:137-166)
+ * for ONE image: correct_yolo_boxes (:121-138), crop of each [S,S] mask to its box, cv2.resize
+ * INTER_LINEAR to the box size in the original image, > 0.5, paste.  det_box_dev [max_det,6] and
+ * det_count_dev [1] and masks_dev [max_det,S,S] are one image's slice of dy_forward's outputs.
+ * boxes_out_dev [max_det,4] int32 = (x1,y1,x2,y2) in original pixels; valid_out_dev [max_det] = 0 for
+ * detections the reference skips ((y2-y1)*(x2-x1) <= 0); full_masks_dev [max_det,image_h,image_w]
+ * bool bytes (may be NULL); merged_dev [image_h,image_w] = class+1 of the last detection covering
+ * each pixel, 0 elsewhere (may be NULL). */
+int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32_t max_det, const float* masks_dev,
+                   int32_t S, int32_t image_h, int32_t image_w, int32_t net_size, int32_t* boxes_out_dev,
+                   uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev, void* stream);
+
 /* Measurement aid for bench.py: device milliseconds of each post-processing kernel (decode+threshold,
  * per-class NMS, top-k/finalize, mask assembly), each launched `reps` times back to back between two
  * CUDA events on `stream`; ms_host[4] receives the per-launch averages.  Same inputs as dy_detect +

@@ -73,3 +73,23 @@ out['voc_ap'] = dict(rec=[.5, .5, 1.], prec=[1., .5, 2. / 3],
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_kat.json')
 json.dump(out, open(dst, 'w'), indent=1, sort_keys=True)
 print('wrote', dst)
+
+# --- letterbox on seeded synthetic images through the reference's own image_read (bit-level pin for
+# oracle/dis_oracle_io.letterbox; the GPU kernel dy_letterbox is then compared with that oracle) ---
+import hashlib  # noqa: E402
+import tempfile  # noqa: E402
+syn = []
+for seed, (h, w) in enumerate([(348, 620), (700, 500), (576, 576), (1000, 1001), (97, 1300)]):
+    rgb = np.random.default_rng(100 + seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    path = os.path.join(tempfile.gettempdir(), 'dy_golden_%d.png' % seed)
+    cv2.imwrite(path, rgb[:, :, ::-1])                      # image_read reads BGR and converts to RGB
+    img, win = dv.image_read(path)
+    f32 = np.ascontiguousarray(img, np.float32)
+    ys, xs = [0, 100, 288, 400, 575], [0, 57, 288, 431, 575]
+    syn.append(dict(seed=100 + seed, h=h, w=w, window=[float(v) for v in win],
+                    sha256_f32=hashlib.sha256(f32.tobytes()).hexdigest(),
+                    samples=[[y, x, [float(v) for v in f32[y, x]]] for y, x in zip(ys, xs)]))
+out['letterbox_synthetic'] = syn
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_kat.json'), 'w') as f:
+    json.dump(out, f, indent=1, sort_keys=True)
+print('letterbox_synthetic:', len(syn), 'cases')
