@@ -307,6 +307,35 @@ def run_ours(args):
     e2e_value = world * B * n_e2e / e2e_s
     h2d = B * IMAGE * IMAGE * 3 * 4 + B * 16
 
+    # ---- e2e of the whole per-image sequence of the reference's test driver (calculate_test_map.py:208-269):
+    # uint8 images up, letterbox + network + post-processing to original-image masks on the GPU, boxes and
+    # merged masks down (ImagePipeline, two batches in flight) ----
+    pipe_line = None
+    if not args.no_pipeline:
+        ph, pw = 720, 1280
+        pipe = dy.ImagePipeline(eng, ph, pw, depth=2)
+        prng = np.random.default_rng(2000 + rank)
+        frames = [torch.from_numpy(prng.integers(0, 256, (ph, pw, 3), dtype=np.uint8)).pin_memory() for _ in range(8)]
+        frames = [frames[i % 8] for i in range(B)]
+        for _ in range(2):
+            pipe.result(pipe.submit(frames, THRESH))
+        barrier()
+        n_p = max(6, args.steps)
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        tp0 = time.perf_counter()
+        tk = pipe.submit(frames, THRESH)
+        for i in range(n_p):
+            nxt = pipe.submit(frames, THRESH) if i + 1 < n_p else None
+            res = pipe.result(tk)
+            tk = nxt
+        torch.cuda.synchronize()
+        pipe_s = max_over_ranks(time.perf_counter() - tp0)
+        pipe_line = dict(value=world * B * n_p / pipe_s, unit='images/s', h2d_bytes_per_step=pipe.h2d_bytes // n_p,
+                         d2h_bytes_per_step=pipe.d2h_bytes // n_p, steps=n_p,
+                         mode='uint8 %dx%d frames in, letterbox + forward + un-letterboxed boxes and merged masks '
+                              'out (ImagePipeline, 2 batches in flight)' % (ph, pw))
+        del pipe
+
     # post-processing kernels, each timed alone (20 back-to-back launches between two CUDA events inside
     # the library).  decode and mask assembly are the HBM-bound ones; NMS / top-k work on a few KB and are
     # latency-bound (reported as times only).
@@ -391,6 +420,7 @@ def run_ours(args):
             clocks=clocks,
             e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h // n_e2e,
                      steps=n_e2e, mode='3 batches in flight: dy_forward_host_begin/_end'),
+            e2e_pipeline=pipe_line,
             gpu_launches=launches,
             roofline=dict(bound='tensor', kernel='conv_tc_kernel (81 launches/step, layers 2..82)',
                           achieved=achieved_tf, peak=peaks['tf_sustained'], unit='TFLOP/s',
@@ -512,6 +542,7 @@ def main():
     ap.add_argument('--batch', type=int, default=PER_GPU_BATCH)
     ap.add_argument('--latency', type=int, default=200, help='batch-1 latency iterations (0 = skip)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-pipeline', action='store_true', help='skip the whole-image pipeline e2e leg')
     ap.add_argument('--workload', default='inference', choices=['inference', 'train'])
     ap.add_argument('--train-precision', default='bf16', choices=['bf16', 'fp32'],
                     help='training engine: bf16 = tcgen05 dgrad/wgrad (mixed precision), fp32 = verification engine')

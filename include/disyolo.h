@@ -164,7 +164,7 @@ int dy_letterbox(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_siz
  * det_count_dev [1] and masks_dev [max_det,S,S] are one image's slice of dy_forward's outputs.
  * boxes_out_dev [max_det,4] int32 = (x1,y1,x2,y2) in original pixels; valid_out_dev [max_det] = 0 for
  * detections the reference skips ((y2-y1)*(x2-x1) <= 0); full_masks_dev [max_det,image_h,image_w]
- * bool bytes (may be NULL); merged_dev [image_h,image_w] = class+1 of the last detection covering
+ * bool bytes (may be NULL; planes at or beyond det_count are left unwritten); merged_dev [image_h,image_w] = class+1 of the last detection covering
  * each pixel, 0 elsewhere (may be NULL). */
 int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32_t max_det, const float* masks_dev,
                    int32_t S, int32_t image_h, int32_t image_w, int32_t net_size, int32_t* boxes_out_dev,

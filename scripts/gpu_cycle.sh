@@ -10,7 +10,7 @@ python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
 pl=d.pop('per_layer')
-for k in ('value','ms_per_step','e2e','gpu_launches','latency_batch1','cpu_baseline','clocks'): print(k, d[k])
+for k in ("value","ms_per_step","e2e","e2e_pipeline",'gpu_launches','latency_batch1','cpu_baseline','clocks'): print(k, d[k])
 r=d['roofline']; print('roofline', r['achieved'], r['frac'], r['kernel_ms_per_step'], r['network_ms_per_step'])
 print(d['roofline_extra'])
 print(' '.join('%s:%.3f/%.0f'%(k,v['ms'],v['tflops']) for k,v in pl.items()))
