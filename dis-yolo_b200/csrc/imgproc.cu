@@ -110,30 +110,78 @@ __global__ void post_prepare_kernel(const float* __restrict__ det_box, const int
 }
 
 // one thread per pixel of the original image: every detection's boolean mask at that pixel, and the
-// merged semantic mask (class + 1 of the LAST detection covering it: the reference overwrites in order)
-__global__ void post_pixel_kernel(const PostDet* __restrict__ ws, const int* __restrict__ count, int n_max,
-                                  const float* __restrict__ masks, int S, int image_h, int image_w,
-                                  unsigned char* __restrict__ full_masks, unsigned char* __restrict__ merged) {
+// merged semantic mask (class + 1 of the LAST detection covering it: the reference overwrites in order).
+// A block covers 128 pixels of one row: the detections are staged in shared memory and warp 0 compacts
+// the ones whose box meets this row segment, so a pixel only visits boxes that can contain it.
+constexpr int kPostMaxSmemDet = 64;
+
+__global__ void __launch_bounds__(128)
+post_pixel_kernel(const PostDet* __restrict__ ws, const int* __restrict__ count, int n_max,
+                  const float* __restrict__ masks, int S, int image_h, int image_w,
+                  unsigned char* __restrict__ full_masks, unsigned char* __restrict__ merged) {
+  __shared__ PostDet sd[kPostMaxSmemDet];
+  __shared__ int list[kPostMaxSmemDet];
+  __shared__ int nlist;
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= image_w) return;
+  const int xb0 = blockIdx.x * blockDim.x, xb1 = min(xb0 + (int)blockDim.x, image_w);
   const int n = min(count[0], n_max);
+  const bool staged = n <= kPostMaxSmemDet;
+  if (staged) {
+    if (threadIdx.x < 32) {
+      int base = 0;
+      for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + threadIdx.x;
+        bool hit = false;
+        if (k < n) {
+          const PostDet d = ws[k];
+          hit = d.valid && y >= d.y1 && y < d.y2 && d.x1 < xb1 && d.x2 > xb0;
+          if (hit) sd[k] = d;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) list[base + __popc(m & ((1u << threadIdx.x) - 1u))] = k;     // ascending k: "last wins" order kept
+        base += __popc(m);
+      }
+      if (threadIdx.x == 0) nlist = base;
+    }
+    __syncthreads();
+  }
+  if (x >= image_w) return;
   const size_t pix = (size_t)y * image_w + x, plane = (size_t)image_h * image_w;
   unsigned char m = 0;
-  for (int k = 0; k < n; ++k) {
-    const PostDet d = ws[k];
-    unsigned char v = 0;
-    if (d.valid && x >= d.x1 && x < d.x2 && y >= d.y1 && y < d.y2) {
-      const int cw = d.cx2 - d.cx1, ch = d.cy2 - d.cy1;
-      const Tap ty = linear_tap(y - d.y1, d.scale_y, ch), tx = linear_tap(x - d.x1, d.scale_x, cw);
-      const float* base = masks + (size_t)k * S * S;
-      const float* r0 = base + (size_t)(d.cy1 + ty.i0) * S + d.cx1;
-      const float* r1 = base + (size_t)(d.cy1 + ty.i1) * S + d.cx1;
-      const float h0 = lerp2(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), tx.w0, tx.w1);
-      const float h1 = lerp2(__ldg(r1 + tx.i0), __ldg(r1 + tx.i1), tx.w0, tx.w1);
-      v = lerp2(h0, h1, ty.w0, ty.w1) > 0.5f ? 1 : 0;
-      if (v) m = (unsigned char)(d.cls + 1);
+  auto sample = [&](const PostDet& d, int k) -> unsigned char {
+    const int cw = d.cx2 - d.cx1, ch = d.cy2 - d.cy1;
+    const Tap ty = linear_tap(y - d.y1, d.scale_y, ch), tx = linear_tap(x - d.x1, d.scale_x, cw);
+    const float* base = masks + (size_t)k * S * S;
+    const float* r0 = base + (size_t)(d.cy1 + ty.i0) * S + d.cx1;
+    const float* r1 = base + (size_t)(d.cy1 + ty.i1) * S + d.cx1;
+    const float h0 = lerp2(__ldg(r0 + tx.i0), __ldg(r0 + tx.i1), tx.w0, tx.w1);
+    const float h1 = lerp2(__ldg(r1 + tx.i0), __ldg(r1 + tx.i1), tx.w0, tx.w1);
+    return lerp2(h0, h1, ty.w0, ty.w1) > 0.5f ? 1 : 0;
+  };
+  if (staged) {
+    if (full_masks)
+      for (int k = 0; k < n; ++k) full_masks[(size_t)k * plane + pix] = 0;
+    for (int i = 0; i < nlist; ++i) {
+      const int k = list[i];
+      const PostDet& d = sd[k];
+      if (x >= d.x1 && x < d.x2) {
+        const unsigned char v = sample(d, k);
+        if (v) {
+          m = (unsigned char)(d.cls + 1);
+          if (full_masks) full_masks[(size_t)k * plane + pix] = 1;
+        }
+      }
     }
-    if (full_masks) full_masks[(size_t)k * plane + pix] = v;
+  } else {
+    for (int k = 0; k < n; ++k) {
+      const PostDet d = ws[k];
+      unsigned char v = 0;
+      if (d.valid && x >= d.x1 && x < d.x2 && y >= d.y1 && y < d.y2) {
+        v = sample(d, k);
+        if (v) m = (unsigned char)(d.cls + 1);
+      }
+      if (full_masks) full_masks[(size_t)k * plane + pix] = v;
+    }
   }
   if (merged) merged[pix] = m;
 }
