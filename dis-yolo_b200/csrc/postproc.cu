@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(256) nms_kernel(NmsArgs a) {
         }
       }
       const uint32_t m = __ballot_sync(0xffffffffu, al);
+      __syncwarp();                               // every lane has read alive[w] before lane 0 rewrites it
       if (lane == 0) alive[w] = m;
     }
   }
