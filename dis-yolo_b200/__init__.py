@@ -19,6 +19,7 @@ from .weights import init_weights, save_npz, load_npz, variable_names  # noqa: F
 from .yolo.yolo3_net_pos import YOLONet, Session, AdamOptimizer      # noqa: F401
 from .parallel import DataParallelTrainer, plan_buckets, BucketedAllReduce   # noqa: F401
 from .pipeline import ImagePipeline                   # noqa: F401
+from . import tf_checkpoint                           # noqa: F401
 
 __all__ = ['Engine', 'ImagePipeline', 'YOLONet', 'Session', 'AdamOptimizer', 'DataParallelTrainer', 'plan_buckets', 'init_weights', 'save_npz', 'load_npz',
            'variable_names', 'layer_table']

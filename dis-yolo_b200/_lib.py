@@ -72,6 +72,7 @@ SIGNATURES = {
     'dy_train_apply': (C.c_int, [_P, _P, _F, _F, _P]),
     'dy_train_get_tensor': (C.c_int, [_P, _I, _I, _I, _P, _P]),
     'dy_get_weights': (C.c_int, [_P, C.c_char_p, _P, C.c_int64]),
+    'dy_crc32c': (C.c_uint32, [_P, C.c_uint64, C.c_uint32]),
     'dy_set_option': (C.c_int, [C.c_char_p, _I]),
     'dy_launch_count': (C.c_int64, [_I]),
 }

@@ -1278,6 +1278,36 @@ int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32
   return rc;
 }
 
+// CRC-32C (Castagnoli), slicing-by-8: checksums of TensorFlow checkpoint-V2 bundles (tf_checkpoint.py).
+// Host-only utility: no device is touched.
+uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc) {
+  static uint32_t T[8][256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      T[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xFFu];
+    init = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= (uint64_t)c;
+    c = T[7][w & 0xFF] ^ T[6][(w >> 8) & 0xFF] ^ T[5][(w >> 16) & 0xFF] ^ T[4][(w >> 24) & 0xFF] ^
+        T[3][(w >> 32) & 0xFF] ^ T[2][(w >> 40) & 0xFF] ^ T[1][(w >> 48) & 0xFF] ^ T[0][(w >> 56) & 0xFF];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = T[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
+  return ~c;
+}
+
 int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
                   const float* w_host, int32_t k, int32_t stride, int32_t cout, const float* scale_host,
                   const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,

@@ -119,12 +119,34 @@ class Session(object):
 
     def restore(self, weights):
         """weights: dict {tf variable name: ndarray} (what Saver.restore would read,
-        train_yolo3_mask.py:104-111) or a path to an .npz written by weights.save_npz."""
+        train_yolo3_mask.py:104-111), the prefix of a TensorFlow checkpoint-V2 bundle (`model.ckpt-500`:
+        read without TensorFlow by tf_checkpoint.read_checkpoint; variables the net does not have are
+        ignored like slim's ignore_missing_vars=True, :106), or a path to an .npz written by
+        weights.save_npz."""
         if isinstance(weights, str):
-            from ..weights import load_npz
-            weights = load_npz(weights)
+            from .. import tf_checkpoint
+            if tf_checkpoint.is_checkpoint_prefix(weights):
+                weights = tf_checkpoint.network_variables(tf_checkpoint.read_checkpoint(weights))
+            else:
+                from ..weights import load_npz
+                weights = load_npz(weights)
         self.net.engine.load_weights(weights)
         self.restored = True
+
+    def save(self, prefix):
+        """Saver.save counterpart (train_yolo3_mask.py:221-226): the current value of every
+        yolo/convolutional{N}/... variable as a TensorFlow checkpoint-V2 bundle at `prefix`."""
+        from .. import tf_checkpoint
+        from ..weights import variable_names
+        from ..engine import layer_table
+        eng, out = self.net.engine, {}
+        for L in layer_table():
+            k, cin, cout = L['k'], L['cin'], L['cout']
+            for name in variable_names(L['id'], L['bn']):
+                shape = (k, k, cin, cout) if name.endswith('/weights') else (cout,)
+                out[name] = eng.get_weights(name, shape)
+        tf_checkpoint.write_checkpoint(prefix, out)
+        return prefix
 
     def run(self, fetches, feed_dict=None):
         if not self.restored:

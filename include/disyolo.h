@@ -229,6 +229,11 @@ int dy_train_get_tensor(dy_net* net, int32_t layer, int32_t which, int32_t B, fl
 /* Current value of a variable by its TF name (Saver.save counterpart, train_yolo3_mask.py:221-226). */
 int dy_get_weights(dy_net* net, const char* tf_name, float* host, int64_t capacity);
 
+/* CRC-32C (Castagnoli) of `n` bytes continuing from `crc` (0 to start): the checksum of TensorFlow
+ * checkpoint-V2 bundles (Saver.save / Saver.restore, train_yolo3_mask.py:104-111,221-226), used by
+ * dis-yolo_b200/tf_checkpoint.py.  Host-only. */
+uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
+
 /* Tuning / test overrides of the conv engine's planning heuristics; value -1 = automatic.
  *   "tc_resident": 0 never / 1 whenever it fits -- keep a CTA's weight slab resident in smem
  *   "tc_halo":     0 never / 1 whenever legal   -- one halo'd activation box feeds all 3 horizontal taps

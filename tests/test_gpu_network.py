@@ -241,3 +241,27 @@ def test_first_forward_of_fresh_engines_is_reproducible():
             seen.add(h.hexdigest())
         eng.close()
     assert len(seen) == 1, seen
+
+
+def test_checkpoint_v2_save_restore_through_session(tmp_path):
+    """Saver.save / Saver.restore counterparts (train_yolo3_mask.py:104-111,221-226): a net restored from the
+    checkpoint-V2 bundle another net saved evaluates identically."""
+    import disyolo_b200.yolo.config as cfg
+    from disyolo_b200.yolo.yolo3_net_pos import YOLONet, Session
+    cfg.BATCH_SIZE, cfg.IMAGE_SIZE = 1, 96
+    try:
+        img, win = _inputs(1, 96, 21)
+        feed = lambda net: {net.is_training: False, net.det_thresh: [0.1], net.clip_window: win, net.images: img}
+        a = YOLONet(False)
+        sa = Session(a)
+        sa.restore(O.make_weights('lively', 4))
+        prefix = sa.save(str(tmp_path / 'model.ckpt-7'))
+        ba, ma = sa.run(a.evaluation, feed_dict=feed(a))
+        b = YOLONet(False)
+        sb = Session(b)
+        sb.restore(prefix)
+        bb, mb = sb.run(b.evaluation, feed_dict=feed(b))
+        assert len(ba[0]) == len(bb[0]) and np.array_equal(ba[0], bb[0])
+        assert np.array_equal(np.asarray(ma[0]), np.asarray(mb[0]))
+    finally:
+        cfg.BATCH_SIZE, cfg.IMAGE_SIZE = 2, 576
