@@ -186,7 +186,73 @@ post_pixel_kernel(const PostDet* __restrict__ ws, const int* __restrict__ count,
   if (merged) merged[pix] = m;
 }
 
+// ---- mask IoU matrix: compute_overlaps_masks (utils/voc_eval_mask.py:38-56) ----------------------------
+// A block owns 4096 pixels: every mask's bytes are turned into bits with warp ballots (one coalesced
+// 32-byte read per ballot, no alignment requirement), then each (i, j) pair is 128 AND + POPC.
+constexpr int kOvChunk = 4096, kOvWords = kOvChunk / 32;
+
+__global__ void __launch_bounds__(256)
+overlaps_count_kernel(const unsigned char* __restrict__ m1, int n1, const unsigned char* __restrict__ m2, int n2,
+                      long long P, int* __restrict__ inter, int* __restrict__ area) {
+  extern __shared__ uint32_t bits[];                       // [(n1+n2)][kOvWords]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long p0 = (long long)blockIdx.x * kOvChunk;
+  const int nm = n1 + n2;
+  for (int t = warp; t < nm * kOvWords; t += 8) {
+    const int r = t / kOvWords, w = t - r * kOvWords;
+    const unsigned char* src = r < n1 ? m1 + (long long)r * P : m2 + (long long)(r - n1) * P;
+    const long long px = p0 + w * 32 + lane;
+    const bool on = px < P && __ldg(src + px) != 0;
+    const uint32_t word = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) bits[t] = word;
+  }
+  __syncthreads();
+  for (int pr = threadIdx.x; pr < n1 * n2; pr += 256) {
+    const int i = pr / n2, j = pr - i * n2;
+    const uint32_t* a = bits + i * kOvWords;
+    const uint32_t* b = bits + (n1 + j) * kOvWords;
+    int s = 0;
+#pragma unroll 8
+    for (int w = 0; w < kOvWords; ++w) s += __popc(a[w] & b[w]);
+    if (s) atomicAdd(inter + pr, s);
+  }
+  for (int r = threadIdx.x; r < nm; r += 256) {
+    int s = 0;
+    for (int w = 0; w < kOvWords; ++w) s += __popc(bits[r * kOvWords + w]);
+    if (s) atomicAdd(area + r, s);
+  }
+}
+
+__global__ void overlaps_finalize_kernel(const int* __restrict__ inter, const int* __restrict__ area, int n1, int n2,
+                                         float* __restrict__ out) {
+  const int pr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pr >= n1 * n2) return;
+  const int i = pr / n2, j = pr - i * n2;
+  const float it = (float)inter[pr], a1 = (float)area[i], a2 = (float)area[n1 + j];
+  out[pr] = __fdiv_rn(it, __fsub_rn(__fadd_rn(a1, a2), it));      // 0/0 = NaN, like NumPy
+}
+
 }  // namespace
+
+int launch_mask_overlaps(const unsigned char* m1, int n1, const unsigned char* m2, int n2, long long P, int* ws,
+                         float* out, cudaStream_t st) {
+  DY_CHECK(n1 >= 1 && n2 >= 1 && P >= 1, "empty mask set");
+  DY_CHECK(n1 + n2 <= 384, "at most 384 masks per call");
+  const size_t smem = (size_t)(n1 + n2) * kOvWords * 4;
+  static bool attr = false;
+  if (!attr) {
+    DY_CUDA(cudaFuncSetAttribute(overlaps_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  DY_CUDA(cudaMemsetAsync(ws, 0, (size_t)(n1 * n2 + n1 + n2) * 4, st));
+  const long long blocks = (P + kOvChunk - 1) / kOvChunk;
+  DY_CHECK(blocks < (1ll << 31), "mask too large");
+  overlaps_count_kernel<<<(int)blocks, 256, smem, st>>>(m1, n1, m2, n2, P, ws, ws + n1 * n2);
+  DY_CUDA(cudaGetLastError());
+  overlaps_finalize_kernel<<<(n1 * n2 + 127) / 128, 128, 0, st>>>(ws, ws + n1 * n2, n1, n2, out);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
 
 LetterboxGeom letterbox_geom(int src_h, int src_w, int size) {
   LetterboxGeom g;

@@ -33,4 +33,9 @@ int launch_postprocess(const float* det_box, const int* count, int n_max, const 
                        int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
                        unsigned char* full_masks, unsigned char* merged, cudaStream_t st);
 
+// compute_overlaps_masks (utils/voc_eval_mask.py:38-56): IoU of every mask of set 1 with every mask of set 2;
+// masks are [n, P] bytes (non-zero = inside), ws = n1*n2 + n1 + n2 ints of scratch, out [n1, n2] fp32
+int launch_mask_overlaps(const unsigned char* m1, int n1, const unsigned char* m2, int n2, long long P, int* ws,
+                         float* out, cudaStream_t st);
+
 }  // namespace dy

@@ -1278,6 +1278,19 @@ int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32
   return rc;
 }
 
+int dy_mask_overlaps(const uint8_t* masks1_dev, int32_t n1, const uint8_t* masks2_dev, int32_t n2, int64_t pixels,
+                     float* overlaps_dev, void* stream) {
+  DY_CHECK(masks1_dev && masks2_dev && overlaps_dev, "null argument");
+  DY_CHECK(n1 >= 1 && n2 >= 1 && pixels >= 1, "empty mask set");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* ws = nullptr;
+  DY_CUDA(cudaMallocAsync((void**)&ws, (size_t)(n1 * n2 + n1 + n2) * 4, st));
+  note_launch(2);
+  const int rc = launch_mask_overlaps(masks1_dev, n1, masks2_dev, n2, pixels, ws, overlaps_dev, st);
+  cudaFreeAsync(ws, st);
+  return rc;
+}
+
 // CRC-32C (Castagnoli), slicing-by-8: checksums of TensorFlow checkpoint-V2 bundles (tf_checkpoint.py).
 // Host-only utility: no device is touched.
 uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc) {

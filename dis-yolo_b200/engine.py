@@ -442,6 +442,25 @@ class Engine(object):
                                            _ptr(merged), self._stream()), 'dy_postprocess')
         return dict(boxes=boxes, valid=valid, full_masks=full, merged=merged)
 
+    def mask_overlaps(self, masks1, masks2):
+        """compute_overlaps_masks (utils/voc_eval_mask.py:38-56) on the GPU: masks1 [n1,h,w], masks2 [n2,h,w]
+        (bool / uint8; numpy or cuda tensors, instance-major) -> IoU [n1,n2] fp32 cuda tensor."""
+        t = self.torch
+        a = masks1 if isinstance(masks1, t.Tensor) else t.from_numpy(np.ascontiguousarray(masks1).astype(np.uint8))
+        b = masks2 if isinstance(masks2, t.Tensor) else t.from_numpy(np.ascontiguousarray(masks2).astype(np.uint8))
+        a = a.to(self.device).to(t.uint8).contiguous()
+        b = b.to(self.device).to(t.uint8).contiguous()
+        n1, n2 = int(a.shape[0]), int(b.shape[0])
+        if n1 == 0 or n2 == 0:
+            return t.zeros((n1, n2), dtype=t.float32, device=self.device)
+        P = int(a[0].numel())
+        if int(b[0].numel()) != P:
+            raise ValueError('mask sets have different extents')
+        out = t.empty((n1, n2), dtype=t.float32, device=self.device)
+        _lib.check(self.lib.dy_mask_overlaps(_ptr(a), n1, _ptr(b), n2, P, _ptr(out), self._stream()),
+                   'dy_mask_overlaps')
+        return out
+
 
 def set_option(name, value):
     """dy_set_option: planning overrides of the conv engine ('tc_resident', 'tc_halo'; -1 = auto)."""

@@ -170,6 +170,13 @@ int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32
                    int32_t S, int32_t image_h, int32_t image_w, int32_t net_size, int32_t* boxes_out_dev,
                    uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev, void* stream);
 
+/* Replaces compute_overlaps_masks (utils/voc_eval_mask.py:38-56), the inner operation of the mask-level
+ * mAP (voc_eval, :58-134): IoU of every mask of set 1 with every mask of set 2.
+ * Masks are instance-major [n, pixels] bytes (non-zero = inside; dy_postprocess's full_masks layout);
+ * overlaps_dev [n1, n2] fp32 = inter / (area1 + area2 - inter), NaN for two empty masks like NumPy. */
+int dy_mask_overlaps(const uint8_t* masks1_dev, int32_t n1, const uint8_t* masks2_dev, int32_t n2, int64_t pixels,
+                     float* overlaps_dev, void* stream);
+
 /* Measurement aid for bench.py: device milliseconds of each post-processing kernel (decode+threshold,
  * per-class NMS, top-k/finalize, mask assembly), each launched `reps` times back to back between two
  * CUDA events on `stream`; ms_host[4] receives the per-launch averages.  Same inputs as dy_detect +

@@ -93,3 +93,28 @@ out['letterbox_synthetic'] = syn
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_kat.json'), 'w') as f:
     json.dump(out, f, indent=1, sort_keys=True)
 print('letterbox_synthetic:', len(syn), 'cases')
+
+# --- mask-level mAP: the reference's own voc_eval (utils/voc_eval_mask.py:58-134) on seeded synthetic data
+# sets (oracle/dis_oracle_eval.synthetic_dataset); pins oracle/dis_oracle_eval.voc_eval ---
+if not hasattr(np, 'bool'):
+    np.bool = bool            # the reference predates NumPy 1.24 (np.bool alias, voc_eval_mask.py:80)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle import dis_oracle_eval as OE  # noqa: E402
+ve = []
+for seed in (1, 2, 3):
+    names, recs, dets = OE.synthetic_dataset(seed)
+    setfile = os.path.join(tempfile.gettempdir(), 'dy_golden_set_%d.txt' % seed)
+    with open(setfile, 'w') as f:
+        f.write('\n'.join(names) + '\n')
+    for c in range(3):
+        for use07 in (False, True):
+            if not dets[c]:
+                continue
+            import copy  # noqa: E402
+            r, p, ap = voc_eval_mask.voc_eval(copy.deepcopy(dets[c]), copy.deepcopy(recs), setfile, c, ovthresh=0.5,
+                                              use_07_metric=use07)
+            ve.append(dict(seed=seed, classid=c, use_07_metric=use07, recall=float(r), precision=float(p), ap=float(ap)))
+out['voc_eval_synthetic'] = ve
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'ref_kat.json'), 'w') as f:
+    json.dump(out, f, indent=1, sort_keys=True)
+print('voc_eval_synthetic:', len(ve), 'cases', ve[:2])
