@@ -1470,7 +1470,7 @@ int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t
   cudaMemcpyAsync(d_one, ones.data(), (size_t)npad * 4, cudaMemcpyHostToDevice, st);
   note_launch(2);
   rc = launch_nhwc_to_p1(x_dev, d_x, B, H, W, cin, FORM_SAME, st);
-  if (rc == DY_OK) rc = launch_f32_to_p1(dz_dev, B, H, W, cout, d_dz, Cg, st);
+  if (rc == DY_OK) rc = launch_f32_to_p1(dz_dev, B, H, W, cout, d_dz, Cg, nullptr, st);
   if (rc == DY_OK && dx_dev) {
     note_launch(3);
     rc = launch_pack_dgrad_bf16(d_w, k, cin, 0, cin, cout, Cg, d_wdg, st);
@@ -1868,17 +1868,17 @@ static int train_forward_layer_tc(dy_net* net, int n, const float* images, int B
   DY_TRY(run_tc_plan(s.plan_z, B, net->num_sms, st));
   const long long rows = (long long)B * (d.H + 1) * (d.H + 1);
   const long long M = (long long)B * d.H * d.H;
-  note_launch(3);
+  note_launch(2);
+  const __nv_bfloat16* res = d.res > 0 ? L[d.res].same : nullptr;
   if (s.unlocked) {
     DY_CUDA(cudaMemsetAsync(s.stat, 0, (size_t)4 * d.cout * 8, st));
     DY_TRY(launch_bn_stats_p1(s.zb, rows, d.cout, s.stat, s.stat + d.cout, st));
-    DY_TRY(launch_bn_finalize(s.stat, s.stat + d.cout, M, d.cout, s.d_gamma, s.d_beta, net->cfg.bn_eps, s.bn_a,
-                              s.bn_b, s.bmean, s.bvar, s.binvstd, st));
-  } else {
-    DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, d.cout, s.bn_a, s.bn_b, st));
+    return launch_bn_finalize_act_p1(s.zb, s.stat, s.stat + d.cout, M, s.d_gamma, s.d_beta, net->cfg.bn_eps, s.bn_a,
+                                     s.bn_b, s.bmean, s.bvar, s.binvstd, res, B, d.H, d.H, d.cout, net->cfg.alpha, 1,
+                                     s.same, s.up, st);
   }
-  return launch_bn_act_p1(s.zb, s.bn_a, s.bn_b, d.res > 0 ? L[d.res].same : nullptr, B, d.H, d.H, d.cout,
-                          net->cfg.alpha, 1, s.same, s.up, st);
+  DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, d.cout, s.bn_a, s.bn_b, st));
+  return launch_bn_act_p1(s.zb, s.bn_a, s.bn_b, res, B, d.H, d.H, d.cout, net->cfg.alpha, 1, s.same, s.up, st);
 }
 
 static int train_backward_layer_tc(dy_net* net, int n, int B, float* grad_flat, cudaStream_t st) {
@@ -1887,7 +1887,6 @@ static int train_backward_layer_tc(dy_net* net, int n, int B, float* grad_flat, 
   const LayerDef& d = s.def;
   if (!s.in_bwd) return DY_OK;
   const long long rows = (long long)B * (d.H + 1) * (d.H + 1);
-  const long long M = (long long)B * d.H * d.H;
   const int C = d.cout;
   double* s1 = s.stat + 2 * C;
   double* s2 = s.stat + 3 * C;
@@ -1901,24 +1900,18 @@ static int train_backward_layer_tc(dy_net* net, int n, int B, float* grad_flat, 
       DY_CUDA(cudaMemsetAsync(s1, 0, (size_t)2 * C * 8, st));
       DY_TRY(launch_bn_bwd_reduce_p1(s.dyb, s.zb, s.bn_a, s.bn_b, s.bmean, s.binvstd, net->cfg.alpha, 1, rows, C, s1,
                                      s2, st));
-      DY_TRY(launch_copy_stats_to_grads(s1, s2, C, grad_flat + s.off_g, grad_flat + s.off_b, st));
       DY_TRY(launch_bn_bwd_apply_p1(s.dyb, s.zb, s.bn_a, s.bn_b, s.bmean, s.binvstd, s.d_gamma, s1, s2,
-                                    net->cfg.alpha, 1, 0, B, d.H, d.H, C, net->dzb_scratch, st));
+                                    net->cfg.alpha, 1, 0, B, d.H, d.H, C, net->dzb_scratch, grad_flat + s.off_g,
+                                    grad_flat + s.off_b, st));
     } else {
       DY_TRY(launch_bn_bwd_apply_p1(s.dyb, s.zb, s.bn_a, s.bn_b, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                    net->cfg.alpha, 1, 1, B, d.H, d.H, C, net->dzb_scratch, st));
+                                    net->cfg.alpha, 1, 1, B, d.H, d.H, C, net->dzb_scratch, nullptr, nullptr, st));
     }
-    note_launch(3);
+    note_launch(2);
   } else {
     // biased linear conv: dz = dy (the loss kernels wrote it in fp32 NHWC); d bias = column sums
-    DY_TRY(launch_f32_to_p1(s.dyf, B, d.H, d.H, C, s.dyb, s.Cg, st));
+    DY_TRY(launch_f32_to_p1(s.dyf, B, d.H, d.H, C, s.dyb, s.Cg, s.unlocked ? grad_flat + s.off_b : nullptr, st));
     note_launch();
-    if (s.unlocked) {
-      DY_CUDA(cudaMemsetAsync(s1, 0, (size_t)C * 8, st));
-      DY_TRY(launch_bn_stats(s.dyf, M, C, s1, nullptr, st));
-      DY_TRY(launch_copy_stats_to_grads(s1, s1, C, nullptr, grad_flat + s.off_b, st));
-      note_launch(2);
-    }
   }
   if (s.unlocked) {
     DY_CUDA(cudaMemsetAsync(grad_flat + s.off_w, 0, (size_t)s.K * C * 4, st));

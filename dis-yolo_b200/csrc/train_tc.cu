@@ -141,17 +141,55 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
   }
 }
 
+// fin.sum != nullptr: the batch-moment finalize (bn_finalize_kernel: a = gamma*invstd, b = beta - mean*a, in
+// double from the per-channel sums) is done here by every thread for its own 8 channels, and block 0 also
+// publishes a / b / mean / var / invstd for the backward pass -- one launch less per trained layer
+struct BnFinalize {
+  const double* sum;
+  const double* sumsq;
+  const float* gamma;
+  const float* beta;
+  float* a_out;
+  float* b_out;
+  float* mean_out;
+  float* var_out;
+  float* invstd_out;
+  long long M;
+  float eps;
+};
+
 __global__ void __launch_bounds__(kT)
 bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
-                 const __nv_bfloat16* __restrict__ residual, uint32_t rows, int H, int W, int C, float alpha, int act,
-                 __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up) {
+                 BnFinalize fin, const __nv_bfloat16* __restrict__ residual, uint32_t rows, int H, int W, int C,
+                 float alpha, int act, __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up) {
   const int cv = C >> 3;
   const uint32_t Hp = H + 1, Wp = W + 1;
   const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
   const uint32_t G = gridDim.x * (uint32_t)R;
   float fa[8], fb[8];
-  load8f(a + v * 8, fa);
-  load8f(b + v * 8, fb);
+  if (fin.sum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const double m = fin.sum[c] / (double)fin.M;
+      double var = fin.sumsq[c] / (double)fin.M - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
+      const float aa = fin.gamma[c] * is;
+      fa[j] = aa;
+      fb[j] = fin.beta[c] - (float)m * aa;
+      if (blockIdx.x == 0 && rl == 0) {
+        fin.a_out[c] = aa;
+        fin.b_out[c] = fb[j];
+        fin.mean_out[c] = (float)m;
+        fin.var_out[c] = (float)var;
+        fin.invstd_out[c] = is;
+      }
+    }
+  } else {
+    load8f(a + v * 8, fa);
+    load8f(b + v * 8, fb);
+  }
   for (uint32_t r = blockIdx.x * (uint32_t)R + rl; r < rows; r += kUnroll * G) {
     uint4 qz[kUnroll], qr[kUnroll];
     int pn[kUnroll], py[kUnroll], px[kUnroll];
@@ -199,12 +237,19 @@ bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                        const double* __restrict__ s1, const double* __restrict__ s2, float alpha, int act, int mode,
                        uint32_t rows, uint32_t rows_out, long long mvalid, int H, int W, int C,
-                       __nv_bfloat16* __restrict__ dz) {
+                       __nv_bfloat16* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int cv = C >> 3;
   const uint32_t Hp = H + 1, Wp = W + 1;
   const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
   const uint32_t G = gridDim.x * (uint32_t)R;
   const float invM = 1.f / (float)mvalid;
+  if (dgamma != nullptr && blockIdx.x == 0 && rl == 0) {      // d gamma = sum g*xhat, d beta = sum g (copy_stats)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dgamma[v * 8 + j] = (float)s2[v * 8 + j];
+      dbeta[v * 8 + j] = (float)s1[v * 8 + j];
+    }
+  }
   // per-channel constants of this thread's 8 channels: dz = g*k0 - k1 - xhat*k2 (mode 0) or g*k0 (mode 1)
   float fa[8], fb[8], k0[8], k1[8], k2[8], fm[8], fi[8];
   load8f(a + v * 8, fa);
@@ -259,11 +304,18 @@ bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   }
 }
 
+// colsum != nullptr: per-channel sums of src (= the bias gradient of a biased linear conv, dz = dy) are
+// accumulated on the way: shared-memory float partials per block, one float atomic per channel per block
 __global__ void __launch_bounds__(kT)
 f32_to_p1_kernel(const float* __restrict__ src, long long rows, long long rows_out, int H, int W, int C, int Cg,
-                 __nv_bfloat16* __restrict__ dst) {
+                 __nv_bfloat16* __restrict__ dst, float* __restrict__ colsum) {
+  __shared__ float part[64];
   const int cv = Cg >> 3, Hp = H + 1, Wp = W + 1;
   const long long total = rows_out * cv;
+  if (colsum) {
+    if (threadIdx.x < 64) part[threadIdx.x] = 0.f;
+    __syncthreads();
+  }
   for (long long i = blockIdx.x * (long long)kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
     const long long r = i / cv;
     const int v = (int)(i - r * cv);
@@ -275,8 +327,17 @@ f32_to_p1_kernel(const float* __restrict__ src, long long rows, long long rows_o
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (v * 8 + j < C) ? __ldg(s + v * 8 + j) : 0.f;
       q = pack8(f);
+      if (colsum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v * 8 + j < C && f[j] != 0.f) atomicAdd(&part[v * 8 + j], f[j]);
+      }
     }
     reinterpret_cast<uint4*>(dst + r * Cg)[v] = q;
+  }
+  if (colsum) {
+    __syncthreads();
+    if (threadIdx.x < C && part[threadIdx.x] != 0.f) atomicAdd(colsum + threadIdx.x, part[threadIdx.x]);
   }
 }
 
@@ -636,8 +697,23 @@ int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, con
                      cudaStream_t st) {
   const long long rows = (long long)B * (H + 1) * (W + 1);
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
-  bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, a, b, residual, (uint32_t)rows, H, W, C, alpha, act, out_same,
-                                                     out_up);
+  BnFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, a, b, fin, residual, (uint32_t)rows, H, W, C, alpha, act,
+                                                     out_same, out_up);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_bn_finalize_act_p1(const __nv_bfloat16* z, const double* sum, const double* sumsq, long long M,
+                              const float* gamma, const float* beta, float eps, float* a, float* b, float* mean,
+                              float* var, float* invstd, const __nv_bfloat16* residual, int B, int H, int W, int C,
+                              float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up, cudaStream_t st) {
+  const long long rows = (long long)B * (H + 1) * (W + 1);
+  DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
+  BnFinalize fin{sum, sumsq, gamma, beta, a, b, mean, var, invstd, M, eps};
+  bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, nullptr, nullptr, fin, residual, (uint32_t)rows, H, W, C, alpha,
+                                                     act, out_same, out_up);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -647,23 +723,25 @@ static long long round_up64(long long r) { return (r + 63) / 64 * 64; }
 int launch_bn_bwd_apply_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
                            const float* mean, const float* invstd, const float* gamma, const double* s1,
                            const double* s2, float alpha, int act, int mode, int B, int H, int W, int C,
-                           __nv_bfloat16* dz, cudaStream_t st) {
+                           __nv_bfloat16* dz, float* dgamma, float* dbeta, cudaStream_t st) {
   DY_CHECK(C % 8 == 0, "channel count");
   const long long rows = (long long)B * (H + 1) * (W + 1);
   const long long ro = round_up64(rows);
   DY_CHECK(kT % (C / 8) == 0 && C <= 8 * kT && ro < (1ll << 31), "channel count / rows");
   bn_bwd_apply_p1_kernel<<<row_grid(ro, C), kT, 0, st>>>(dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act, mode,
                                                          (uint32_t)rows, (uint32_t)ro, (long long)B * H * W, H, W, C,
-                                                         dz);
+                                                         dz, dgamma, dbeta);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
 
-int launch_f32_to_p1(const float* src, int B, int H, int W, int C, __nv_bfloat16* dst, int Cg, cudaStream_t st) {
-  DY_CHECK(Cg % 8 == 0 && Cg >= C, "channel count");
+int launch_f32_to_p1(const float* src, int B, int H, int W, int C, __nv_bfloat16* dst, int Cg, float* colsum,
+                     cudaStream_t st) {
+  DY_CHECK(Cg % 8 == 0 && Cg >= C && (colsum == nullptr || C <= 64), "channel count");
   const long long rows = (long long)B * (H + 1) * (W + 1);
   const long long ro = round_up64(rows);
-  f32_to_p1_kernel<<<grid_for(ro * (Cg / 8)), kT, 0, st>>>(src, rows, ro, H, W, C, Cg, dst);
+  if (colsum) DY_CUDA(cudaMemsetAsync(colsum, 0, (size_t)C * 4, st));
+  f32_to_p1_kernel<<<grid_for(ro * (Cg / 8)), kT, 0, st>>>(src, rows, ro, H, W, C, Cg, dst, colsum);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

@@ -23,6 +23,12 @@ int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* su
 int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, const __nv_bfloat16* residual, int B,
                      int H, int W, int C, float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up,
                      cudaStream_t st);
+// the same with bn_finalize fused in: a, b, mean, biased var, invstd are derived from the per-channel sums
+// (and written out for the backward pass by block 0)
+int launch_bn_finalize_act_p1(const __nv_bfloat16* z, const double* sum, const double* sumsq, long long M,
+                              const float* gamma, const float* beta, float eps, float* a, float* b, float* mean,
+                              float* var, float* invstd, const __nv_bfloat16* residual, int B, int H, int W, int C,
+                              float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up, cudaStream_t st);
 // g = dy * leaky'(z*a+b);  s1 = sum g, s2 = sum g*xhat
 int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
                             const float* mean, const float* invstd, float alpha, int act, long long rows, int C,
@@ -32,9 +38,12 @@ int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, con
 int launch_bn_bwd_apply_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
                            const float* mean, const float* invstd, const float* gamma, const double* s1,
                            const double* s2, float alpha, int act, int mode, int B, int H, int W, int C,
-                           __nv_bfloat16* dz, cudaStream_t st);
+                           __nv_bfloat16* dz, float* dgamma, float* dbeta, cudaStream_t st);
+// (dgamma / dbeta non-null: block 0 also writes d gamma = s2, d beta = s1 into the flat gradient vector)
 // fp32 [B,H,W,C] -> bf16 P1 [B,H+1,W+1,Cg] (channels >= C and pad pixels zero; tail rows zeroed)
-int launch_f32_to_p1(const float* src, int B, int H, int W, int C, __nv_bfloat16* dst, int Cg, cudaStream_t st);
+// colsum (may be null): [C] fp32 receives the per-channel sums of src (zeroed here first)
+int launch_f32_to_p1(const float* src, int B, int H, int W, int C, __nv_bfloat16* dst, int Cg, float* colsum,
+                     cudaStream_t st);
 // 2x2 sum pooling: P1 [B,2h+1,2w+1,C] -> P1 [B,h+1,w+1,C]   (backward of nearest-neighbour upsampling)
 int launch_pool2x2_p1(const __nv_bfloat16* src, int B, int h, int w, int C, __nv_bfloat16* dst, cudaStream_t st);
 int launch_add_p1(__nv_bfloat16* dst, const __nv_bfloat16* src, long long n, cudaStream_t st);
