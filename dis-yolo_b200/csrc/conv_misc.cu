@@ -91,23 +91,22 @@ conv1_kernel(const float* __restrict__ img, const float* __restrict__ w_hwio, co
 // ------------------------------------------------------------------------------------------
 // conv1 on the tensor cores.  K = 3*3*3 = 27 is padded to 32 (one 64-byte SWIZZLE_64B row); the A
 // operand does not exist in memory: producer warps build it on the fly (im2col in shared memory).
-//   warps 0..3   producers: each warp owns one 32-pixel segment of the 128-pixel tile; coalesced
+//   warps 0..7   producers, two warpgroups on alternate tiles: each warp owns one 32-pixel segment of a 128-pixel tile;
 //                loads of its 3 x 34 x 3 fp32 patch into a warp-private smem patch (next tile's
 //                patch is prefetched into registers), then each lane packs its pixel's 27 taps to
 //                bf16 and writes its swizzled 64-byte row; fence.proxy.async + mbarrier arrive
-//   warp  4      MMA issuer: 2 x tcgen05.mma (M=128, N=32, K=16) per tile into 1 of 4 TMEM stages
-//   warp  5      TMEM allocator
-//   warps 8..15  epilogue, two warpgroups on alternate tiles: tcgen05.ld -> folded BN -> leaky -> bf16 ->
+//   warp  8      TMEM allocator + MMA issuer: 2 x tcgen05.mma (M=128, N=32, K=16) per tile into 1 of 4 TMEM stages
+//   warps 10..17 epilogue, two warpgroups on alternate tiles: tcgen05.ld -> folded BN -> leaky -> bf16 ->
 //                space-to-depth (TMA store from a double-buffered staging row) or P1 store
 // Tiles are 128 consecutive pixels in (n,y,x) raster order; W % 32 == 0 keeps a segment in one row.
 // ------------------------------------------------------------------------------------------
-constexpr int kC1Threads = 512;
+constexpr int kC1Threads = 576;
 constexpr int kC1Stages = 3;
 constexpr int kPatchW = 112;                 // pixels x0-4 .. x0+32 (37 x 3 = 111 floats): the TMA box must start 16-byte aligned
 constexpr int kPatchLead = 4;                // leading pixels before x0 inside the patch
 constexpr int kC1Patches = 4;                // patch prefetch depth per producer warp (TMA latency > 1 tile time)
 constexpr int kC1PatchFloats = 3 * kPatchW + 16;   // 1408 B, a multiple of 128 B
-constexpr size_t kC1SmemBytes = 3 * 8192 + 2048 + 16 * 2048 + 4 * kC1Patches * kC1PatchFloats * 4 + 1024;
+constexpr size_t kC1SmemBytes = 3 * 8192 + 2048 + 16 * 2048 + 8 * kC1Patches * kC1PatchFloats * 4 + 1024;
 
 // (n, y, x0) of a 32-pixel segment, advanced tile by tile without divisions: consecutive tiles of a CTA
 // are gridDim.x * 128 pixels apart = (sy rows, sx pixels)
@@ -145,10 +144,15 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
   float (*patch)[kC1Patches][kC1PatchFloats] =
       reinterpret_cast<float (*)[kC1Patches][kC1PatchFloats]>(sB + 2048 + 16 * 2048);
   __shared__ __align__(8) uint64_t full_bar[kC1Stages], empty_bar[kC1Stages], tfull_bar[4], tempty_bar[4];
-  __shared__ __align__(8) uint64_t patch_bar[4][kC1Patches];
+  __shared__ __align__(8) uint64_t patch_bar[8][kC1Patches];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_sc[32], s_sh[32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {
+    s_sc[threadIdx.x] = __ldg(scale + threadIdx.x);
+    s_sh[threadIdx.x] = __ldg(shift + threadIdx.x);
+  }
   const long long total = (long long)B * H * W;
   const int num_tiles = (int)((total + 127) / 128);
 
@@ -175,11 +179,14 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);    // one arrive per epilogue warp
-      for (int b2 = 0; b2 < kC1Patches; ++b2) mbar_init(&patch_bar[i][b2], 1);
+      for (int b2 = 0; b2 < kC1Patches; ++b2) {
+        mbar_init(&patch_bar[i][b2], 1);
+        mbar_init(&patch_bar[4 + i][b2], 1);
+      }
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 8) {
     tmem_alloc(&tmem_base_smem, 128);
     tmem_relinquish();
   }
@@ -189,34 +196,39 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ================================ im2col producers ================================
-    // running coordinate of the NEXT patch to request (kC1Patches-1 tiles ahead of the one being built)
-    const int step_px = 128 * (int)gridDim.x, sx = step_px % W, sy = step_px / W;
+    // Two producer warpgroups (warps 0..3, 4..7) build alternate tiles: a tile's A rows come from the four
+    // warps of ONE group (full_bar counts 4), so each warp's wait-patch -> LDS -> pack -> STS -> fence chain
+    // has two tile periods to complete.
+    const int pg = warp >> 2, seg = warp & 3;
+    // running coordinate of the NEXT patch to request (kC1Patches-1 of this warp's tiles ahead)
+    const int step_px = 256 * (int)gridDim.x, sx = step_px % W, sy = step_px / W;
     SegCoord nx;
-    nx.init((long long)blockIdx.x * 128 + warp * 32, H, W);
+    nx.init((long long)(blockIdx.x + pg * gridDim.x) * 128 + seg * 32, H, W);
     auto issue_patch = [&](int buf) {                                // lane 0 only; n >= B past the end: zero fill
       mbar_expect_tx(&patch_bar[warp][buf], 3 * kPatchW * 4);
       tma_load_3d(&patch[warp][buf][0], &mapImg, &patch_bar[warp][buf], (nx.x0 - kPatchLead) * 3, nx.y - 1, nx.n);
     };
-    int it = 0, issued = blockIdx.x;                                 // tile index of the next patch to request
+    int it = pg, li = 0;                                             // it: tile sequence number in the CTA; li: this warp's
+    int issued = blockIdx.x + pg * gridDim.x;                        // tile index of the next patch to request
     for (int d = 0; d < kC1Patches - 1; ++d) {
       if (issued < num_tiles) {
         if (lane == 0) issue_patch(d);
-        issued += gridDim.x;
+        issued += 2 * gridDim.x;
         nx.advance(sx, sy, H, W);
       }
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int stage = it % kC1Stages, buf = it % kC1Patches;
+    for (int tile = blockIdx.x + pg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2, ++li) {
+      const int stage = it % kC1Stages, buf = li % kC1Patches;
       const uint32_t ph = (uint32_t)(it / kC1Stages) & 1u;
       // refill the buffer that was consumed last iteration (all lanes passed the __syncwarp after reading it)
       if (issued < num_tiles) {
-        if (lane == 0) issue_patch((it + kC1Patches - 1) % kC1Patches);
-        issued += gridDim.x;
+        if (lane == 0) issue_patch((li + kC1Patches - 1) % kC1Patches);
+        issued += 2 * gridDim.x;
         nx.advance(sx, sy, H, W);
       }
-      mbar_wait(&patch_bar[warp][buf], (uint32_t)(it / kC1Patches) & 1u);
+      mbar_wait(&patch_bar[warp][buf], (uint32_t)(li / kC1Patches) & 1u);
       const float* mp = &patch[warp][buf][0];
       // this lane's pixel: tap (kh,kw,c) = patch[kh][(lane + kw - 1 + kPatchLead)*3 + c], k = (kh*3+kw)*3 + c
       uint32_t pk[16];
@@ -233,7 +245,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
       }
       if (lane == 0) mbar_wait(&empty_bar[stage], ph ^ 1u);          // MMA has released this stage
       __syncwarp();                                                  // also: every lane is done reading the patch
-      const int row = warp * 32 + lane;
+      const int row = seg * 32 + lane;
       uint8_t* rp = &sA[stage][row * 64];
       const int sw = (row >> 1) & 3;
 #pragma unroll
@@ -243,7 +255,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(32);
@@ -261,17 +273,13 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
         umma_commit(&tfull_bar[acc]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 10) {
     // ================================ epilogue ================================
     // two warpgroups (warps 8..11, 12..15) drain alternate tiles: group g owns TMEM stages g and g+2
-    const int q = warp & 3, grp = (warp - 8) >> 2;
+    const int q = warp & 3, grp = (warp - 10) >> 2;      // q = hardware TMEM lane quarter of this warp (warp % 4)
     const int Hq = H / 2 + 1, Wq = W / 2 + 1;
-    float sc[32], sh[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      sc[c] = __ldg(scale + c);
-      sh[c] = __ldg(shift + c);
-    }
+    // folded BN scale / shift live in shared memory (broadcast float4 reads): 64 registers less per thread
+    // keeps the 576-thread CTA spill-free
     const bool use_tma = out_same == nullptr;
     const int step_px = 256 * (int)gridDim.x, sx = step_px % W, sy = step_px / W;
     SegCoord sg;
@@ -295,18 +303,22 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
       if (!seg_ok) continue;
       uint32_t packed[16];
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const uint32_t a = c < 16 ? r0[c] : r1[c - 16], b = c < 16 ? r0[c + 1] : r1[c - 15];
-        float v0 = fmaf(__uint_as_float(a), sc[c], sh[c]);
-        float v1 = fmaf(__uint_as_float(b), sc[c + 1], sh[c + 1]);
+      for (int c = 0; c < 32; c += 4) {
+        const float4 sc4 = *reinterpret_cast<const float4*>(s_sc + c), sh4 = *reinterpret_cast<const float4*>(s_sh + c);
+        const uint32_t* rr = c < 16 ? &r0[c] : &r1[c - 16];
+        float v0 = fmaf(__uint_as_float(rr[0]), sc4.x, sh4.x), v1 = fmaf(__uint_as_float(rr[1]), sc4.y, sh4.y);
+        float v2 = fmaf(__uint_as_float(rr[2]), sc4.z, sh4.z), v3 = fmaf(__uint_as_float(rr[3]), sc4.w, sh4.w);
         v0 = fmaxf(alpha * v0, v0);
         v1 = fmaxf(alpha * v1, v1);
-        __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-        packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        v2 = fmaxf(alpha * v2, v2);
+        v3 = fmaxf(alpha * v3, v3);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+        packed[c >> 1] = *reinterpret_cast<uint32_t*>(&h0);
+        packed[(c >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h1);
       }
       if (use_tma) {
         // pixel pair (lane>>1) = one 128-byte row of the s2d tensor; SWIZZLE_128B chunk = c ^ (pair & 7)
-        uint8_t* so = &sOut[warp - 8][nst & 1][0];
+        uint8_t* so = &sOut[warp - 10][nst & 1][0];
         ++nst;
         if (lane == 0) bulk_wait_read<1>();                          // the store two tiles ago has read this buffer
         __syncwarp();
@@ -335,7 +347,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 128);
   }

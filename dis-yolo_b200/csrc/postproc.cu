@@ -16,31 +16,9 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 
 // ------------------------------------------------------------------------------------------
 // decode: one thread per candidate (interpret_output :465-514 + filter_detections :523-561)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
-  const int b = blockIdx.y;
-  const int n0 = 3 * (a.g[0] * a.g[0] + a.g[1] * a.g[1] + a.g[2] * a.g[2]);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n0) return;
-  const int off1 = 3 * a.g[0] * a.g[0];
-  const int off2 = off1 + 3 * a.g[1] * a.g[1];
-  const int j = idx < off1 ? 0 : (idx < off2 ? 1 : 2);
-  const int local = idx - (j == 0 ? 0 : (j == 1 ? off1 : off2));
-  const int g = a.g[j];
-  const int anchor = local % 3;
-  const int cell = local / 3;
-  const int cy = cell / g, cx = cell % g;
-  const int depth = 5 + a.num_class;
-  const float* p = a.yolo[j] + (((long long)b * g + cy) * g + cx) * (3 * depth) + anchor * depth;
-
-  float t[5 + kMaxClasses];
-  if (depth == 8) {
-    const float4 u = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    t[0] = u.x; t[1] = u.y; t[2] = u.z; t[3] = u.w;
-    t[4] = v.x; t[5] = v.y; t[6] = v.z; t[7] = v.w;
-  } else {
-    for (int i = 0; i < depth; ++i) t[i] = __ldg(p + i);
-  }
+// one candidate: class-specific confidence, threshold, box, clip, append (any order: NMS is order independent)
+__device__ __forceinline__ void decode_candidate(const DecodeArgs& a, const float (&t)[5 + kMaxClasses], int b, int j,
+                                                 int g, int cy, int cx, int anchor, int idx, int n0) {
   // class-specific confidence = sigmoid(obj) * max softmax(cls)   (:528-548, softmax not sigmoid)
   float mx = t[5];
   int cls = 0;
@@ -81,6 +59,43 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
       c.y1 = y1; c.x1 = x1; c.y2 = y2; c.x2 = x2;
       c.score = score; c.idx = idx; c.cls = cls; c.pad = 0;
       a.cand[(long long)b * a.cap + slot] = c;
+    }
+  }
+}
+
+// One thread per grid CELL (its 3 anchors): for 3 classes a cell is 24 consecutive floats = six 16-byte
+// loads, consecutive threads read consecutive cells (96 B apart), and the cell -> (y, x) division is paid
+// once per 3 candidates.  Candidate index = scale offset + cell*3 + anchor (the reference's flattening order,
+// :527-542).
+__global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
+  const int b = blockIdx.y;
+  const int c0 = a.g[0] * a.g[0], c1 = c0 + a.g[1] * a.g[1], ncell = c1 + a.g[2] * a.g[2];
+  const int n0 = 3 * ncell;
+  const int cell_all = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell_all >= ncell) return;
+  const int j = cell_all < c0 ? 0 : (cell_all < c1 ? 1 : 2);
+  const int cell = cell_all - (j == 0 ? 0 : (j == 1 ? c0 : c1));
+  const int g = a.g[j];
+  const int cy = cell / g, cx = cell - cy * g;
+  const int depth = 5 + a.num_class;
+  const float* p = a.yolo[j] + ((long long)b * g * g + cell) * (3 * depth);
+  const int idx0 = 3 * (cell_all);                     // = 3*(cells of the earlier scales) + cell*3
+  float t[5 + kMaxClasses];
+  if (depth == 8) {
+    float4 q[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) q[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
+#pragma unroll
+    for (int an = 0; an < 3; ++an) {
+      const float4 u = q[2 * an], v = q[2 * an + 1];
+      t[0] = u.x; t[1] = u.y; t[2] = u.z; t[3] = u.w;
+      t[4] = v.x; t[5] = v.y; t[6] = v.z; t[7] = v.w;
+      decode_candidate(a, t, b, j, g, cy, cx, an, idx0 + an, n0);
+    }
+  } else {
+    for (int an = 0; an < 3; ++an) {
+      for (int i = 0; i < depth; ++i) t[i] = __ldg(p + an * depth + i);
+      decode_candidate(a, t, b, j, g, cy, cx, an, idx0 + an, n0);
     }
   }
 }
@@ -405,7 +420,7 @@ void masks_set_streaming(int on) { g_mask_stream = on; }
 int launch_decode(const DecodeArgs& a, cudaStream_t st) {
   DY_CHECK(a.num_class >= 1 && a.num_class <= kMaxClasses, "num_class");
   const int n0 = 3 * (a.g[0] * a.g[0] + a.g[1] * a.g[1] + a.g[2] * a.g[2]);
-  dim3 grid((n0 + 255) / 256, a.B);
+  dim3 grid((n0 / 3 + 255) / 256, a.B);              // one thread per cell
   decode_kernel<<<grid, 256, 0, st>>>(a);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
