@@ -168,23 +168,35 @@ bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ 
   const uint32_t G = gridDim.x * (uint32_t)R;
   float fa[8], fb[8];
   if (fin.sum != nullptr) {
+    // the double-precision finalize is done once per block (row-0 threads, one vector column each) and
+    // shared through smem: FP64 sqrt / div are too slow to repeat in every thread
+    __shared__ float s_a[8 * kT], s_b[8 * kT];
+    if (rl == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j;
+        const double m = fin.sum[c] / (double)fin.M;
+        double var = fin.sumsq[c] / (double)fin.M - m * m;
+        if (var < 0.0) var = 0.0;
+        const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
+        const float aa = fin.gamma[c] * is;
+        const float bb = fin.beta[c] - (float)m * aa;
+        s_a[c] = aa;
+        s_b[c] = bb;
+        if (blockIdx.x == 0) {
+          fin.a_out[c] = aa;
+          fin.b_out[c] = bb;
+          fin.mean_out[c] = (float)m;
+          fin.var_out[c] = (float)var;
+          fin.invstd_out[c] = is;
+        }
+      }
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = v * 8 + j;
-      const double m = fin.sum[c] / (double)fin.M;
-      double var = fin.sumsq[c] / (double)fin.M - m * m;
-      if (var < 0.0) var = 0.0;
-      const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
-      const float aa = fin.gamma[c] * is;
-      fa[j] = aa;
-      fb[j] = fin.beta[c] - (float)m * aa;
-      if (blockIdx.x == 0 && rl == 0) {
-        fin.a_out[c] = aa;
-        fin.b_out[c] = fb[j];
-        fin.mean_out[c] = (float)m;
-        fin.var_out[c] = (float)var;
-        fin.invstd_out[c] = is;
-      }
+      fa[j] = s_a[v * 8 + j];
+      fb[j] = s_b[v * 8 + j];
     }
   } else {
     load8f(a + v * 8, fa);
