@@ -232,7 +232,75 @@ __global__ void overlaps_finalize_kernel(const int* __restrict__ inter, const in
   out[pr] = __fdiv_rn(it, __fsub_rn(__fadd_rn(a1, a2), it));      // 0/0 = NaN, like NumPy
 }
 
+// ---- training label assignment: utils/train_data.py:134-178 (+ flips :189-228, normalisation :258-262) -------
+// One thread per image (at most 20 boxes, and "the first box wins a cell" makes the loop sequential).
+__global__ void assign_labels_kernel(LabelArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const int depth = 5 + a.num_class, net = a.net;
+  const double sx = a.place[b * 4 + 0], sy = a.place[b * 4 + 1], dx = a.place[b * 4 + 2], dy = a.place[b * 4 + 3];
+  const int flip = a.flip ? a.flip[b] : 1;
+  const int nb = min(a.nbox[b], a.max_box);
+  const float netm1 = (float)(net - 1), size_f = (float)net;
+  for (int i = 0; i < nb; ++i) {
+    const float* bx = a.boxes + ((long long)b * a.max_box + i) * 5;
+    const int cls = (int)bx[4];
+    auto clampd = [&](double v) { return fmax(fmin(v, (double)(net - 1)), 0.0); };
+    const double x1 = clampd((double)bx[0] * sx + dx), y1 = clampd((double)bx[1] * sy + dy);
+    const double x2 = clampd((double)bx[2] * sx + dx), y2 = clampd((double)bx[3] * sy + dy);
+    const double xc = (x2 + x1) / 2.0, yc = (y2 + y1) / 2.0, w = x2 - x1, h = y2 - y1;
+    float fx = (float)xc, fy = (float)yc;
+    const float fw = (float)w, fh = (float)h;
+    // best anchor by IoU of the centred (w, h) boxes, fp32 like the reference's np.float32 arrays
+    const float hw = (float)(w / 2.0), hh = (float)(h / 2.0);
+    const float box_area = __fmul_rn(__fmul_rn(hw, hh), 4.f);
+    float best = -1.f;
+    int besti = 0;
+    for (int k = 0; k < 9; ++k) {
+      const float aw = __fdiv_rn(a.anchors[2 * k], 2.f), ah = __fdiv_rn(a.anchors[2 * k + 1], 2.f);
+      const float anc_area = __fmul_rn(__fmul_rn(ah, aw), 4.f);
+      const float iw = fmaxf(__fsub_rn(fminf(hw, aw), fmaxf(-hw, -aw)), 0.f);
+      const float ih = fmaxf(__fsub_rn(fminf(hh, ah), fmaxf(-hh, -ah)), 0.f);
+      const float inter = __fmul_rn(iw, ih);
+      const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(box_area, anc_area), inter));
+      if (iou > best) { best = iou; besti = k; }        // first maximum, like np.argmax
+    }
+    if (best > 0.f) {
+      const int s = besti / 3, an = besti % 3;
+      const int g = a.grid[s];
+      int x_ind = (int)(xc * g / net), y_ind = (int)(yc * g / net);
+      float lx = fx, ly = fy;
+      if (flip == 2) { x_ind = g - 1 - x_ind; lx = __fsub_rn(netm1, fx); }
+      if (flip == 3) { y_ind = g - 1 - y_ind; ly = __fsub_rn(netm1, fy); }
+      float* cell = a.yolo[s] + ((((long long)b * g + y_ind) * g + x_ind) * 3 + an) * depth;
+      if (cell[4] != 1.f) {                              // an earlier box owns this cell: skipped (:166-167)
+        cell[0] = __fdiv_rn(lx, size_f); cell[1] = __fdiv_rn(ly, size_f);
+        cell[2] = __fdiv_rn(fw, size_f); cell[3] = __fdiv_rn(fh, size_f);
+        cell[4] = 1.f;
+        cell[5 + cls] = 1.f;
+      }
+    }
+    if (flip == 2) fx = __fsub_rn(netm1, fx);
+    if (flip == 3) fy = __fsub_rn(netm1, fy);
+    float* tb = a.true_boxes + ((long long)b * a.max_box + i) * 5;
+    tb[0] = __fdiv_rn(fx, size_f); tb[1] = __fdiv_rn(fy, size_f);
+    tb[2] = __fdiv_rn(fw, size_f); tb[3] = __fdiv_rn(fh, size_f);
+    tb[4] = (float)cls;
+  }
+}
+
 }  // namespace
+
+int launch_assign_labels(const LabelArgs& a, cudaStream_t st) {
+  DY_CHECK(a.B >= 1 && a.max_box >= 1 && a.num_class >= 1 && a.net >= 32, "label geometry");
+  const int depth = 5 + a.num_class;
+  for (int s = 0; s < 3; ++s)
+    DY_CUDA(cudaMemsetAsync(a.yolo[s], 0, (size_t)a.B * a.grid[s] * a.grid[s] * 3 * depth * 4, st));
+  DY_CUDA(cudaMemsetAsync(a.true_boxes, 0, (size_t)a.B * a.max_box * 5 * 4, st));
+  assign_labels_kernel<<<(a.B + 63) / 64, 64, 0, st>>>(a);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
 
 int launch_mask_overlaps(const unsigned char* m1, int n1, const unsigned char* m2, int n2, long long P, int* ws,
                          float* out, cudaStream_t st) {

@@ -33,6 +33,20 @@ int launch_postprocess(const float* det_box, const int* count, int n_max, const 
                        int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
                        unsigned char* full_masks, unsigned char* merged, cudaStream_t st);
 
+// training labels (utils/train_data.py:134-178, flips :189-228, normalisation :258-262)
+struct LabelArgs {
+  const float* boxes;     // [B,max_box,5] (x1,y1,x2,y2,class) in ORIGINAL image pixels, first nbox[b] rows valid
+  const int* nbox;        // [B]
+  const float* place;     // [B,4] (sx, sy, dx, dy): letterbox / scale-crop placement into the net square
+  const int* flip;        // [B] 1 none, 2 horizontal, 3 vertical (null = none)
+  float* yolo[3];         // yolo3 (stride 8), yolo2 (stride 16), yolo1 (stride 32): [B,g,g,3,5+C], zeroed here
+  float* true_boxes;      // [B,max_box,5] (xc,yc,w,h)/net, class; zeroed here
+  int grid[3];
+  float anchors[18];
+  int B, max_box, num_class, net;
+};
+int launch_assign_labels(const LabelArgs& a, cudaStream_t st);
+
 // compute_overlaps_masks (utils/voc_eval_mask.py:38-56): IoU of every mask of set 1 with every mask of set 2;
 // masks are [n, P] bytes (non-zero = inside), ws = n1*n2 + n1 + n2 ints of scratch, out [n1, n2] fp32
 int launch_mask_overlaps(const unsigned char* m1, int n1, const unsigned char* m2, int n2, long long P, int* ws,

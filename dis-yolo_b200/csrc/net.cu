@@ -1291,6 +1291,24 @@ int dy_mask_overlaps(const uint8_t* masks1_dev, int32_t n1, const uint8_t* masks
   return rc;
 }
 
+int dy_assign_labels(dy_net* net, const float* boxes_dev, const int32_t* nbox_dev, const float* place_dev,
+                     const int32_t* flip_dev, int32_t B, int32_t max_box, float* yolo3_dev, float* yolo2_dev,
+                     float* yolo1_dev, float* true_boxes_dev, void* stream) {
+  DY_CHECK(net && boxes_dev && nbox_dev && place_dev && yolo3_dev && yolo2_dev && yolo1_dev && true_boxes_dev,
+           "null argument");
+  DY_CHECK(B >= 1 && max_box >= 1, "batch / max_box");
+  LabelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.boxes = boxes_dev; a.nbox = nbox_dev; a.place = place_dev; a.flip = flip_dev;
+  a.yolo[0] = yolo3_dev; a.yolo[1] = yolo2_dev; a.yolo[2] = yolo1_dev;
+  a.true_boxes = true_boxes_dev;
+  a.grid[0] = net->S / 8; a.grid[1] = net->S / 16; a.grid[2] = net->S / 32;
+  memcpy(a.anchors, net->cfg.anchors, sizeof(a.anchors));
+  a.B = B; a.max_box = max_box; a.num_class = net->cfg.num_classes; a.net = net->S;
+  note_launch();
+  return launch_assign_labels(a, (cudaStream_t)stream);
+}
+
 // CRC-32C (Castagnoli), slicing-by-8: checksums of TensorFlow checkpoint-V2 bundles (tf_checkpoint.py).
 // Host-only utility: no device is touched.
 uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc) {

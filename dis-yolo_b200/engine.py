@@ -461,6 +461,22 @@ class Engine(object):
                    'dy_mask_overlaps')
         return out
 
+    def assign_labels(self, boxes, nbox, place, flip=None, max_box=20):
+        """The label assignment of defect_train.get (utils/train_data.py:134-178) on the GPU.
+        boxes [B,max_box,5] (x1,y1,x2,y2,class; original pixels), nbox [B], place [B,4] (sx,sy,dx,dy),
+        flip [B] (1/2/3) -> (yolo3, yolo2, yolo1, true_boxes) cuda tensors in the training step's feed layout."""
+        t = self.torch
+        boxes, place = self._dev(boxes, t.float32), self._dev(place, t.float32)
+        nbox = self._dev(nbox, t.int32)
+        flip = self._dev(flip, t.int32) if flip is not None else None
+        B, S, d = int(boxes.shape[0]), self.image_size, 5 + self.num_classes
+        ys = [t.empty((B, S // m, S // m, 3, d), dtype=t.float32, device=self.device) for m in (8, 16, 32)]
+        tb = t.empty((B, max_box, 5), dtype=t.float32, device=self.device)
+        _lib.check(self.lib.dy_assign_labels(self.h, _ptr(boxes), _ptr(nbox), _ptr(place), _ptr(flip), B, int(max_box),
+                                             _ptr(ys[0]), _ptr(ys[1]), _ptr(ys[2]), _ptr(tb), self._stream()),
+                   'dy_assign_labels')
+        return ys[0], ys[1], ys[2], tb
+
 
 def set_option(name, value):
     """dy_set_option: planning overrides of the conv engine ('tc_resident', 'tc_halo'; -1 = auto)."""

@@ -177,6 +177,16 @@ int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32
 int dy_mask_overlaps(const uint8_t* masks1_dev, int32_t n1, const uint8_t* masks2_dev, int32_t n2, int64_t pixels,
                      float* overlaps_dev, void* stream);
 
+/* Replaces the label assignment of defect_train.get (utils/train_data.py:134-178; flips :189-228;
+ * normalisation :258-262): ground-truth boxes (x1,y1,x2,y2,class) in original image
+ * pixels [B,max_box,5] with nbox_dev[b] valid rows, the placement place_dev [B,4] = (sx, sy, dx, dy) of the
+ * (augmented) image inside the net square and flip_dev [B] (1 none / 2 horizontal / 3 vertical, may be
+ * NULL) -> the feed tensors of the training step: yolo3/yolo2/yolo1 [B,g,g,3,5+C] (best-IoU anchor, first
+ * box wins a cell, coordinates / image_size) and true_boxes [B,max_box,5].  Outputs are zeroed first. */
+int dy_assign_labels(dy_net* net, const float* boxes_dev, const int32_t* nbox_dev, const float* place_dev,
+                     const int32_t* flip_dev, int32_t B, int32_t max_box, float* yolo3_dev, float* yolo2_dev,
+                     float* yolo1_dev, float* true_boxes_dev, void* stream);
+
 /* Measurement aid for bench.py: device milliseconds of each post-processing kernel (decode+threshold,
  * per-class NMS, top-k/finalize, mask assembly), each launched `reps` times back to back between two
  * CUDA events on `stream`; ms_host[4] receives the per-launch averages.  Same inputs as dy_detect +
