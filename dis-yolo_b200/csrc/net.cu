@@ -182,7 +182,6 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   const bool enough_work = m_tiles >= num_sms;
   const bool fits = d.cout_pad <= 256 && (size_t)d.cout_pad * K * 2 <= kResidentSlabMax;
   const bool has_res = d.residual != nullptr;
-  const bool dual = d.out[1].mode != OUT_NONE;
   const bool up2 = d.out[0].mode == OUT_UP2 || d.out[1].mode == OUT_UP2;
   if (enough_work) {
     if (d.k == 1) {
