@@ -251,10 +251,19 @@ int dy_get_weights(dy_net* net, const char* tf_name, float* host, int64_t capaci
  * dis-yolo_b200/tf_checkpoint.py.  Host-only. */
 uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
 
-/* Tuning / test overrides of the conv engine's planning heuristics; value -1 = automatic.
- *   "tc_resident": 0 never / 1 whenever it fits -- keep a CTA's weight slab resident in smem
- *   "tc_halo":     0 never / 1 whenever legal   -- one halo'd activation box feeds all 3 horizontal taps
- * Affects plans built afterwards (dy_finalize_weights, dy_conv_layer). */
+/* Tuning / test / measurement overrides (A/B runs in scripts/, forced-mode parity tests); value -1 =
+ * automatic for the planning switches.  Planning switches affect plans built afterwards
+ * (dy_finalize_weights, dy_conv_layer, dy_train_init).
+ *   "tc_resident"   0 never / 1 whenever it fits -- keep a CTA's weight slab resident in smem
+ *   "tc_halo"       0 never / 1 whenever legal   -- one halo'd activation box feeds all 3 horizontal taps
+ *   "tc_staged", "tc_tma_epi"   epilogue through shared memory / through TMA stores + TMA residual loads
+ *   "tc_dual_issue" two MMA-issuer threads with split stage rings (thin tiles)
+ *   "tc_skip_epilogue"          measurement only: epilogues drain the accumulator and do nothing else
+ *   "conv1_tc"      0: the stem on CUDA cores instead of the tcgen05 im2col kernel
+ *   "wgrad_fuse_kw" 0 one CTA per tap / 1 (default) fused kernel rows where the N tile is kept / 2 always
+ *   "wgrad_lbo_a", "wgrad_sbo_a", "wgrad_lbo_b", "wgrad_sbo_b"  bring-up: UMMA descriptor field overrides
+ *   "mask_streaming_stores"     1 (default) st.global.cs in the mask-assembly kernel, 0 plain stores
+ * Unknown names return DY_STATUS_NOTFOUND. */
 int dy_set_option(const char* name, int32_t value);
 
 /* Kernel launches issued by this library since the last call (bench.py's gpu_launches). */
