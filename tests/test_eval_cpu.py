@@ -24,3 +24,11 @@ def test_overlaps_and_ap_known_answers(golden):
     b = np.zeros((8, 8, 2), bool); b[:4, :2, 0] = True; b[:, :, 1] = True
     assert OE.compute_overlaps_masks(a, b).tolist() == [[0.5, 0.25]]           # SURVEY 8c known answer (4)
     assert abs(OE.voc_ap(np.array([.5, .5, 1.]), np.array([1., .5, 2. / 3])) - golden['voc_ap']['ap']) < 1e-15
+
+
+def test_product_voc_ap_matches_reference(golden):
+    """evalmap.voc_ap (host part of the product's voc_eval mirror) against the reference's voc_ap output."""
+    from disyolo_b200 import evalmap
+    rec, prec = np.array([.5, .5, 1.]), np.array([1., .5, 2. / 3])
+    assert abs(evalmap.voc_ap(rec, prec, False) - golden['voc_ap']['ap']) < 1e-15
+    assert evalmap.voc_ap(rec, prec, True) == OE.voc_ap(rec, prec, True)
