@@ -190,17 +190,20 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: use every host core
     W = dy.init_weights('lively', 0)
     t0 = time.perf_counter()
-    ips, total, cores = cpu_reference_images_per_s(args.steps, max(1, min(args.warmup, 1)), W)
-    ms = 1000.0 * CPU_SAMPLE_BATCH / ips
+    # images per step sized so that the K timed steps stay around a minute of host work (~0.35 s per image
+    # on 16 cores): 4 images per step up to K = 40, 1 image per step from K = 160
+    batch = max(1, min(CPU_SAMPLE_BATCH, 160 // max(1, args.steps)))
+    ips, total, cores = cpu_reference_images_per_s(args.steps, max(1, min(args.warmup, 1)), W, batch=batch)
+    ms = 1000.0 * batch / ips
     line = dict(metric=METRIC, value=ips, unit='images/s', impl='reference', n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic',
                 config=dict(workload='DIS-YOLO inference 576x576 (BASELINE configs[1]), lively random-init weights',
-                            per_step='%d images (bounded sample of the batch-64 step)' % CPU_SAMPLE_BATCH,
+                            per_step='%d images (bounded sample of the batch-64 step)' % batch,
                             image=IMAGE, thresh=THRESH),
                 cpu_baseline=dict(value=ips, unit='images/s', cores=cores, kind='port',
                                   sample='%d steps x %d images 576x576 through oracle.evaluate (median step)'
-                                         % (args.steps, CPU_SAMPLE_BATCH)),
+                                         % (args.steps, batch)),
                 e2e=dict(value=ips, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0, wall_s=time.perf_counter() - t0)
     print(json.dumps(line))
