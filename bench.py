@@ -10,8 +10,10 @@ N > 1 every rank runs its own shard of the batch, no collective on the data path
 weak scaling).  One JSON line is printed by rank 0.
 
   value    images/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e      the same metric through the host-buffer C-ABI call (dy_forward_host): pinned host
-           images H2D, forward, D2H of counts / boxes / the det_count masks -- inside the timing
+  e2e      the same metric through the host-buffer C-ABI call (dy_forward_host_begin_u8 / _end_cropped):
+           pinned host uint8 images H2D (divided by 255 on the device exactly like image_read), forward,
+           D2H of counts / boxes / the box-cropped mask maps the reference's consumer reads -- inside the
+           timing; e2e_reference_layout = the same through fp32 images and full [n,S,S] maps
   roofline dominant kernel = the tcgen05 conv kernel (81 launches per step): algorithmic FLOPs of
            layers 2..82 / summed per-layer device time measured live with CUDA events
   cpu_baseline  the oracle (NumPy/torch-CPU restatement of the reference graph; TensorFlow 1.x
@@ -228,12 +230,19 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     B = args.batch
     peaks = measured_peaks()
+    # pinned staging memory on the GPU's own NUMA node (first touch follows the CPU affinity)
+    from disyolo_b200.hostmem import bind_to_gpu_numa
+    affinity0 = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+    numa = bind_to_gpu_numa(local) if not args.no_numa else dict(bound=False, node=None, cpus=0)
 
     W = dy.init_weights('lively', 0)
     eng = dy.Engine(image_size=IMAGE, max_batch=B, precision='bf16', device=local)
     eng.load_weights(W)
     rng = np.random.default_rng(1000 + rank)
-    img_host = torch.from_numpy(rng.random((B, IMAGE, IMAGE, 3), dtype=np.float32)).pin_memory()
+    # synthetic letterboxed images as image_read holds them before its `/ 255.`: uint8 RGB; the fp32 feed of
+    # the reference protocol is their float64 quotient rounded to float32 (calculate_test_map.py:175)
+    u8_host = torch.from_numpy(rng.integers(0, 256, (B, IMAGE, IMAGE, 3), dtype=np.uint8)).pin_memory()
+    img_host = (u8_host.to(torch.float64) / 255.0).to(torch.float32).pin_memory()
     win_host = torch.tensor([[0, 0, 1, 1]], dtype=torch.float32).repeat(B, 1).pin_memory()
     img = img_host.to(dev)
     win = win_host.to(dev)
@@ -293,29 +302,42 @@ def run_ours(args):
                  for n in range(1, 83)}
 
     # ---- e2e: host buffers through the C-ABI call ----
-    for _ in range(2):          # warm-up through the same pipelined calls (allocates all pinned result sets)
-        tks = [eng.forward_host_begin(img_host, win_host, THRESH) for _ in range(3)]
-        for tkk in tks:
-            eng.forward_host_end(tkk)
-    barrier()
-    # steady-state serving loop: two batches in flight (dy_forward_host_begin / _end), every step
-    # includes its own pinned-host -> device image copy and the device -> host copy of its results
-    t0 = time.perf_counter()
-    n_e2e = max(6, args.steps)
-    d2h = 0
+    # steady-state serving loop, 3 batches in flight (dy_forward_host_begin* / _end*): every step includes its
+    # own pinned-host -> device image copy and the device -> host copy of its results
     from collections import deque
-    flight = deque(eng.forward_host_begin(img_host, win_host, THRESH) for _ in range(min(2, n_e2e)))
-    begun = len(flight)
-    for i in range(n_e2e):
-        if begun < n_e2e:
-            flight.append(eng.forward_host_begin(img_host, win_host, THRESH))
-            begun += 1
-        raw, box, cnt, msk = eng.forward_host_end(flight.popleft())
-        d2h += int(cnt.sum().item()) * sm * sm * 4 + B * 4 + 2 * B * md * 24
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * B * n_e2e / e2e_s
-    h2d = B * IMAGE * IMAGE * 3 * 4 + B * 16
+
+    def e2e_loop(images, mode, n_steps):
+        for _ in range(2):      # warm-up through the same pipelined calls (allocates all pinned result sets)
+            tks = [eng.forward_host_begin(images, win_host, THRESH, masks=mode) for _ in range(3)]
+            for tkk in tks:
+                eng.forward_host_end(tkk)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        flight = deque(eng.forward_host_begin(images, win_host, THRESH, masks=mode) for _ in range(min(2, n_steps)))
+        begun = len(flight)
+        for i in range(n_steps):
+            if begun < n_steps:
+                flight.append(eng.forward_host_begin(images, win_host, THRESH, masks=mode))
+                begun += 1
+            raw, box, cnt, msk = eng.forward_host_end(flight.popleft())
+            d2h += B * 4 + 2 * B * md * 24
+            if mode == 'cropped':
+                d2h += (B * md + 1) * 8 + int(msk[1].numel()) * 4
+            else:
+                d2h += int(cnt.sum().item()) * sm * sm * 4
+        torch.cuda.synchronize()
+        secs = max_over_ranks(time.perf_counter() - t0)
+        return world * B * n_steps / secs, d2h // n_steps
+
+    n_e2e = max(6, args.steps)
+    e2e_value, d2h = e2e_loop(u8_host, 'cropped', n_e2e)
+    h2d = B * IMAGE * IMAGE * 3 + B * 16
+    ref_value, ref_d2h = e2e_loop(img_host, 'full', max(6, min(args.steps, 20)))
+    e2e_ref = dict(value=ref_value, unit='images/s', h2d_bytes_per_step=B * IMAGE * IMAGE * 3 * 4 + B * 16,
+                   d2h_bytes_per_step=ref_d2h,
+                   mode='fp32 [B,S,S,3] images in, det_count[b] full fp32 [S/2,S/2] maps per image out '
+                        '(the reference feed / fetch layouts verbatim)')
 
     # ---- e2e of the whole per-image sequence of the reference's test driver (calculate_test_map.py:208-269):
     # uint8 images up, letterbox + network + post-processing to original-image masks on the GPU, boxes and
@@ -412,11 +434,29 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        if affinity0 is not None:
+            os.sched_setaffinity(0, affinity0)          # the CPU baseline uses every host core again
         torch.set_num_threads(os.cpu_count() or 1)
         ips, total, cores = cpu_reference_images_per_s(8, 1, W)
         cpu = dict(value=ips, unit='images/s', cores=cores, kind='port',
                    sample='8 steps x %d images 576x576 through oracle.evaluate (median step), %.1f s CPU wall'
                           % (CPU_SAMPLE_BATCH, total))
+
+    # ---- BASELINE configs[3]: the data-parallel training step, every rank (same torchrun launch) ----
+    train = None
+    if not args.no_train:
+        eng.close()                                   # free the batch-64 inference engine first
+        torch.cuda.empty_cache()
+        train = train_leg(16, 'bf16', max(5, min(args.steps, 20)), 3, rank, local, world, dist)
+    # ---- BASELINE configs[4]: stress (rank 0, N=1) ----
+    stress = None
+    if not args.no_stress and rank == 0 and world == 1:
+        try:
+            eng.close()
+        except Exception:
+            pass
+        torch.cuda.empty_cache()
+        stress = stress_leg(local, peaks)
 
     if rank == 0:
         line = dict(
@@ -429,8 +469,12 @@ def run_ours(args):
                         cache='inputs (255 MB) and activations (GBs) exceed the 126 MB L2; no flush needed',
                         detections_per_step=dets),
             clocks=clocks,
-            e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h // n_e2e,
-                     steps=n_e2e, mode='3 batches in flight: dy_forward_host_begin/_end'),
+            e2e=dict(value=e2e_value, unit='images/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                     steps=n_e2e,
+                     mode='3 batches in flight: dy_forward_host_begin_u8 / dy_forward_host_end_cropped -- uint8 '
+                          'letterboxed images in (divided by 255 on the device, bit-identical input), boxes + '
+                          'counts + the box-cropped mask maps det_mask[y1:y2,x1:x2] out', numa=numa),
+            e2e_reference_layout=e2e_ref,
             e2e_pipeline=pipe_line,
             gpu_launches=launches,
             roofline=dict(bound='tensor', kernel='conv_tc_kernel (81 launches/step, layers 2..82)',
@@ -439,32 +483,20 @@ def run_ours(args):
                           peak_source=peaks['source'] + ' (sustained bf16; kernel timed inside a long step)',
                           algorithmic_flops_per_step=tc_flops, kernel_ms_per_step=tc_ms,
                           network_ms_per_step=net_ms, traffic=args.traffic),
-            roofline_extra=extra, latency_batch1=lat, cpu_baseline=cpu, per_layer=per_layer)
+            roofline_extra=extra, latency_batch1=lat, cpu_baseline=cpu, train=train, stress=stress,
+            per_layer=per_layer)
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def run_train(args):
-    """BASELINE configs[3]: training step (forward + losses + backward + all-reduce + Adam), batch
-    16 per GPU at 576x576, data parallel; tensor-core (bf16) engine by default."""
+def synth_train_batch(B, rank):
+    """Synthetic training feed of BASELINE configs[3] in defect_train.get()'s formats (utils/train_data.py:44-52,
+    146-178, 258-265): 6 boxes per image, best-anchor label assignment, rectangular bool masks, fixed RoI permutations."""
     import numpy as np
-    import torch
-    import disyolo_b200 as dy
-    rank, local, world = dist_env()
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    else:
-        dist = None
-    B = args.batch if args.batch != PER_GPU_BATCH else 16
-    eng = dy.Engine(image_size=IMAGE, max_batch=B, precision=args.train_precision, device=local)
-    eng.load_weights(dy.init_weights('lively', 0))
-    tr = dy.DataParallelTrainer(eng, bucket_mb=25)
     rng = np.random.default_rng(7 + rank)
-    img = torch.from_numpy(rng.random((B, IMAGE, IMAGE, 3), dtype=np.float32)).cuda()
+    img = rng.random((B, IMAGE, IMAGE, 3), dtype=np.float32)
     base = IMAGE // 32
     labels = [np.zeros((B, base * m, base * m, 3, 8), np.float32) for m in (4, 2, 1)]
     tb = np.zeros((B, 20, 5), np.float32)
@@ -486,59 +518,161 @@ def run_train(args):
                                                                       cls == 0, cls == 1, cls == 2]
     pp = np.stack([rng.permutation(30) for _ in range(B)]).astype(np.int32)
     pg = np.stack([rng.permutation(20) for _ in range(B)]).astype(np.int32)
+    return img, labels, tb, tm, pp, pg
+
+
+def train_leg(B, precision, steps, warm, rank, local, world, dist, e2e_steps=0):
+    """BASELINE configs[3]: training step (forward + losses + backward + all-reduce + Adam), batch B per GPU at
+    576x576, data parallel (bucketed NCCL all-reduce overlapped with backward).  Returns the result dict."""
+    import torch
+    import disyolo_b200 as dy
+    eng = dy.Engine(image_size=IMAGE, max_batch=B, precision=precision, device=local)
+    eng.load_weights(dy.init_weights('lively', 0))
+    tr = dy.DataParallelTrainer(eng, bucket_mb=25)
+    img_h, labels_h, tb_h, tm_h, pp_h, pg_h = synth_train_batch(B, rank)
     # inputs resident in HBM before the timed region (the host-buffer protocol is timed separately below)
-    host = (labels, tb, tm, pp, pg)
-    labels = [torch.from_numpy(l).cuda() for l in labels]
-    tb, tm = torch.from_numpy(tb).cuda(), torch.from_numpy(tm).cuda()
-    pp, pg = torch.from_numpy(pp).cuda(), torch.from_numpy(pg).cuda()
-    steps, warm = max(1, args.steps), max(3, args.warmup)
+    img = torch.from_numpy(img_h).cuda()
+    labels = [torch.from_numpy(l).cuda() for l in labels_h]
+    tb, tm = torch.from_numpy(tb_h).cuda(), torch.from_numpy(tm_h).cuda()
+    pp, pg = torch.from_numpy(pp_h).cuda(), torch.from_numpy(pg_h).cuda()
+
+    def timed(n):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            out = tr.step(img, labels, tb, tm, pp, pg, THRESH, 1e-4)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n, out
+
     for _ in range(warm):
         losses = tr.step(img, labels, tb, tm, pp, pg, THRESH, 1e-4)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
     eng.lib.dy_launch_count(1)
+    ms_step, losses = timed(steps)
+    launches = int(eng.lib.dy_launch_count(0))
+    res = dict(metric='training images/s @576^2 (fwd+losses+bwd+allreduce+Adam)', value=world * B / (ms_step / 1e3),
+               unit='images/s', ms_per_step=ms_step, steps=steps, per_gpu_batch=B, n_gpus=world,
+               dtype='bf16' if precision == 'bf16' else 'f32', stage='1 (layers 53-82 trainable)',
+               trainable_params=eng.n_train, buckets=len(tr.buckets),
+               gradient_bytes=int(eng.n_train) * 4, losses=[float(v) for v in losses],
+               gpu_launches_per_step=launches // max(1, steps))
+    if world > 1:
+        # the same bucketed step with the collectives left out: the difference is the all-reduce time that the
+        # overlap with the backward pass did NOT hide (ranks diverge from here on; this engine is discarded)
+        tr.skip_allreduce = True
+        ms_nocomm, _ = timed(max(3, steps // 2))
+        tr.skip_allreduce = False
+        res['allreduce_exposed_ms'] = max(0.0, ms_step - ms_nocomm)
+        res['ms_per_step_without_allreduce'] = ms_nocomm
+    if e2e_steps:
+        # end to end: the reference's feed_dict protocol -- host numpy images / labels / masks uploaded every step
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            tr.step(img_h, labels_h, tb_h, tm_h, pp_h, pg_h, THRESH, 1e-4)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d = img_h.nbytes + sum(l.nbytes for l in labels_h) + tb_h.nbytes + tm_h.nbytes + pp_h.nbytes + pg_h.nbytes
+        res['e2e'] = dict(value=world * B * e2e_steps / e2e_s, unit='images/s', h2d_bytes_per_step=int(h2d),
+                          d2h_bytes_per_step=32, steps=e2e_steps,
+                          mode='host numpy feed_dict every step (pageable), losses read back')
+    eng.close()
+    del tr, eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def stress_leg(local, peaks, B=4, size=1152, max_det=1000, thresh=0.05):
+    """BASELINE configs[4]: 1152 x 1152 inputs, low score threshold, >= 1,000 boxes per image through NMS and
+    position-sensitive mask assembly.  The network pass is timed on synthetic images; decode / NMS / top-k / masks on
+    synthetic head maps whose boxes are small enough that >= 1,000 survive NMS (random-init head maps overlap too
+    much for that), the 576 x 576 x 9 score maps being the network's own."""
+    import numpy as np
+    import torch
+    import disyolo_b200 as dy
+    eng = dy.Engine(image_size=size, max_batch=B, precision='bf16', device=local, max_detection=max_det)
+    eng.load_weights(dy.init_weights('lively', 0))
+    rng = np.random.default_rng(26)
+    img = torch.from_numpy(rng.random((B, size, size, 3), dtype=np.float32)).cuda()
+    win = torch.tensor([[0, 0, 1, 1]], dtype=torch.float32).repeat(B, 1).cuda()
+    for _ in range(2):
+        eng.forward_network(img)
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        losses = tr.step(img, labels, tb, tm, pp, pg, THRESH, 1e-4)
+    for _ in range(5):
+        eng.forward_network(img)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = int(eng.lib.dy_launch_count(0))
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # end to end: the reference's feed_dict protocol -- host numpy images / labels / masks uploaded every step
-    img_host = img.cpu().numpy()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(2, min(steps, 5))
-    for _ in range(n_e2e):
-        tr.step(img_host, host[0], host[1], host[2], host[3], host[4], THRESH, 1e-4)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d = img_host.nbytes + sum(l.nbytes for l in host[0]) + host[1].nbytes + host[2].nbytes + host[3].nbytes + host[4].nbytes
+    net_ms = e0.elapsed_time(e1) / 5
+    heads = []
+    for s in (8, 16, 32):
+        g = size // s
+        y = rng.standard_normal((B, g, g, 3, 8)).astype(np.float32)
+        y[..., 2:4] = y[..., 2:4] * 0.5 - 1.5          # small boxes: many survive the IoU > 0.3 suppression
+        y[..., 4] = y[..., 4] * 1.5                     # dense objectness
+        y[..., 5:] *= 2.0
+        heads.append(torch.from_numpy(y).cuda())
+    mp = eng.mask_pos(B).permute(0, 3, 1, 2).contiguous()          # planar [B,9,S,S], the engine's own layout
+    sm = eng.mask_size
+    masks = torch.empty((B, max_det, sm, sm), dtype=torch.float32, device='cuda')
+    raw, box, cnt = eng.detect(heads, win, thresh)
+    pp = eng.postproc_profile(heads, mp, win, thresh, masks, layout='planar', reps=5)
+    dets = cnt.cpu().numpy()
+    mask_bytes = int(dets.sum()) * sm * sm * 4
+    res = dict(workload='stress: %dx%d, batch %d, det_thresh %.2f, max_detection %d' % (size, size, B, thresh, max_det),
+               detections_per_image=[int(v) for v in dets], min_detections=int(dets.min()),
+               candidates_per_image=eng.num_candidates,
+               network_ms=net_ms, network_images_per_s=B / (net_ms / 1e3),
+               decode_ms=pp['decode'], nms_ms=pp['nms'], finalize_ms=pp['finalize'], masks_ms=pp['masks'],
+               mask_bytes=mask_bytes, mask_gbs=mask_bytes / (pp['masks'] / 1e3) / 1e9,
+               mask_frac_of_hbm=mask_bytes / (pp['masks'] / 1e3) / 1e9 / peaks['hbm_gbs'],
+               decode_bytes=B * eng.num_candidates * 32,
+               decode_frac_of_hbm=B * eng.num_candidates * 32 / (pp['decode'] / 1e3) / 1e9 / peaks['hbm_gbs'])
+    eng.close()
+    del masks, eng
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_train(args):
+    """`--workload train`: the training leg alone, printed as its own JSON line."""
+    import torch
+    rank, local, world = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        dist = None
+    B = args.batch if args.batch != PER_GPU_BATCH else 16
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    res = train_leg(B, args.train_precision, steps, warm, rank, local, world, dist, e2e_steps=max(2, min(steps, 5)))
     if rank == 0:
-        print(json.dumps(dict(metric='training images/s @576^2 (fwd+losses+bwd+allreduce+Adam)',
-                              value=world * B * steps / (ms / 1e3), unit='images/s', n_gpus=world, steps=steps,
-                              warmup=warm, ms_per_step=ms / steps, higher_is_better=True, scaling='weak',
-                              vs_baseline=None, dtype='bf16' if args.train_precision == 'bf16' else 'f32',
-                              data='synthetic',
+        e2e = res.pop('e2e')
+        print(json.dumps(dict(metric=res.pop('metric'), value=res.pop('value'), unit='images/s', n_gpus=world,
+                              steps=steps, warmup=warm, ms_per_step=res.pop('ms_per_step'), higher_is_better=True,
+                              scaling='weak', vs_baseline=None, dtype=res['dtype'], data='synthetic',
                               config=dict(workload='DIS-YOLO training step, batch %d/GPU at 576x576, stage 1 '
                                                    '(layers 53-82 trainable), data parallel' % B,
-                                          trainable_params=eng.n_train, buckets=len(tr.buckets)),
-                              e2e=dict(value=world * B * n_e2e / e2e_s, unit='images/s', h2d_bytes_per_step=int(h2d),
-                                       d2h_bytes_per_step=32, steps=n_e2e,
-                                       mode='host numpy feed_dict every step (pageable), losses read back'),
-                              losses=[float(v) for v in losses], gpu_launches=launches)))
+                                          trainable_params=res['trainable_params'], buckets=res['buckets']),
+                              e2e=e2e, losses=res['losses'], gpu_launches=res['gpu_launches_per_step'] * steps,
+                              train=res)))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -557,9 +691,12 @@ def main():
     ap.add_argument('--workload', default='inference', choices=['inference', 'train'])
     ap.add_argument('--train-precision', default='bf16', choices=['bf16', 'fp32'],
                     help='training engine: bf16 = tcgen05 dgrad/wgrad (mixed precision), fp32 = verification engine')
-    ap.add_argument('--traffic', type=float, default=25.9e9,
-                    help='DRAM bytes per step of the conv kernel (sum over its 81 launches) from the committed ncu '
-                         'launch list profiles/r1_launches.csv')
+    ap.add_argument('--traffic', type=float, default=None,
+                    help='DRAM bytes per step of the conv kernel (sum over its launches) from an ncu launch list of '
+                         'THIS build (profiles/); omitted -> roofline.traffic is null (never a stale constant)')
+    ap.add_argument('--no-numa', action='store_true', help='do not bind the process to the GPU NUMA node')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step leg (BASELINE configs[3])')
+    ap.add_argument('--no-stress', action='store_true', help='skip the 1152^2 stress leg (BASELINE configs[4])')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -7,10 +7,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdisyolo_b200.so')
+# DISYOLO_LIB: A/B aid (scripts/): load an alternative build of the same C ABI
+LIB_PATH = os.environ.get('DISYOLO_LIB') or os.path.join(_HERE, 'libdisyolo_b200.so')
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
+MASKS_NONE, MASKS_FULL, MASKS_CROPPED = 0, 1, 2      # enum dy_mask_mode
 
 
 class DyConfig(C.Structure):
@@ -49,6 +51,8 @@ SIGNATURES = {
     'dy_forward_host': (C.c_int, [_P, _P, _I, _P, _F, _P, _P, _P, _P]),
     'dy_forward_host_begin': (C.c_int, [_P, _P, _I, _P, _F, _I, C.POINTER(_I)]),
     'dy_forward_host_end': (C.c_int, [_P, _I, _P, _P, _P, _P]),
+    'dy_forward_host_begin_u8': (C.c_int, [_P, _P, _I, _P, _F, _I, C.POINTER(_I)]),
+    'dy_forward_host_end_cropped': (C.c_int, [_P, _I, _P, _P, _P, _P, _P, C.c_int64]),
     'dy_forward_network': (C.c_int, [_P, _P, _I, _P]),
     'dy_forward_profile': (C.c_int, [_P, _P, _I, _P, _P]),
     'dy_layer_shape': (C.c_int, [_P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
@@ -67,6 +71,7 @@ SIGNATURES = {
     'dy_conv_layer': (C.c_int, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P]),
     'dy_conv_backward': (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P]),
     'dy_train_init': (C.c_int, [_P]),
+    'dy_set_loss_params': (C.c_int, [_P, _F, _F, _F, _F, _F, _F]),
     'dy_train_param_count': (C.c_int64, [_P]),
     'dy_train_layer_span': (C.c_int, [_P, _I, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     'dy_train_forward': (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P]),

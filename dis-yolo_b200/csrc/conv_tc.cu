@@ -85,12 +85,16 @@ __device__ __forceinline__ void write_out16(const ConvParams& p, const OutDesc& 
 
 constexpr int kNumThreads = 384;     // 12 warps: producer, MMA, TMEM-alloc, spare, 2 x 4 epilogue warps
 
-// folded BN scale/shift (+ leaky) on one 16-column accumulator chunk
+// folded BN scale/shift (+ leaky) on one 16-column accumulator chunk.  Packed fp32x2 arithmetic
+// (FFMA2 / FMUL2, sm_100): each lane of a pair is an ordinary IEEE round-to-nearest fma / mul, so the
+// results are bit-identical to the scalar form at half the issue slots -- the epilogue warps (2 per SM
+// sub-partition) are issue/latency bound on the thin layers.
 __device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r)[16], const float* s_scale,
                                          const float* s_shift, int c0, float (&v)[16]) {
+#ifdef DY_SCALAR_EPILOGUE      // A/B build (scripts/build_variant.sh): the scalar form
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
-    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * j4);   // smem broadcast
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * j4);
     const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * j4);
     v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), sc.x, sh.x);
     v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), sc.y, sh.y);
@@ -100,6 +104,41 @@ __device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r
   if (p.act) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(p.alpha * v[j], v[j]);
+  }
+  return;
+#endif
+  const float2 al = make_float2(p.alpha, p.alpha);
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * j4);   // smem broadcast
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * j4);
+    float2 a = __ffma2_rn(make_float2(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1])),
+                          make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+    float2 b = __ffma2_rn(make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])),
+                          make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+    if (p.act) {
+      const float2 ta = __fmul2_rn(a, al), tb = __fmul2_rn(b, al);
+      a.x = fmaxf(ta.x, a.x); a.y = fmaxf(ta.y, a.y);
+      b.x = fmaxf(tb.x, b.x); b.y = fmaxf(tb.y, b.y);
+    }
+    v[4 * j4 + 0] = a.x; v[4 * j4 + 1] = a.y; v[4 * j4 + 2] = b.x; v[4 * j4 + 3] = b.y;
+  }
+}
+
+// v[0..15] += 16 bf16 residual values (two 16-byte vectors); bf16 -> fp32 is a 16-bit shift / mask
+__device__ __forceinline__ void add_res16(float (&v)[16], const uint4& ra, const uint4& rb) {
+  const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 f = make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xFFFF0000u));
+#ifdef DY_SCALAR_EPILOGUE
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+#else
+    const float2 o = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), f);
+    v[2 * j] = o.x;
+    v[2 * j + 1] = o.y;
+#endif
   }
 }
 
@@ -118,14 +157,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
   float v[16];
   bn_act16(p, r, s_scale, s_shift, c0, v);
   if (has_res) {
-    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-      const float2 f = __bfloat1622float2(h);
-      v[2 * j] += f.x;
-      v[2 * j + 1] += f.y;
-    }
+    add_res16(v, ra, rb);
   }
   write_out16(p, p.out[0], px, m, gcol, v);
   if (p.out[1].mode != OUT_NONE) write_out16(p, p.out[1], px, m, gcol, v);
@@ -140,14 +172,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
   uint4* q = reinterpret_cast<uint4*>(srow);
   if (has_res) {
     const uint4 ra = q[0], rb = q[1];
-    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-      const float2 f = __bfloat1622float2(h);
-      v[2 * j] += f.x;
-      v[2 * j + 1] += f.y;
-    }
+    add_res16(v, ra, rb);
   }
   uint4 a, b;
   a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
@@ -170,14 +195,7 @@ __device__ __forceinline__ void epilogue_chunk_swz(const ConvParams& p, const ui
   uint4* qb = reinterpret_cast<uint4*>(srow + (((ch0 + 1) ^ rsw) << 4));
   if (has_res) {
     const uint4 ra = *qa, rb = *qb;
-    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-      const float2 f = __bfloat1622float2(h);
-      v[2 * j] += f.x;
-      v[2 * j + 1] += f.y;
-    }
+    add_res16(v, ra, rb);
   }
   uint4 a = make_uint4(0, 0, 0, 0), b = a;
   if (valid) {
@@ -224,7 +242,7 @@ __device__ __forceinline__ void store_vec(const ConvParams& p, const OutDesc& o,
   }
 }
 
-template <int KCHUNK>
+template <int KCHUNK, bool FUSE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
@@ -244,6 +262,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __shared__ __align__(16) float s_shift[2][256];
   __shared__ long long s_dst[2][2][kBlockM];                      // [warpgroup][output][row] element offset / -1
   __shared__ __align__(8) uint64_t res_full[2][2];                // [warpgroup][staging buffer] residual landed
+  __shared__ __align__(8) uint64_t fuse_bar[2][2];                // [warpgroup][accumulator] fused-tail MMA complete
+  __shared__ __align__(16) float s_fbias[16];
   __shared__ uint32_t tap_a16[kMaxSeg][3];                        // A start offset inside the stage, >>4
   __shared__ uint32_t tap_b16[kMaxSeg][3];                        // B start (absolute if resident, else in-stage), >>4
 
@@ -263,6 +283,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t epi_off = stages_off + (uint32_t)p.num_stages * stage_bytes;
   const int num_tiles = p.n_tiles_m * p.n_tiles_n;
   const bool has_res = p.residual != nullptr;
+  // fused tail: its weights [fuse_n x 64] bf16 (SWIZZLE_128B rows) sit behind the epilogue staging buffers
+  const uint32_t fuse_off = epi_off + 2u * 2u * (uint32_t)kBlockM * 64u * 2u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -282,6 +304,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     mbar_init(&bres_bar, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i >> 1][i & 1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&fuse_bar[i >> 1][i & 1], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -297,28 +320,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                      : (a_bytes + (uint32_t)t * b_bytes) >> 4;
     }
   }
+  if (FUSE && warp >= 4 && warp < 8) {
+    // fused-tail weights -> shared memory in the canonical K-major SWIZZLE_128B layout (row = output
+    // channel, 128 B = 64 input channels; 16-byte chunk c of row r lands at chunk c ^ (r & 7))
+    const int t = threadIdx.x - 128;
+    for (int i = t; i < p.fuse_n * 8; i += 128) {
+      const int r = i >> 3, c = i & 7;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.fuse_w + (size_t)r * 64) + c);
+      *reinterpret_cast<uint4*>(smem_gen + fuse_off + (size_t)r * 128 + ((c ^ (r & 7)) << 4)) = v;
+    }
+    if (t < 16) s_fbias[t] = t < p.fuse_n ? __ldg(p.fuse_bias + t) : 0.f;
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 0) {
-    // ================================ TMA producer ================================
+  if (warp == 0 || (warp == 2 && p.dual_issue && p.dual_producer)) {
+    // ================================ TMA producers ================================
+    // With dual issue the ring is split in two halves, one per MMA issuer (= per tile parity), so that
+    // every mbarrier still has exactly one producer and one consumer.  With dual_producer each half also
+    // has its OWN producer thread (warp 0: even tiles, warp 2: odd tiles): a producer waiting for a free
+    // slot of its ring never holds back the loads of the other ring.
     if (elect_one()) {
-      if (p.b_resident) {
+      const bool split = p.dual_issue && p.dual_producer;
+      const int my_ring = (warp == 2) ? 1 : 0;
+      if (my_ring == 0 && p.b_resident) {
         // this CTA only ever sees one N tile (grid is a multiple of n_tiles_n): park its weights
         const int n0c = (int)(blockIdx.x % p.n_tiles_n) * p.block_n;
         mbar_expect_tx(&bres_bar, bres_bytes);
         for (int kb = 0; kb < p.num_chunks; ++kb)
           tma_load_2d(smem_gen + (size_t)kb * b_bytes, &mapB, &bres_bar, kb * KCHUNK, n0c);
       }
-      // With dual issue the ring is split in two halves, one per MMA issuer (= per tile parity), so
-      // that every mbarrier still has exactly one producer and one consumer.
       const int ring_sz = p.dual_issue ? p.num_stages / 2 : p.num_stages;
+      const int it_step = split ? 2 : 1;
       int rstage[2] = {0, 0};
       uint32_t rphase[2] = {0u, 0u};
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int it = my_ring;
+      for (int tile = blockIdx.x + my_ring * gridDim.x; tile < num_tiles; tile += it_step * gridDim.x, it += it_step) {
         const int ring = p.dual_issue ? (it & 1) : 0;
         int stage = ring ? rstage[1] : rstage[0];
         uint32_t phase = ring ? rphase[1] : rphase[0];
@@ -421,7 +461,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     int cached_n0 = -1;
     uint32_t res_par = 0u;                              // bit b = parity of res_full[wg][b]; persists across tiles
     uint32_t sc = 0u;                                   // slabs processed by this warpgroup so far (buffer = sc & 1)
+    // fused tail, software pipelined: the 1x1 MMA of tile i is issued at the end of tile i and its result
+    // is read (and stored) while tile i+1 of this warpgroup is processed -- two 16-column accumulators
+    uint32_t f_cnt = 0u;                                // fused MMAs issued by this warpgroup
+    PixelInfo f_px = {0, 0, 0, false};                  // this thread's pixel of the pending fused tile
     bool res_primed = false;
+    auto fuse_drain = [&]() {                           // result of fused MMA number f_cnt-1 -> global memory
+      const uint32_t b = (f_cnt - 1u) & 1u;
+      uint32_t fr[16];
+      mbar_wait(&fuse_bar[wg][b], ((f_cnt - 1u) >> 1) & 1u);
+      tc_fence_after();
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.num_acc * p.block_n + (wg * 2 + (int)b) * 16), fr);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (f_px.valid) {
+        float* d = p.fuse_out + (((long long)f_px.n * p.fuse_cout) * p.H + f_px.y) * p.W + f_px.x;
+        const long long plane = (long long)p.H * p.W;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < p.fuse_cout) __stcs(d + j * plane, __uint_as_float(fr[j]) + s_fbias[j]);
+      }
+    };
     int it = wg;
     for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
       const int acc = it & (p.num_acc - 1);             // this warpgroup owns the accumulators of its tile parity
@@ -540,14 +600,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                                    (c0 + 16) >> 3, rsw);
             }
           }
-          if (p.debug_skip == 0 || p.debug_skip >= 4) {
-            fence_proxy_async_smem();                        // generic-proxy smem writes -> async proxy (TMA)
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+          if (sidx + 1 == nslab) {
+            // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA issuer
+            // now, before the store phases
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
           }
+          fence_proxy_async_smem();                          // generic-proxy smem writes -> async proxy (TMA)
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           if (elected) {
-            if (p.debug_skip == 0) {
+            if (p.debug_skip == 0 && (!FUSE || p.fuse_store)) {
               tma_store_2d(&mapO, stg, n0 + slab0, m0);
               bulk_commit();
+            }
+            if constexpr (FUSE) {
+              // the finished bf16 tile [128 x 64] is a K-major SWIZZLE_128B A operand as it stands
+              tc_fence_after();
+              const uint64_t dhi = (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+              const uint64_t fa = dhi | (uint64_t)((smem_u32(stg) & 0x3FFFFu) >> 4);
+              const uint64_t fb = dhi | (uint64_t)(((smem_base + fuse_off) & 0x3FFFFu) >> 4);
+              const uint32_t fd = tmem_base + (uint32_t)(p.num_acc * p.block_n + (wg * 2 + (int)(f_cnt & 1u)) * 16);
+              const uint32_t fidesc = umma_idesc_bf16(p.fuse_n);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(fd, fa + (uint64_t)(2 * k), fb + (uint64_t)(2 * k), fidesc, k ? 1u : 0u);
+              umma_commit(&fuse_bar[wg][f_cnt & 1u]);
             }
             if (has_res) {
               // request the residual of the NEXT slab (this tile's, or the first one of this
@@ -568,6 +645,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 tma_load_2d(stg0 + (size_t)(bsel ^ 1) * buf_bytes, &mapR, &res_full[wg][bsel ^ 1], nn0, nm0);
               }
             }
+          }
+          if constexpr (FUSE) {
+            if (f_cnt > 0u) fuse_drain();                    // the PREVIOUS tile's 1x1 result (long complete)
+            f_px = px;
+            ++f_cnt;
           }
           if (dual) {
             // second destination form (space-to-depth / upsampled): cooperative vector stores
@@ -653,9 +735,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (!(p.tma_epi && p.slab != 0 && p.debug_skip != 1)) {   // (the TMA path released it after its last tcgen05.ld)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+    }
+    if constexpr (FUSE) {
+      if (f_cnt > 0u) fuse_drain();
     }
     if (p.tma_epi && wg_tid == 0) bulk_wait_all<0>();      // stores complete before the CTA retires
   }
@@ -727,7 +814,8 @@ static size_t resident_bytes_of(int kchunk, const ConvParams& p) {
 
 static size_t epilogue_bytes_of(const ConvParams& p) {
   if (!p.slab) return 0;
-  if (p.tma_epi) return 2 * 2 * (size_t)kBlockM * p.slab * 2;          // 2 warpgroups x 2 swizzled buffers
+  if (p.tma_epi)                                                        // 2 warpgroups x 2 swizzled buffers
+    return 2 * 2 * (size_t)kBlockM * p.slab * 2 + (p.fuse_n ? (size_t)p.fuse_n * 128 : 0);   // (+ fused-tail weights)
   return 2 * (size_t)kBlockM * ((size_t)p.slab * 2 + 16);
 }
 
@@ -774,7 +862,11 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
   DY_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n");
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
   DY_CHECK(p.num_acc == 2 || p.num_acc == 4, "num_acc");
-  DY_CHECK(p.tmem_cols >= p.num_acc * p.block_n && p.tmem_cols <= 512, "tmem_cols");
+  DY_CHECK(p.tmem_cols >= p.num_acc * p.block_n + (p.fuse_n ? 64 : 0) && p.tmem_cols <= 512, "tmem_cols");
+  DY_CHECK(!p.fuse_n || (p.fuse_n == 16 && p.tma_epi && p.slab == 64 && p.block_n == 64 && p.cout == 64 &&
+                         p.n_tiles_n == 1 && p.residual == nullptr && p.out[1].mode == OUT_NONE &&
+                         p.fuse_cout >= 1 && p.fuse_cout <= 16 && p.fuse_w && p.fuse_bias && p.fuse_out),
+           "fused tail needs the TMA staged epilogue of a 64-channel layer");
   DY_CHECK(p.a_rows == kBlockM || p.a_rows == kHaloRows, "a_rows");
   DY_CHECK(p.max_ntap >= 1 && p.max_ntap <= 3, "max_ntap");
   DY_CHECK(p.slab == 0 || ((p.slab == 32 || p.slab == 64) && p.block_n % p.slab == 0), "slab");
@@ -787,20 +879,28 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
     grid = grid / p.n_tiles_n * p.n_tiles_n;
     DY_CHECK(grid >= p.n_tiles_n, "grid too small for resident weights");
   }
-  if (kchunk == 64) {
+  DY_CHECK(!p.fuse_n || kchunk == 32, "the fused tail is instantiated for 32-wide K chunks (convolutional81)");
+  if (p.fuse_n) {
+    static bool attr32f = false;
+    if (!attr32f) {
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      attr32f = true;
+    }
+    conv_tc_kernel<32, true><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
+  } else if (kchunk == 64) {
     static bool attr64 = false;
     if (!attr64) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr64 = true;
     }
-    conv_tc_kernel<64><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
+    conv_tc_kernel<64, false><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
   } else {
     static bool attr32 = false;
     if (!attr32) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32 = true;
     }
-    conv_tc_kernel<32><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
+    conv_tc_kernel<32, false><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
   }
   DY_CUDA(cudaGetLastError());
   return DY_OK;

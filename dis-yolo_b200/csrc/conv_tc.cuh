@@ -18,7 +18,7 @@ namespace dy {
 
 constexpr int kBlockM = 128;
 constexpr int kMaxSeg = 9;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
 enum OutMode : int {
   OUT_NONE = 0,
@@ -66,6 +66,7 @@ struct ConvParams {
   int tile_stages; // pipeline stages consumed per tile = sum of seg[].nchunk
   int num_acc;     // TMEM accumulator stages: 2, or 4 (two per MMA issuer) for thin dual-issue tiles
   int dual_issue;  // 1: two MMA-issuer threads, each with its own half of the stage ring (thin layers)
+  int dual_producer;  // with dual_issue: 1 = one TMA producer thread per half ring, 0 = one thread feeds both in tile order
   int a_rows;      // rows per A box: 128, or kHaloRows when taps share a halo'd box
   int max_ntap;    // max seg[].ntap (sizes the per-stage weight slots when weights are streamed)
   int b_resident;  // 1: the CTA's whole [block_n x K] weight slab is loaded to smem once
@@ -81,6 +82,16 @@ struct ConvParams {
   const __nv_bfloat16* residual;    // P1, same geometry, added AFTER the activation (:148-151)
   int res_ld;
   OutDesc out[2];
+  // Fused tail: a biased linear 1x1 conv (convolutional82, 64 -> 9, yolo3_net_pos.py:410-412) evaluated on
+  // this layer's bf16 output tile while it still sits in the swizzled staging buffer: a second
+  // tcgen05.mma (M=128, N=fuse_n, K=64) issued by the epilogue warpgroup itself.  Needs the TMA staged
+  // epilogue with block_n == cout == slab == 64 and no residual.
+  int fuse_n;                       // 0 = off, else the fused conv's padded N (16)
+  int fuse_cout;                    // its real output channels
+  int fuse_store;                   // 1: out[0] is still stored (parity taps / training), 0: never materialised
+  const __nv_bfloat16* fuse_w;      // [fuse_n][64] bf16 K-major (= the fused layer's packed forward weights)
+  const float* fuse_bias;           // [fuse_n]
+  float* fuse_out;                  // fp32 planar [N, fuse_cout, H, W]
 };
 
 // Build a 2D bf16 tensor map over a row-major [rows, cols] matrix with a (box_cols x box_rows) box.

@@ -289,6 +289,32 @@ __global__ void assign_labels_kernel(LabelArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// uint8 RGB -> the network's fp32 input: v / 255 exactly as image_read forms it (float64 division of
+// the 0..255 value, then the float32 cast of the feed; calculate_test_map.py:175).  Only 256 inputs
+// exist, so the quotients are formed once in double (g_u8_lut) and looked up from shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ float g_u8_lut[256];
+
+__global__ void u8_lut_init_kernel() { g_u8_lut[threadIdx.x] = (float)((double)threadIdx.x / 255.0); }
+
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint4* __restrict__ src, float4* __restrict__ dst,
+                                                        long long n16, const unsigned char* __restrict__ tail_src,
+                                                        float* __restrict__ tail_dst, int ntail) {
+  __shared__ float lut[256];
+  lut[threadIdx.x] = g_u8_lut[threadIdx.x];
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(src + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      __stcs(dst + 4 * i + j, make_float4(lut[w[j] & 0xFF], lut[(w[j] >> 8) & 0xFF], lut[(w[j] >> 16) & 0xFF],
+                                          lut[w[j] >> 24]));
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail_dst[threadIdx.x] = lut[tail_src[threadIdx.x]];
+}
+
 }  // namespace
 
 int launch_assign_labels(const LabelArgs& a, cudaStream_t st) {
@@ -337,6 +363,29 @@ LetterboxGeom letterbox_geom(int src_h, int src_w, int size) {
   g.top = (size - h) / 2;
   g.left = (size - w) / 2;
   return g;
+}
+
+int launch_u8_to_f32(const unsigned char* src, float* dst, long long n, cudaStream_t st) {
+  DY_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "alignment");
+  static bool lut_ready[64] = {false};
+  int dev = 0;
+  DY_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !lut_ready[dev]) {
+    u8_lut_init_kernel<<<1, 256, 0, st>>>();
+    DY_CUDA(cudaGetLastError());
+    lut_ready[dev] = true;
+  } else if (dev >= 64) {
+    u8_lut_init_kernel<<<1, 256, 0, st>>>();
+  }
+  const long long n16 = n / 16;
+  const int ntail = (int)(n - n16 * 16);
+  long long blocks = (n16 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  u8_to_f32_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<float4*>(dst),
+                                               n16, src + n16 * 16, dst + n16 * 16, ntail);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
 }
 
 int launch_letterbox(const unsigned char* rgb, const LetterboxGeom& g, float* out, cudaStream_t st) {

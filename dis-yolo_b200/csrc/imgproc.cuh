@@ -18,6 +18,9 @@ struct LetterboxGeom {
 };
 LetterboxGeom letterbox_geom(int src_h, int src_w, int size);
 
+// n uint8 values -> fp32 v/255 (the float64 quotient rounded to float, like image_read's `/ 255.`)
+int launch_u8_to_f32(const unsigned char* src, float* dst, long long n, cudaStream_t st);
+
 // rgb [src_h, src_w, 3] uint8 (device) -> out [size, size, 3] fp32 (device), one image
 int launch_letterbox(const unsigned char* rgb, const LetterboxGeom& g, float* out, cudaStream_t st);
 

@@ -128,6 +128,11 @@ struct TcConvDesc {
   float alpha = 0.1f;
   const __nv_bfloat16* residual = nullptr;
   OutDesc out[2];
+  // fused 1x1 linear tail (ConvParams::fuse_*)
+  int fuse_n = 0, fuse_cout = 0, fuse_store = 0;
+  const __nv_bfloat16* fuse_w = nullptr;
+  const float* fuse_bias = nullptr;
+  float* fuse_out = nullptr;
 };
 
 // tuning overrides (dy_set_option): -1 = automatic
@@ -138,6 +143,9 @@ static int g_opt_tma_epi = -1;      // 0: cooperative staged epilogue, 1: TMA st
 static int g_opt_dual = -1;         // 0: one MMA issuer, 1: two issuers whenever the ring has >= 4 stages
 static int g_opt_skip_epi = 0;      // measurement only: conv epilogues do nothing
 static int g_opt_conv1_tc = -1;     // 0: conv1 on CUDA cores, otherwise the tcgen05 im2col stem kernel
+static int g_opt_dual_producer = -1; // with dual issue: 0 one TMA producer thread for both half rings, 1 one per half ring
+static int g_opt_max_stages = -1;   // cap of the shared-memory pipeline depth (default kMaxStages)
+static int g_opt_fuse_tail = -1;    // 0: convolutional82 as its own launch, otherwise fused into convolutional81's epilogue
 static int g_wg_dbg[4] = {0, 0, 0, 0};   // bring-up aid: wgrad UMMA descriptor overrides (0 = computed)
 
 static int pick_block_n(int cout_pad, long long rows, int num_sms) {
@@ -297,7 +305,11 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   p.debug_skip = g_opt_skip_epi > 0 ? g_opt_skip_epi : 0;
   if (p.tma_epi && p.block_n % 64 == 0) p.slab = 64;
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
+  p.fuse_n = d.fuse_n;      // (sizes the epilogue staging area)
   p.num_stages = conv_tc_pick_stages(kchunk, p);
+  // deeper rings than 8 stages measured slower on every layer (profiles/r2_ab_opts.txt): default cap 8
+  const int stage_cap = g_opt_max_stages >= 2 ? g_opt_max_stages : 8;
+  if (p.num_stages > stage_cap) p.num_stages = stage_cap;
   DY_CHECK(p.num_stages >= 2, "no room for a shared-memory pipeline");
   // two MMA issuers for thin tiles (32/64-cycle MMAs: the issue thread, not the tensor pipe, is the
   // bottleneck); each issuer needs its own half ring with at least one tile's worth of stages in flight
@@ -306,11 +318,19 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (g_opt_dual == 1) dual_issue = p.num_stages >= 4;
   if (dual_issue) p.num_stages &= ~1;
   p.dual_issue = dual_issue ? 1 : 0;
+  p.dual_producer = (dual_issue && g_opt_dual_producer != 0) ? 1 : 0;
   // four TMEM accumulator stages (two per issuer) when they fit: otherwise each issuer would be
   // serialised with its own epilogue warpgroup
   p.num_acc = (dual_issue && 4 * p.block_n <= 512) ? 4 : 2;
+  if (d.fuse_n) {
+    DY_CHECK(p.tma_epi && p.slab == 64 && p.block_n == 64 && d.cout == 64 && !has_res && d.out[1].mode == OUT_NONE,
+             "fused tail: the producer must be a 64-channel layer on the TMA staged epilogue");
+    p.fuse_n = d.fuse_n; p.fuse_cout = d.fuse_cout; p.fuse_store = d.fuse_store;
+    p.fuse_w = d.fuse_w; p.fuse_bias = d.fuse_bias; p.fuse_out = d.fuse_out;
+  }
   tc = 32;
-  while (tc < p.num_acc * p.block_n) tc <<= 1;
+  while (tc < p.num_acc * p.block_n + (p.fuse_n ? 64 : 0)) tc <<= 1;
+  DY_CHECK(tc <= 512, "TMEM columns");
   p.tmem_cols = tc;
   const int a0_cols = (d.s == 2) ? 4 * d.cin0 : d.cin0;
   DY_TRY(make_tmap_2d(&plan->a0, d.a0, rows_max, a0_cols, a0_cols, kchunk, p.a_rows));
@@ -358,6 +378,8 @@ static void pack_weights_bf16(const float* w_hwio, int K, int cout, int cout_pad
 struct LayerState {
   LayerDef def;
   std::vector<float> w, gamma, beta, mean, var, bias;   // host copies as loaded
+  unsigned host_new = 0;     // bit v set: variable v (0 w, 1 gamma, 2 beta, 3 mean, 4 var, 5 bias) was loaded
+                             // by dy_load_weights since the last dy_finalize_weights
   int cout_pad = 0, K = 0;
   float* d_w_f32 = nullptr;
   __nv_bfloat16* d_wpk = nullptr;
@@ -370,6 +392,8 @@ struct LayerState {
   __nv_bfloat16* up = nullptr;
   float* f32 = nullptr;     // bf16 mode: heads (compact) / score maps (planar); fp32 mode: every layer, NHWC
   TcPlan plan;
+  TcPlan plan_fused;         // convolutional81 with convolutional82 evaluated in its epilogue (inference)
+  bool has_fused = false;
   bool planned = false;
   // ---- training state (fp32 engine) ----
   bool unlocked = false, in_bwd = false, need_in_grad = false;
@@ -420,17 +444,32 @@ struct dy_net {
   static constexpr int kHostSlots = 3;
   struct HostSlot {
     float* images = nullptr;
+    uint8_t* images_u8 = nullptr;    // dy_forward_host_begin_u8 staging
     float* windows = nullptr;
+    void* small = nullptr;           // [det_count | det_box | det_raw | crop offsets] in one block
+    uint8_t* small_host = nullptr;   // pinned mirror of `small`
     float* det_raw = nullptr;
     float* det_box = nullptr;
     int* det_count = nullptr;
-    float* masks = nullptr;
+    long long* crop_off = nullptr;
+    float* masks = nullptr;          // [B,max_det,S,S] maps, or the packed box crops
     cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr;
     int B = 0;
-    bool busy = false, want_masks = false;
+    bool busy = false;
+    int mask_mode = 0;
   } slot[kHostSlots];
   int next_slot = 0;
   cudaStream_t h2d_stream = nullptr, comp_stream = nullptr, d2h_stream = nullptr;
+  // The host-buffer pipeline runs the network on comp_stream, every other entry point on the caller's
+  // stream, and both use the same activation / weight buffers: ev_user is recorded after the last
+  // caller-stream work (comp_stream waits for it), ev_host after the last comp_stream work (caller
+  // streams wait for it).
+  cudaEvent_t ev_user = nullptr, ev_host = nullptr;
+  bool user_work = false, host_work = false;
+  // loss hyper-parameters (yolo/config.py:49-57), dy_set_loss_params
+  float object_scale = 2.f, noobject_scale = 1.f, class_scale = 1.f, coord_scale = 1.f, mask_scale = 5.f;
+  float ignore_thresh = 0.5f;
+  bool last_fused = false;         // the last forward skipped materialising convolutional81 (fused tail)
   // ---- training ----
   bool train_ready = false;
   long long n_train = 0;           // number of trainable scalars
@@ -466,6 +505,30 @@ static int dev_alloc(dy_net* net, void** p, size_t bytes, bool zero = true) {
 }
 
 static size_t p1_elems(int B, int H, int W, int C) { return (size_t)B * (H + 1) * (W + 1) * C; }
+
+static bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
+// Entry points that run on a caller stream bracket their work with these two: the caller stream first
+// waits for the host-buffer pipeline's last network pass (same activation buffers), and the pipeline's
+// compute stream will wait for what the caller enqueued (train-then-evaluate, train_yolo3_mask.py:146-176).
+static int user_begin(dy_net* net, cudaStream_t st) {
+  if (net->host_work && !stream_capturing(st)) DY_CUDA(cudaStreamWaitEvent(st, net->ev_host, 0));
+  return DY_OK;
+}
+static int user_end(dy_net* net, cudaStream_t st) {
+  if (stream_capturing(st)) return DY_OK;
+  if (!net->ev_user) DY_CUDA(cudaEventCreateWithFlags(&net->ev_user, cudaEventDisableTiming));
+  DY_CUDA(cudaEventRecord(net->ev_user, st));
+  net->user_work = true;
+  return DY_OK;
+}
 
 static int allocate_buffers(dy_net* net) {
   const int B = net->cfg.max_batch;
@@ -608,15 +671,37 @@ static int plan_layer(dy_net* net, int n) {
   DY_CHECK(no >= 1 && no <= 2, "layer has no consumer");
   DY_TRY(build_tc_plan(c, net->num_sms, &s.plan));
   s.planned = true;
+  // convolutional81 -> convolutional82 (64 -> k*k linear 1x1, :408-412): in inference nothing else reads
+  // convolutional81's output, so the 1x1 runs on the finished tile inside the epilogue and the 64-channel
+  // 288x288 activation is never written (dy_forward); dy_forward_network keeps the two launches.
+  s.has_fused = false;
+  if (n == 81 && g_opt_fuse_tail != 0 && s.plan.p.tma_epi && s.plan.p.slab == 64 && s.plan.p.block_n == 64 &&
+      d.cout == 64 && no == 1 && net->L[82].def.src0 == 81 && net->L[82].def.k == 1 && net->L[82].cout_pad == 16 &&
+      net->L[82].d_wpk != nullptr) {
+    c.fuse_n = 16;
+    c.fuse_cout = net->L[82].def.cout;
+    c.fuse_store = 0;
+    c.fuse_w = net->L[82].d_wpk;
+    c.fuse_bias = net->L[82].d_shift;
+    c.fuse_out = net->L[82].f32;
+    DY_TRY(build_tc_plan(c, net->num_sms, &s.plan_fused));
+    s.has_fused = true;
+  }
   return DY_OK;
 }
 
-static int run_network_bf16(dy_net* net, const float* images, int B, cudaStream_t st) {
+static int run_network_bf16(dy_net* net, const float* images, int B, cudaStream_t st, bool fused) {
   auto& L = net->L;
   note_launch();
   DY_TRY(launch_conv1(images, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S, L[1].s2d,
                       L[1].same, g_opt_conv1_tc != 0, net->num_sms, st));
-  for (int n = 2; n <= 82; ++n) DY_TRY(run_tc_plan(L[n].plan, B, net->num_sms, st));
+  fused = fused && L[81].has_fused;
+  for (int n = 2; n <= 82; ++n) {
+    if (fused && n == 81) DY_TRY(run_tc_plan(L[81].plan_fused, B, net->num_sms, st));
+    else if (fused && n == 82) continue;
+    else DY_TRY(run_tc_plan(L[n].plan, B, net->num_sms, st));
+  }
+  net->last_fused = fused;
   return DY_OK;
 }
 
@@ -650,10 +735,11 @@ static int run_network_fp32(dy_net* net, const float* images, int B, cudaStream_
   return DY_OK;
 }
 
-static int run_network(dy_net* net, const float* images, int B, cudaStream_t st) {
+static int run_network(dy_net* net, const float* images, int B, cudaStream_t st, bool fused) {
   DY_CHECK(net->finalized, "dy_finalize_weights has not been called");
   DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
-  if (net->cfg.precision == DY_PRECISION_BF16) return run_network_bf16(net, images, B, st);
+  if (net->cfg.precision == DY_PRECISION_BF16) return run_network_bf16(net, images, B, st, fused);
+  net->last_fused = false;
   return run_network_fp32(net, images, B, st);
 }
 
@@ -698,8 +784,7 @@ static int run_detect(dy_net* net, const float* y8, const float* y16, const floa
   return DY_OK;
 }
 
-static int run_masks(dy_net* net, const float* score, int layout, int B, const int* det_count, float* masks,
-                     cudaStream_t st) {
+static MaskArgs mask_args(dy_net* net, const float* score, int layout, int B, const int* det_count, float* masks) {
   MaskArgs ma;
   const int Sm = net->S / 2, kk = net->cfg.k_map * net->cfg.k_map;
   ma.score = score;
@@ -711,6 +796,12 @@ static int run_masks(dy_net* net, const float* score, int layout, int B, const i
   ma.det_count = det_count; ma.edges = net->edges;
   ma.B = B; ma.max_det = net->cfg.max_detection; ma.S = Sm; ma.k = net->cfg.k_map;
   ma.out = masks;
+  return ma;
+}
+
+static int run_masks(dy_net* net, const float* score, int layout, int B, const int* det_count, float* masks,
+                     cudaStream_t st) {
+  const MaskArgs ma = mask_args(net, score, layout, B, det_count, masks);
   note_launch();
   return launch_masks(ma, st);
 }
@@ -792,6 +883,11 @@ __global__ void edges_from_boxes_kernel(const float* det_box, const int* det_cou
 }
 }  // namespace dy
 
+namespace dy {
+static int sync_masters(dy_net* net, bool* any_new);
+static int retrain_refresh(dy_net* net, bool any_new);
+}  // namespace dy
+
 // =============================================================================================
 // C ABI
 // =============================================================================================
@@ -817,6 +913,9 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_staged") g_opt_staged = value;
   else if (n == "tc_tma_epi") g_opt_tma_epi = value;
   else if (n == "conv1_tc") g_opt_conv1_tc = value;
+  else if (n == "tc_fuse_tail") g_opt_fuse_tail = value;
+  else if (n == "tc_dual_producer") g_opt_dual_producer = value;
+  else if (n == "tc_max_stages") g_opt_max_stages = value;
   else if (n == "tc_skip_epilogue") g_opt_skip_epi = value;
   else if (n == "tc_dual_issue") g_opt_dual = value;
   else if (n == "mask_streaming_stores") masks_set_streaming(value);
@@ -885,7 +984,10 @@ int dy_destroy(dy_net* net) {
   for (auto& sl : net->slot) {
     if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
     if (sl.ev_comp) cudaEventDestroy(sl.ev_comp);
+    if (sl.small_host) cudaFreeHost(sl.small_host);
   }
+  if (net->ev_user) cudaEventDestroy(net->ev_user);
+  if (net->ev_host) cudaEventDestroy(net->ev_host);
   delete net;
   return DY_OK;
 }
@@ -911,23 +1013,25 @@ int dy_load_weights(dy_net* net, const char* tf_name, const float* host, const i
   size_t count = 1;
   for (int i = 0; i < ndim; ++i) count *= (size_t)shape[i];
   std::vector<float>* dst = nullptr;
+  unsigned bit = 0;
   if (what == "weights") {
     DY_CHECK(ndim == 4 && shape[0] == d.k && shape[1] == d.k && shape[2] == d.cin0 + d.cin1 && shape[3] == d.cout,
              "weights must be HWIO [k,k,cin,cout]");
-    dst = &s.w;
+    dst = &s.w; bit = 1u << 0;
   } else {
     DY_CHECK(ndim == 1 && shape[0] == d.cout, "per-channel variable must be [cout]");
-    if (what == "biases") dst = &s.bias;
-    else if (what == "BatchNorm/gamma") dst = &s.gamma;
-    else if (what == "BatchNorm/beta") dst = &s.beta;
-    else if (what == "BatchNorm/moving_mean") dst = &s.mean;
-    else if (what == "BatchNorm/moving_variance") dst = &s.var;
+    if (what == "biases") { dst = &s.bias; bit = 1u << 5; }
+    else if (what == "BatchNorm/gamma") { dst = &s.gamma; bit = 1u << 1; }
+    else if (what == "BatchNorm/beta") { dst = &s.beta; bit = 1u << 2; }
+    else if (what == "BatchNorm/moving_mean") { dst = &s.mean; bit = 1u << 3; }
+    else if (what == "BatchNorm/moving_variance") { dst = &s.var; bit = 1u << 4; }
   }
   if (!dst) {
     set_error("unknown variable " + name);
     return DY_ERR_NOTFOUND;
   }
   dst->assign(host, host + count);
+  s.host_new |= bit;
   net->finalized = false;
   return DY_OK;
 }
@@ -935,11 +1039,27 @@ int dy_load_weights(dy_net* net, const char* tf_name, const float* host, const i
 int dy_finalize_weights(dy_net* net) {
   DY_CHECK(net, "null net");
   DY_CUDA(cudaSetDevice(net->cfg.device));
+  DY_CUDA(cudaDeviceSynchronize());                  // nothing in flight may still read the old operands
+  // Once dy_train_init has run the truth lives in the device master copies: variables loaded since the
+  // last finalize (Saver.restore, train_yolo3_mask.py:104-111) overwrite their masters, every other
+  // variable's host copy is refreshed FROM its master, so that the fold below never reverts training.
+  bool any_new = false;
+  if (net->train_ready) DY_TRY(sync_masters(net, &any_new));
   for (int n = 1; n <= 82; ++n) DY_TRY(fold_and_upload(net, n));
   if (net->cfg.precision == DY_PRECISION_BF16)
     for (int n = 2; n <= 82; ++n) DY_TRY(plan_layer(net, n));
+  if (net->train_ready) DY_TRY(retrain_refresh(net, any_new));
+  for (int n = 1; n <= 82; ++n) net->L[n].host_new = 0;
   DY_CUDA(cudaDeviceSynchronize());
   net->finalized = true;
+  return DY_OK;
+}
+
+int dy_set_loss_params(dy_net* net, float object_scale, float noobject_scale, float class_scale, float coord_scale,
+                       float mask_scale, float ignore_thresh) {
+  DY_CHECK(net, "null net");
+  net->object_scale = object_scale; net->noobject_scale = noobject_scale; net->class_scale = class_scale;
+  net->coord_scale = coord_scale; net->mask_scale = mask_scale; net->ignore_thresh = ignore_thresh;
   return DY_OK;
 }
 
@@ -949,6 +1069,7 @@ int dy_forward_profile(dy_net* net, const float* images_dev, int32_t B, float* l
   DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
   DY_CHECK(net->cfg.precision == DY_PRECISION_BF16, "per-layer profile is for the bf16 engine");
   cudaStream_t st = (cudaStream_t)stream;
+  DY_TRY(user_begin(net, st));
   std::vector<cudaEvent_t> ev(83);
   for (auto& e : ev) DY_CUDA(cudaEventCreate(&e));
   auto& L = net->L;
@@ -958,10 +1079,14 @@ int dy_forward_profile(dy_net* net, const float* images_dev, int32_t B, float* l
   rc = launch_conv1(images_dev, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S,
                     L[1].s2d, L[1].same, g_opt_conv1_tc != 0, net->num_sms, st);
   cudaEventRecord(ev[1], st);
+  // the launches dy_forward issues: with the fused tail convolutional82 has no launch of its own (0 ms)
+  const bool fused = L[81].has_fused;
   for (int n = 2; n <= 82 && rc == DY_OK; ++n) {
-    rc = run_tc_plan(L[n].plan, B, net->num_sms, st);
+    if (fused && n == 81) rc = run_tc_plan(L[81].plan_fused, B, net->num_sms, st);
+    else if (!(fused && n == 82)) rc = run_tc_plan(L[n].plan, B, net->num_sms, st);
     cudaEventRecord(ev[n], st);
   }
+  net->last_fused = fused;
   if (rc == DY_OK && cudaStreamSynchronize(st) != cudaSuccess) {
     set_error("stream synchronize failed in dy_forward_profile");
     rc = DY_ERR_CUDA;
@@ -971,12 +1096,16 @@ int dy_forward_profile(dy_net* net, const float* images_dev, int32_t B, float* l
     for (int n = 1; n <= 82; ++n) cudaEventElapsedTime(&layer_ms_host[n], ev[n - 1], ev[n]);
   }
   for (auto& e : ev) cudaEventDestroy(e);
+  if (rc == DY_OK) rc = user_end(net, st);
   return rc;
 }
 
 int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream) {
   DY_CHECK(net && images_dev, "null argument");
-  return run_network(net, images_dev, B, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  DY_TRY(user_begin(net, st));
+  DY_TRY(run_network(net, images_dev, B, st, /*fused=*/false));     // parity taps: every layer materialised
+  return user_end(net, st);
 }
 
 static void head_ptrs(dy_net* net, const float** y8, const float** y16, const float** y32, const float** mp,
@@ -988,11 +1117,11 @@ static void head_ptrs(dy_net* net, const float** y8, const float** y16, const fl
   *layout = net->cfg.precision == DY_PRECISION_BF16 ? 1 : 0;
 }
 
-int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* windows_dev, float det_thresh,
-               float* det_raw_dev, float* det_box_dev, int32_t* det_count_dev, float* masks_dev, void* stream) {
-  DY_CHECK(net && images_dev && windows_dev, "null argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  DY_TRY(run_network(net, images_dev, B, st));
+// network + decode + NMS + top-k (+ masks) on `st`; crop_* non-null selects the box-cropped mask form
+static int forward_impl(dy_net* net, const float* images_dev, int32_t B, const float* windows_dev, float det_thresh,
+                        float* det_raw_dev, float* det_box_dev, int32_t* det_count_dev, float* masks_dev,
+                        long long* crop_off_dev, float* crops_dev, cudaStream_t st) {
+  DY_TRY(run_network(net, images_dev, B, st, /*fused=*/true));
   const float *y8, *y16, *y32, *mp;
   int layout;
   head_ptrs(net, &y8, &y16, &y32, &mp, &layout);
@@ -1001,50 +1130,134 @@ int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* win
   DY_TRY(run_detect(net, y8, y16, y32, B, windows_dev, det_thresh, nullptr, nullptr, nullptr, det_raw_dev, box, cnt,
                     st));
   if (masks_dev) DY_TRY(run_masks(net, mp, layout, B, cnt, masks_dev, st));
+  if (crops_dev) {
+    MaskArgs ma = mask_args(net, mp, layout, B, cnt, nullptr);
+    note_launch(2);
+    DY_TRY(launch_crop_offsets(ma, crop_off_dev, st));
+    DY_TRY(launch_masks_cropped(ma, crop_off_dev, crops_dev, st));
+  }
   return DY_OK;
+}
+
+int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* windows_dev, float det_thresh,
+               float* det_raw_dev, float* det_box_dev, int32_t* det_count_dev, float* masks_dev, void* stream) {
+  DY_CHECK(net && images_dev && windows_dev, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DY_TRY(user_begin(net, st));
+  DY_TRY(forward_impl(net, images_dev, B, windows_dev, det_thresh, det_raw_dev, det_box_dev, det_count_dev, masks_dev,
+                      nullptr, nullptr, st));
+  return user_end(net, st);
+}
+
+// small results of one slot, contiguous so that they leave in ONE device -> host copy:
+// [det_count B*4 | det_box B*md*24 | det_raw B*md*24 | crop offsets (B*md+1)*8], each part 16-byte aligned
+static size_t small_part(size_t bytes) { return (bytes + 15) & ~(size_t)15; }
+static size_t small_bytes(const dy_net* net) {
+  const size_t MB = net->cfg.max_batch, md = net->cfg.max_detection;
+  return small_part(MB * 4) + 2 * small_part(MB * md * 24) + small_part((MB * md + 1) * 8);
 }
 
 static int host_slots_init(dy_net* net) {
   if (net->h2d_stream) return DY_OK;
-  const int S = net->S, Sm = S / 2, md = net->cfg.max_detection, MB = net->cfg.max_batch;
+  const int S = net->S, MB = net->cfg.max_batch;
   DY_CUDA(cudaStreamCreateWithFlags(&net->h2d_stream, cudaStreamNonBlocking));
   DY_CUDA(cudaStreamCreateWithFlags(&net->comp_stream, cudaStreamNonBlocking));
   DY_CUDA(cudaStreamCreateWithFlags(&net->d2h_stream, cudaStreamNonBlocking));
+  DY_CUDA(cudaEventCreateWithFlags(&net->ev_host, cudaEventDisableTiming));
+  const size_t md = net->cfg.max_detection;
   for (auto& sl : net->slot) {
     DY_TRY(dev_alloc(net, (void**)&sl.images, (size_t)MB * S * S * 3 * 4, false));
     DY_TRY(dev_alloc(net, (void**)&sl.windows, (size_t)MB * 16, false));
-    DY_TRY(dev_alloc(net, (void**)&sl.det_raw, (size_t)MB * md * 24, false));
-    DY_TRY(dev_alloc(net, (void**)&sl.det_box, (size_t)MB * md * 24, false));
-    DY_TRY(dev_alloc(net, (void**)&sl.det_count, (size_t)MB * 4, false));
-    DY_TRY(dev_alloc(net, (void**)&sl.masks, (size_t)MB * md * Sm * Sm * 4, false));
+    DY_TRY(dev_alloc(net, (void**)&sl.small, small_bytes(net), false));
+    // carve the small-result block
+    uint8_t* q = reinterpret_cast<uint8_t*>(sl.small);
+    sl.det_count = reinterpret_cast<int*>(q);          q += small_part((size_t)MB * 4);
+    sl.det_box = reinterpret_cast<float*>(q);          q += small_part((size_t)MB * md * 24);
+    sl.det_raw = reinterpret_cast<float*>(q);          q += small_part((size_t)MB * md * 24);
+    sl.crop_off = reinterpret_cast<long long*>(q);
+    // pinned host mirror (allocated by the calling thread: NUMA-local under the caller's CPU affinity)
+    DY_CUDA(cudaHostAlloc((void**)&sl.small_host, small_bytes(net), cudaHostAllocDefault));
     DY_CUDA(cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming));
     DY_CUDA(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
   }
   return DY_OK;
 }
 
-int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, const float* windows_host,
-                          float det_thresh, int32_t want_masks, int32_t* ticket) {
+// the [B,max_det,S,S] mask block (full or cropped form: the cropped maps never exceed it) and the uint8
+// image staging are allocated on first use
+static int slot_need(dy_net* net, dy_net::HostSlot& sl, bool masks, bool u8) {
+  const int S = net->S, Sm = S / 2, md = net->cfg.max_detection, MB = net->cfg.max_batch;
+  if (masks && !sl.masks) DY_TRY(dev_alloc(net, (void**)&sl.masks, (size_t)MB * md * Sm * Sm * 4, false));
+  if (u8 && !sl.images_u8) DY_TRY(dev_alloc(net, (void**)&sl.images_u8, (size_t)MB * S * S * 3, false));
+  return DY_OK;
+}
+
+static int host_begin(dy_net* net, const void* images_host, bool u8, int32_t B, const float* windows_host,
+                      float det_thresh, int32_t mask_mode, int32_t* ticket) {
   DY_CHECK(net && images_host && windows_host && ticket, "null argument");
   DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
+  DY_CHECK(mask_mode >= DY_MASKS_NONE && mask_mode <= DY_MASKS_CROPPED, "mask_mode");
   DY_CUDA(cudaSetDevice(net->cfg.device));
   DY_TRY(host_slots_init(net));
   const int id = net->next_slot;
   auto& sl = net->slot[id];
   DY_CHECK(!sl.busy, "all three pipeline slots are in flight: call dy_forward_host_end first");
+  DY_TRY(slot_need(net, sl, mask_mode != DY_MASKS_NONE, u8));
   const int S = net->S;
-  DY_CUDA(cudaMemcpyAsync(sl.images, images_host, (size_t)B * S * S * 3 * 4, cudaMemcpyHostToDevice, net->h2d_stream));
+  const size_t npix = (size_t)B * S * S * 3;
+  if (u8) DY_CUDA(cudaMemcpyAsync(sl.images_u8, images_host, npix, cudaMemcpyHostToDevice, net->h2d_stream));
+  else DY_CUDA(cudaMemcpyAsync(sl.images, images_host, npix * 4, cudaMemcpyHostToDevice, net->h2d_stream));
   DY_CUDA(cudaMemcpyAsync(sl.windows, windows_host, (size_t)B * 16, cudaMemcpyHostToDevice, net->h2d_stream));
   DY_CUDA(cudaEventRecord(sl.ev_h2d, net->h2d_stream));
   DY_CUDA(cudaStreamWaitEvent(net->comp_stream, sl.ev_h2d, 0));
-  DY_TRY(dy_forward(net, sl.images, B, sl.windows, det_thresh, sl.det_raw, sl.det_box, sl.det_count,
-                    want_masks ? sl.masks : nullptr, net->comp_stream));
+  // the caller's own streams may still be using the activation / weight buffers (training step, dy_forward)
+  if (net->user_work) DY_CUDA(cudaStreamWaitEvent(net->comp_stream, net->ev_user, 0));
+  if (u8) {
+    note_launch();
+    DY_TRY(launch_u8_to_f32(sl.images_u8, sl.images, (long long)npix, net->comp_stream));
+  }
+  const bool crop = mask_mode == DY_MASKS_CROPPED;
+  DY_TRY(forward_impl(net, sl.images, B, sl.windows, det_thresh, sl.det_raw, sl.det_box, sl.det_count,
+                      mask_mode == DY_MASKS_FULL ? sl.masks : nullptr, crop ? sl.crop_off : nullptr,
+                      crop ? sl.masks : nullptr, net->comp_stream));
   DY_CUDA(cudaEventRecord(sl.ev_comp, net->comp_stream));
+  DY_CUDA(cudaEventRecord(net->ev_host, net->comp_stream));
+  net->host_work = true;
   sl.B = B;
   sl.busy = true;
-  sl.want_masks = want_masks != 0;
+  sl.mask_mode = mask_mode;
   net->next_slot = (id + 1) % dy_net::kHostSlots;
   *ticket = id;
+  return DY_OK;
+}
+
+int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, const float* windows_host,
+                          float det_thresh, int32_t mask_mode, int32_t* ticket) {
+  return host_begin(net, images_host, false, B, windows_host, det_thresh, mask_mode, ticket);
+}
+
+int dy_forward_host_begin_u8(dy_net* net, const uint8_t* images_host, int32_t B, const float* windows_host,
+                             float det_thresh, int32_t mask_mode, int32_t* ticket) {
+  return host_begin(net, images_host, true, B, windows_host, det_thresh, mask_mode, ticket);
+}
+
+// one D2H copy of the slot's small results into the pinned mirror, then plain memcpy to the caller
+static int host_end_small(dy_net* net, dy_net::HostSlot& sl, float* det_raw_host, float* det_box_host,
+                          int32_t* det_count_host, long long* crop_off_host) {
+  const size_t MB = net->cfg.max_batch, md = net->cfg.max_detection, B = sl.B;
+  cudaStream_t st = net->d2h_stream;
+  DY_CUDA(cudaStreamWaitEvent(st, sl.ev_comp, 0));
+  const size_t used = (sl.mask_mode == DY_MASKS_CROPPED || det_raw_host)
+                          ? small_bytes(net) - (sl.mask_mode == DY_MASKS_CROPPED ? 0 : small_part((MB * md + 1) * 8))
+                          : small_part(MB * 4) + small_part(MB * md * 24);
+  DY_CUDA(cudaMemcpyAsync(sl.small_host, sl.small, used, cudaMemcpyDeviceToHost, st));
+  DY_CUDA(cudaStreamSynchronize(st));
+  const uint8_t* q = sl.small_host;
+  memcpy(det_count_host, q, B * 4);                      q += small_part(MB * 4);
+  memcpy(det_box_host, q, B * md * 24);                  q += small_part(MB * md * 24);
+  if (det_raw_host) memcpy(det_raw_host, q, B * md * 24);
+  q += small_part(MB * md * 24);
+  if (crop_off_host) memcpy(crop_off_host, q, (B * md + 1) * 8);
   return DY_OK;
 }
 
@@ -1054,15 +1267,14 @@ int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float*
   DY_CHECK(ticket >= 0 && ticket < dy_net::kHostSlots, "bad ticket");
   auto& sl = net->slot[ticket];
   DY_CHECK(sl.busy, "ticket is not in flight");
-  DY_CHECK(!masks_host || sl.want_masks, "masks were not requested at dy_forward_host_begin");
+  DY_CHECK(sl.mask_mode != DY_MASKS_CROPPED, "this ticket carries cropped masks: call dy_forward_host_end_cropped");
+  DY_CHECK(!masks_host || sl.mask_mode == DY_MASKS_FULL, "masks were not requested at dy_forward_host_begin");
   const int Sm = net->S / 2, md = net->cfg.max_detection, B = sl.B;
-  cudaStream_t st = net->d2h_stream;
-  DY_CUDA(cudaStreamWaitEvent(st, sl.ev_comp, 0));
-  DY_CUDA(cudaMemcpyAsync(det_count_host, sl.det_count, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  DY_CUDA(cudaMemcpyAsync(det_box_host, sl.det_box, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
-  if (det_raw_host) DY_CUDA(cudaMemcpyAsync(det_raw_host, sl.det_raw, (size_t)B * md * 24, cudaMemcpyDeviceToHost, st));
-  DY_CUDA(cudaStreamSynchronize(st));
+  DY_TRY(host_end_small(net, sl, det_raw_host, det_box_host, det_count_host, nullptr));
   if (masks_host) {
+    // reference layout [B,max_det,S,S]: exactly det_count[b] maps per image; runs of images whose maps are
+    // all valid (n == max_det) or empty are merged so that the copy count stays small
+    cudaStream_t st = net->d2h_stream;
     const size_t per = (size_t)Sm * Sm;
     for (int b = 0; b < B; ++b) {
       const int n = det_count_host[b];
@@ -1076,11 +1288,37 @@ int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float*
   return DY_OK;
 }
 
+int dy_forward_host_end_cropped(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
+                                int32_t* det_count_host, int64_t* crop_offsets_host, float* crops_host,
+                                int64_t crops_capacity) {
+  DY_CHECK(net && det_box_host && det_count_host && crop_offsets_host && crops_host, "null argument");
+  DY_CHECK(ticket >= 0 && ticket < dy_net::kHostSlots, "bad ticket");
+  auto& sl = net->slot[ticket];
+  DY_CHECK(sl.busy, "ticket is not in flight");
+  DY_CHECK(sl.mask_mode == DY_MASKS_CROPPED, "cropped masks were not requested at dy_forward_host_begin");
+  const int md = net->cfg.max_detection, B = sl.B;
+  DY_TRY(host_end_small(net, sl, det_raw_host, det_box_host, det_count_host,
+                        reinterpret_cast<long long*>(crop_offsets_host)));
+  const long long total = crop_offsets_host[(size_t)B * md];
+  if (total > crops_capacity) {
+    sl.busy = false;
+    set_error("crops_host is too small: " + std::to_string(total) + " floats needed");
+    return DY_ERR_INVALID;
+  }
+  if (total > 0) {
+    DY_CUDA(cudaMemcpyAsync(crops_host, sl.masks, (size_t)total * 4, cudaMemcpyDeviceToHost, net->d2h_stream));
+    DY_CUDA(cudaStreamSynchronize(net->d2h_stream));
+  }
+  sl.busy = false;
+  return DY_OK;
+}
+
 int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const float* windows_host, float det_thresh,
                     float* det_raw_host, float* det_box_host, int32_t* det_count_host, float* masks_host) {
   DY_CHECK(net && images_host && windows_host && det_box_host && det_count_host, "null argument");
   int32_t ticket = -1;
-  DY_TRY(dy_forward_host_begin(net, images_host, B, windows_host, det_thresh, masks_host != nullptr, &ticket));
+  DY_TRY(dy_forward_host_begin(net, images_host, B, windows_host, det_thresh,
+                               masks_host != nullptr ? DY_MASKS_FULL : DY_MASKS_NONE, &ticket));
   return dy_forward_host_end(net, ticket, det_raw_host, det_box_host, det_count_host, masks_host);
 }
 
@@ -1100,6 +1338,10 @@ int dy_get_activation(dy_net* net, int32_t layer, int32_t B, float* out_dev, voi
   const LayerState& s = net->L[layer];
   const LayerDef& d = s.def;
   const size_t n = (size_t)B * d.H * d.H * d.cout;
+  if (layer == 81 && net->last_fused) {
+    set_error("convolutional81 was not materialised by the last forward (fused tail): use dy_forward_network");
+    return DY_ERR_STATE;
+  }
   if (net->cfg.precision == DY_PRECISION_FP32) {
     DY_CUDA(cudaMemcpyAsync(out_dev, s.f32, n * 4, cudaMemcpyDeviceToDevice, st));
     return DY_OK;
@@ -1871,6 +2113,42 @@ static int train_init_tc(dy_net* net) {
   return DY_OK;
 }
 
+// dy_finalize_weights after dy_train_init: host copies <-> device masters (see dy_finalize_weights)
+static int sync_masters(dy_net* net, bool* any_new) {
+  *any_new = false;
+  for (int n = 1; n <= 82; ++n) {
+    LayerState& s = net->L[n];
+    const size_t C = (size_t)s.def.cout, wn = (size_t)s.K * C;
+    struct Var { unsigned bit; std::vector<float>* host; float* dev; size_t cnt; };
+    const Var vars[6] = {{1u << 0, &s.w, s.d_w_f32, wn},     {1u << 1, &s.gamma, s.d_gamma, C}, {1u << 2, &s.beta, s.d_beta, C},
+                         {1u << 3, &s.mean, s.d_mean, C},    {1u << 4, &s.var, s.d_var, C},     {1u << 5, &s.bias, s.d_bias, C}};
+    for (const Var& v : vars) {
+      if (v.dev == nullptr || v.host->size() != v.cnt) continue;
+      if (s.host_new & v.bit) {
+        DY_CUDA(cudaMemcpy(v.dev, v.host->data(), v.cnt * 4, cudaMemcpyHostToDevice));
+        *any_new = true;
+      } else if (s.unlocked) {
+        DY_CUDA(cudaMemcpy(v.host->data(), v.dev, v.cnt * 4, cudaMemcpyDeviceToHost));
+      }
+    }
+  }
+  return DY_OK;
+}
+
+// ... and afterwards: the tensor-core engine's dgrad operands follow the (possibly restored) masters; a restore
+// starts the optimizer afresh (the reference's Saver does not save Adam slots, train_yolo3_mask.py:47-58)
+static int retrain_refresh(dy_net* net, bool any_new) {
+  if (net->cfg.precision == DY_PRECISION_BF16)
+    for (int n = 1; n <= 82; ++n)
+      if (net->L[n].in_bwd) DY_TRY(repack_tc(net, n, 0));
+  if (any_new && net->n_train > 0) {
+    DY_CUDA(cudaMemset(net->adam_m, 0, (size_t)net->n_train * 4));
+    DY_CUDA(cudaMemset(net->adam_v, 0, (size_t)net->n_train * 4));
+    net->adam_step = 0;
+  }
+  return DY_OK;
+}
+
 static int train_forward_layer_tc(dy_net* net, int n, const float* images, int B, cudaStream_t st) {
   auto& L = net->L;
   LayerState& s = L[n];
@@ -1975,6 +2253,8 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   DY_CHECK(net->train_ready, "dy_train_init has not been called");
   DY_CHECK(B >= 1 && B <= net->cfg.max_batch, "batch exceeds max_batch");
   cudaStream_t st = (cudaStream_t)stream;
+  DY_TRY(user_begin(net, st));
+  net->last_fused = false;
   auto& L = net->L;
   const bool tc = net->cfg.precision == DY_PRECISION_BF16;
   if (tc) {
@@ -2001,7 +2281,8 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   ya.B = B; ya.net = 32 * ya.g[2];
   memcpy(ya.anchors, net->cfg.anchors, sizeof(ya.anchors));
   ya.true_boxes = true_boxes_dev;
-  ya.ignore_thresh = 0.5f; ya.object_scale = 2.f; ya.noobject_scale = 1.f; ya.class_scale = 1.f; ya.coord_scale = 1.f;
+  ya.ignore_thresh = net->ignore_thresh; ya.object_scale = net->object_scale; ya.noobject_scale = net->noobject_scale;
+  ya.class_scale = net->class_scale; ya.coord_scale = net->coord_scale;
   ya.loss = net->loss_acc;
   note_launch();
   DY_TRY(launch_yolo_loss(ya, st));
@@ -2016,7 +2297,7 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   ma.dmask = tc ? L[82].dyf : L[82].dy;
   ma.mp_planar = tc ? 1 : 0;           // the bf16 engine keeps the score maps planar [B,kk,S,S]
   ma.B = B; ma.max_det = net->cfg.max_detection; ma.S = net->S / 2; ma.H = net->S; ma.k = net->cfg.k_map;
-  ma.mask_scale = 5.f; ma.iou_thresh = 0.5f;
+  ma.mask_scale = net->mask_scale; ma.iou_thresh = 0.5f;      // 0.5: literal of loss_mask (:784-791)
   ma.rois = net->mask_rois; ma.assign = net->mask_assign; ma.npos = net->mask_npos;
   ma.loss = net->loss_acc + 5;
   note_launch(2);
@@ -2032,23 +2313,25 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   for (int i = 0; i < 7; ++i) total += acc[i];
   losses_host[0] = (float)total;
   for (int i = 0; i < 7; ++i) losses_host[1 + i] = (float)acc[i];
-  return DY_OK;
+  return user_end(net, st);
 }
 
 int dy_train_backward(dy_net* net, int32_t B, int32_t layer_hi, int32_t layer_lo, float* grad_flat_dev, void* stream) {
   DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
   DY_CHECK(layer_lo >= 1 && layer_hi <= 82 && layer_lo <= layer_hi, "layer range");
+  DY_TRY(user_begin(net, (cudaStream_t)stream));
   const bool tc = net->cfg.precision == DY_PRECISION_BF16;
   for (int n = layer_hi; n >= layer_lo; --n) {
     if (tc) DY_TRY(train_backward_layer_tc(net, n, B, grad_flat_dev, (cudaStream_t)stream));
     else DY_TRY(train_backward_layer(net, n, B, grad_flat_dev, (cudaStream_t)stream));
   }
-  return DY_OK;
+  return user_end(net, (cudaStream_t)stream);
 }
 
 int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad_scale, void* stream) {
   DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
+  DY_TRY(user_begin(net, st));
   auto& L = net->L;
   net->adam_step += 1;
   const double t = (double)net->adam_step;
@@ -2068,7 +2351,7 @@ int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad
     note_launch(2);
     DY_TRY(launch_pack_multi(net->kseg_dev, net->n_kseg, net->max_pack_tiles, st));
   }
-  return DY_OK;
+  return user_end(net, st);      // the host-buffer pipeline must not read weights Adam is still rewriting
 }
 
 int dy_train_get_tensor(dy_net* net, int32_t layer, int32_t which, int32_t B, float* out_dev, void* stream) {

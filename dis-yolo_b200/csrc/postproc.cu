@@ -413,6 +413,90 @@ __global__ void __launch_bounds__(512) mask_kernel(MaskArgs a, int rpi) {
 
 int g_mask_stream = 1;
 
+// ------------------------------------------------------------------------------------------
+// Box-cropped form of the same maps: the reference's consumer only ever reads
+// det_mask[y1:y2, x1:x2] with (y1,x1,y2,x2) = round(box * S) (calculate_test_map.py:247-252), i.e. the
+// box region whose bin edges finalize_kernel already holds.  crop_offsets_kernel: exclusive scan of the
+// crop areas over (image, detection) -> off[B*max_det + 1] (off[last] = total floats).
+// crop_mask_kernel: crop d of image b = rows [y1,y2) x cols [x1,x2) of its [S,S] map, row-major, at off.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void crop_rect(const int* ed, int k, int S, int& x1, int& y1, int& w, int& h) {
+  x1 = max(ed[0], 0);
+  y1 = max(ed[kMaxK + 1], 0);
+  w = max(min(ed[k], S) - x1, 0);
+  h = max(min(ed[kMaxK + 1 + k], S) - y1, 0);
+}
+
+__global__ void __launch_bounds__(1024) crop_offsets_kernel(MaskArgs a, long long* off) {
+  __shared__ long long part[1024];
+  const int n = a.B * a.max_det;
+  const int per = (n + 1023) / 1024;
+  const int i0 = threadIdx.x * per;
+  long long sum = 0;
+  for (int i = i0; i < i0 + per && i < n; ++i) {
+    const int b = i / a.max_det, d = i - b * a.max_det;
+    if (d < a.det_count[b]) {
+      int x1, y1, w, h;
+      crop_rect(a.edges + (long long)i * (2 * (kMaxK + 1)), a.k, a.S, x1, y1, w, h);
+      sum += (long long)w * h;
+    }
+  }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {          // Hillis-Steele inclusive scan
+    const long long v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  long long run = part[threadIdx.x] - sum;      // exclusive prefix of this thread's chunk
+  for (int i = i0; i < i0 + per && i < n; ++i) {
+    off[i] = run;
+    const int b = i / a.max_det, d = i - b * a.max_det;
+    if (d < a.det_count[b]) {
+      int x1, y1, w, h;
+      crop_rect(a.edges + (long long)i * (2 * (kMaxK + 1)), a.k, a.S, x1, y1, w, h);
+      run += (long long)w * h;
+    }
+  }
+  if (threadIdx.x == 1023) off[n] = part[1023];
+}
+
+constexpr int kCropPerCta = 4096;   // crop elements per CTA (256 threads x 16)
+
+__global__ void __launch_bounds__(256) crop_mask_kernel(MaskArgs a, const long long* __restrict__ off,
+                                                        float* __restrict__ out) {
+  const int d = blockIdx.y, b = blockIdx.z;
+  if (d >= __ldg(a.det_count + b)) return;
+  const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
+  int gx[kMaxK + 1], gy[kMaxK + 1];
+#pragma unroll
+  for (int j = 0; j <= kMaxK; ++j) {
+    gx[j] = (j <= a.k) ? __ldg(ed + j) : 0x7fffffff;
+    gy[j] = (j <= a.k) ? __ldg(ed + kMaxK + 1 + j) : 0x7fffffff;
+  }
+  int x1, y1, w, h;
+  crop_rect(ed, a.k, a.S, x1, y1, w, h);
+  const int area = w * h;
+  const int e0 = blockIdx.x * kCropPerCta;
+  if (e0 >= area) return;
+  const float* sbase = a.score + b * a.s_img;
+  float* o = out + __ldg(off + (long long)b * a.max_det + d);
+  const int e1 = min(area, e0 + kCropPerCta);
+  for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+    const int r = e / w;
+    const int y = y1 + r, x = x1 + (e - r * w);
+    int bx = 0, by = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxK; ++j) {
+      if (j < a.k && x >= gx[j]) bx = j;
+      if (j < a.k && y >= gy[j]) by = j;
+    }
+    const float v = __ldg(sbase + (long long)(by * a.k + bx) * a.s_ch + (long long)y * a.s_row + (long long)x * a.s_pix);
+    __stcs(o + e, sigmoid_fast(v));
+  }
+}
+
 }  // namespace
 
 void masks_set_streaming(int on) { g_mask_stream = on; }
@@ -461,6 +545,21 @@ int launch_masks(const MaskArgs& a, cudaStream_t st) {
   dim3 grid((a.S + kMaskRowsPerCta - 1) / kMaskRowsPerCta, a.max_det, a.B);
   if (g_mask_stream) mask_kernel<true><<<grid, qpr * rpi, 0, st>>>(a, rpi);
   else mask_kernel<false><<<grid, qpr * rpi, 0, st>>>(a, rpi);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_crop_offsets(const MaskArgs& a, long long* off, cudaStream_t st) {
+  DY_CHECK(off != nullptr, "null offsets");
+  crop_offsets_kernel<<<1, 1024, 0, st>>>(a, off);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_masks_cropped(const MaskArgs& a, const long long* off, float* out, cudaStream_t st) {
+  DY_CHECK(a.max_det <= 65535 && a.B <= 65535, "grid limits");
+  dim3 grid((a.S * a.S + kCropPerCta - 1) / kCropPerCta, a.max_det, a.B);
+  crop_mask_kernel<<<grid, 256, 0, st>>>(a, off, out);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

@@ -66,6 +66,9 @@ int launch_decode(const DecodeArgs& a, cudaStream_t st);
 int launch_nms(const NmsArgs& a, cudaStream_t st);
 int launch_finalize(const FinalizeArgs& a, cudaStream_t st);
 int launch_masks(const MaskArgs& a, cudaStream_t st);
+// box-cropped maps: off[B*max_det+1] = exclusive scan of the crop areas (floats), then the packed crops
+int launch_crop_offsets(const MaskArgs& a, long long* off, cudaStream_t st);
+int launch_masks_cropped(const MaskArgs& a, const long long* off, float* out, cudaStream_t st);
 void masks_set_streaming(int on);   // 1 (default): st.global.cs streaming stores, 0: plain stores
 
 }  // namespace dy

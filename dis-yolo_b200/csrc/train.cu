@@ -1,5 +1,6 @@
-// Training-step kernels, fp32 (see train.cuh).  These run on CUDA cores: round-1 correctness path of
-// the training step (the tcgen05 dgrad/wgrad engines are the listed next step in DESIGN.md).
+// Training-step kernels, fp32 (see train.cuh): the fused loss + gradient kernels, Adam, the multi-tensor
+// helpers (shared by both engines) and the CUDA-core conv backward of the fp32 VERIFICATION engine.  The
+// tensor-core dgrad / wgrad / BN kernels of the bf16 engine live in train_tc.cu.
 #include "train.cuh"
 
 namespace dy {

@@ -221,45 +221,103 @@ class Engine(object):
                                             _ptr(cnt), _ptr(msk)), 'dy_forward_host')
         return raw, box, cnt, msk
 
-    def forward_host_begin(self, images, windows, det_thresh, want_masks=True):
-        """Pipelined form: enqueue H2D + forward of one batch, return a ticket (see dy_forward_host_begin)."""
+    def forward_host_begin(self, images, windows, det_thresh, want_masks=True, masks=None):
+        """Pipelined form: enqueue H2D + forward of one batch, return a ticket (dy_forward_host_begin /
+        dy_forward_host_begin_u8).  images: fp32 [B,S,S,3] in [0,1] (the reference's feed) or uint8
+        [B,S,S,3] (the letterboxed image before image_read's `/ 255.`; divided on the device, bit-identical
+        input, a quarter of the bytes).  masks: 'full' (reference layout [B,max_det,S/2,S/2]), 'cropped'
+        (only det_mask[y1:y2, x1:x2] per detection -- what calculate_test_map.py:247-252 reads) or 'none';
+        default follows want_masks."""
         t = self.torch
         B = int(images.shape[0])
         S = self.image_size
+        mode = masks if masks is not None else ('full' if want_masks else 'none')
+        mode_id = {'none': _lib.MASKS_NONE, 'full': _lib.MASKS_FULL, 'cropped': _lib.MASKS_CROPPED}[mode]
+        u8 = (images.dtype == t.uint8) if isinstance(images, t.Tensor) else (np.asarray(images).dtype == np.uint8)
+        dt = t.uint8 if u8 else t.float32
 
-        def stage(key, x, shape):
-            if isinstance(x, t.Tensor) and x.is_pinned() and x.dtype == t.float32 and x.is_contiguous():
+        def stage(key, x, shape, dtype):
+            if isinstance(x, t.Tensor) and x.is_pinned() and x.dtype == dtype and x.is_contiguous():
                 return x
-            buf = self.pinned(key, shape, t.float32)
-            buf.copy_(x if isinstance(x, t.Tensor) else t.from_numpy(np.ascontiguousarray(x, np.float32)))
+            buf = self.pinned(key, shape, dtype)
+            buf.copy_(x if isinstance(x, t.Tensor) else
+                      t.from_numpy(np.ascontiguousarray(x, np.uint8 if dtype == t.uint8 else np.float32)))
             return buf
         if getattr(self, '_inflight', 0) >= 3:
             # refuse BEFORE touching a staging buffer: all three belong to batches whose H2D may still run
             raise _lib.DisYoloError('all three pipeline slots are in flight: call forward_host_end first')
         n = getattr(self, '_begin_count', 0)
-        img = stage('img%d' % (n % 3), images, (B, S, S, 3))
-        win = stage('win%d' % (n % 3), windows, (B, 4))
+        img = stage('img%s%d' % ('u8' if u8 else '', n % 3), images, (B, S, S, 3), dt)
+        win = stage('win%d' % (n % 3), windows, (B, 4), t.float32)
         ticket = C.c_int32(-1)
-        _lib.check(self.lib.dy_forward_host_begin(self.h, _ptr(img), B, _ptr(win), float(det_thresh),
-                                                  int(bool(want_masks)), C.byref(ticket)), 'dy_forward_host_begin')
+        fn = self.lib.dy_forward_host_begin_u8 if u8 else self.lib.dy_forward_host_begin
+        _lib.check(fn(self.h, _ptr(img), B, _ptr(win), float(det_thresh), mode_id, C.byref(ticket)),
+                   'dy_forward_host_begin')
         self._begin_count = n + 1
         self._inflight = getattr(self, '_inflight', 0) + 1
-        return (ticket.value, B, bool(want_masks), (img, win))
+        return (ticket.value, B, mode, (img, win))
 
     def forward_host_end(self, ticket):
+        """-> (det_raw, det_box, det_count, masks) pinned CPU tensors.  masks is [B,max_det,S/2,S/2] ('full'),
+        None ('none') or, for a 'cropped' ticket, the pair (offsets int64 [B*max_det+1], crops fp32 [total]):
+        crop (b,d) = crops[offsets[b*max_det+d] : offsets[b*max_det+d+1]] viewed (y2-y1, x2-x1), see
+        crop_view / expand_masks."""
         t = self.torch
-        tid, B, want_masks, _keep = ticket
+        tid, B, mode, _keep = ticket
+        if mode is True or mode is False:           # tickets of the round-1 form (want_masks flag)
+            mode = 'full' if mode else 'none'
         md, sm = self.max_detection, self.mask_size
         raw = self.pinned('raw%d' % tid, (B, md, 6), t.float32)
         box = self.pinned('box%d' % tid, (B, md, 6), t.float32)
         cnt = self.pinned('cnt%d' % tid, (B,), t.int32)
-        msk = self.pinned('msk%d' % tid, (B, md, sm, sm), t.float32) if want_masks else None
+        if mode == 'cropped':
+            off = self.pinned('off%d' % tid, (B * md + 1,), t.int64)
+            crops = self.pinned('crop%d' % tid, (B * md * sm * sm,), t.float32)
+            _lib.check(self.lib.dy_forward_host_end_cropped(self.h, tid, _ptr(raw), _ptr(box), _ptr(cnt), _ptr(off),
+                                                            _ptr(crops), crops.numel()), 'dy_forward_host_end_cropped')
+            self._inflight = max(0, getattr(self, '_inflight', 0) - 1)
+            return raw, box, cnt, (off, crops[:int(off[B * md])])
+        msk = self.pinned('msk%d' % tid, (B, md, sm, sm), t.float32) if mode == 'full' else None
         _lib.check(self.lib.dy_forward_host_end(self.h, tid, _ptr(raw), _ptr(box), _ptr(cnt), _ptr(msk)),
                    'dy_forward_host_end')
         self._inflight = max(0, getattr(self, '_inflight', 0) - 1)
         return raw, box, cnt, msk
 
+    def crop_rect(self, box_row):
+        """(y1, x1, y2, x2) = np.around(box * S/2) clamped to the map: the reference consumer's crop
+        (calculate_test_map.py:247-252) and the extent of a 'cropped' map."""
+        sm = self.mask_size
+        r = np.around(np.asarray(box_row[:4], np.float32) * np.float32(sm)).astype(np.int64)
+        y1, x1, y2, x2 = [int(min(max(v, 0), sm)) for v in r]
+        return y1, x1, y2, x2
+
+    def crop_view(self, box, offsets, crops, b, d):
+        """The crop of detection d of image b as a 2-D view [(y2-y1), (x2-x1)] of `crops`."""
+        y1, x1, y2, x2 = self.crop_rect(box[b, d])
+        o = int(offsets[b * self.max_detection + d])
+        return crops[o:o + (y2 - y1) * (x2 - x1)].view(y2 - y1, x2 - x1)
+
+    def expand_masks(self, box, cnt, offsets, crops):
+        """Cropped result -> the reference's per-image det_mask arrays [n,S/2,S/2] (sigmoid(0) = 0.5 outside
+        the box, yolo3_net_pos.py:925-928): host-side convenience for callers that want the dense layout."""
+        sm, out = self.mask_size, []
+        for b in range(int(cnt.shape[0])):
+            n = int(cnt[b])
+            m = np.full((n, sm, sm), 0.5, np.float32)
+            for d in range(n):
+                y1, x1, y2, x2 = self.crop_rect(box[b, d])
+                m[d, y1:y2, x1:x2] = self.crop_view(box, offsets, crops, b, d).numpy()
+            out.append(m)
+        return out
+
     # ---- training step (bf16 tensor-core engine or fp32 verification engine) ----------------------------------------------------------
+    def set_loss_params(self, object_scale=2.0, noobject_scale=1.0, class_scale=1.0, coord_scale=1.0,
+                        mask_scale=5.0, ignore_thresh=0.5):
+        """cfg.OBJECT_SCALE ... cfg.IGNORE_THRESH (yolo/config.py:49-57) of the training losses."""
+        _lib.check(self.lib.dy_set_loss_params(self.h, float(object_scale), float(noobject_scale), float(class_scale),
+                                               float(coord_scale), float(mask_scale), float(ignore_thresh)),
+                   'dy_set_loss_params')
+
     def train_init(self):
         """Allocate the training state; returns the number of trainable scalars."""
         _lib.check(self.lib.dy_train_init(self.h), 'dy_train_init')

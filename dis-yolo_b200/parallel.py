@@ -10,25 +10,31 @@ import numpy as np
 def plan_buckets(spans, bucket_bytes=25 << 20, elem_bytes=4):
     """spans: [(layer, offset, count)] of the trainable layers (ascending layer = ascending offset).
     Returns buckets [(layer_hi, layer_lo, offset, count)] in the order backward produces them
-    (descending layers); each bucket is one contiguous slice of the flat gradient vector."""
+    (descending layers); each bucket is one contiguous slice of the flat gradient vector.
+
+    The layer ranges tile 82..1 without gaps: a locked layer that sits between two trainable ones still
+    has to propagate its input gradient, and dy_train_backward plans statically (in descending layer
+    order) which consumer overwrites a gradient buffer and which accumulates into it, so every layer
+    must be visited exactly once per step."""
     spans = sorted([s for s in spans if s[2] > 0], key=lambda s: s[0], reverse=True)
-    buckets, cur = [], []
+    groups, cur = [], []
     size = 0
     for layer, off, cnt in spans:
         cur.append((layer, off, cnt))
         size += cnt * elem_bytes
         if size >= bucket_bytes:
-            buckets.append(cur)
+            groups.append(cur)
             cur, size = [], 0
     if cur:
-        buckets.append(cur)
+        groups.append(cur)
     out = []
-    for b in buckets:
-        hi, lo = b[0][0], b[-1][0]
-        off = min(x[1] for x in b)
-        end = max(x[1] + x[2] for x in b)
-        if sum(x[2] for x in b) != end - off:
+    for i, g in enumerate(groups):
+        off = min(x[1] for x in g)
+        end = max(x[1] + x[2] for x in g)
+        if sum(x[2] for x in g) != end - off:
             raise ValueError('bucket is not contiguous in the flat gradient vector')
+        hi = 82 if i == 0 else groups[i - 1][-1][0] - 1            # right below the previous bucket's lowest layer
+        lo = 1 if i == len(groups) - 1 else g[-1][0]              # down to this bucket's lowest trainable layer
         out.append((hi, lo, off, end - off))
     return out
 
@@ -83,6 +89,9 @@ class DataParallelTrainer(object):
                 spans.append((layer, off, cnt))
         self.buckets = plan_buckets(spans, int(bucket_mb) << 20)
         self.comm_stream = torch.cuda.Stream(device=engine.device) if self.world > 1 else None
+        # measurement only (bench.py): the same bucketed step without the collectives; step time with minus
+        # step time without = the all-reduce time that is NOT hidden behind the backward pass
+        self.skip_allreduce = False
 
     def step(self, images, labels, true_boxes, true_masks, perm_prop, perm_gt, det_thresh, lr):
         """One data-parallel training step on this rank's shard; returns the 8 loss scalars averaged
@@ -96,12 +105,10 @@ class DataParallelTrainer(object):
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(t.cuda.current_stream(eng.device))
         ar = BucketedAllReduce(eng.grad_flat, self.buckets, self.group, self.comm_stream)
-        lowest = min(b[1] for b in self.buckets)
         for i, (hi, lo, off, cnt) in enumerate(self.buckets):
             eng.train_backward(hi, lo)
-            ar.bucket_ready(i)
-        if lowest > 1:
-            pass      # layers below the lowest trainable layer have no gradients (frozen backbone)
+            if not self.skip_allreduce:
+                ar.bucket_ready(i)
         ar.wait()
         eng.train_apply(lr, 1.0 / self.world)
         lt = t.from_numpy(np.asarray(losses, np.float32)).to(eng.device)

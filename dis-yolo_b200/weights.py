@@ -47,27 +47,33 @@ def init_weights(flavour='lively', seed=0, lock=None):
             else:
                 out[base + 'biases'] = np.zeros(cout, np.float32)
             continue
+        # 'lively': the oracle's generator statement by statement (oracle/dis_oracle.py make_weights): the same
+        # draws in the same order, the same float32 roundings -- bit-identical weights
+        # (tests/test_oracle_golden.py::test_product_and_oracle_lively_weights_are_bit_identical)
+        f32 = np.float32
         gain = 0.3 if L['res'] else 1.0
-        w = rng.standard_normal(shape) * (gain * np.sqrt(2.0 / (1.01 * k * k * cin)))
+        std = gain * np.sqrt(2.0 / ((1.0 + 0.1 * 0.1) * k * k * cin))
+        w = (rng.standard_normal(shape) * std).astype(f32)
         if L['bn']:
-            out[base + 'weights'] = w.astype(np.float32)
-            out[base + 'BatchNorm/gamma'] = rng.uniform(0.7, 1.3, cout).astype(np.float32)
-            out[base + 'BatchNorm/beta'] = (rng.standard_normal(cout) * 0.2).astype(np.float32)
-            out[base + 'BatchNorm/moving_mean'] = (rng.standard_normal(cout) * 0.2).astype(np.float32)
-            out[base + 'BatchNorm/moving_variance'] = rng.uniform(0.6, 1.6, cout).astype(np.float32)
+            out[base + 'weights'] = w
+            out[base + 'BatchNorm/gamma'] = rng.uniform(0.7, 1.3, cout).astype(f32)
+            out[base + 'BatchNorm/beta'] = (rng.standard_normal(cout) * 0.2).astype(f32)
+            out[base + 'BatchNorm/moving_mean'] = (rng.standard_normal(cout) * 0.2).astype(f32)
+            out[base + 'BatchNorm/moving_variance'] = rng.uniform(0.6, 1.6, cout).astype(f32)
         elif cout == 24:
-            w = w.reshape(k, k, cin, 3, 8) * 0.1
-            w[..., 2:4] *= 0.25
-            b = np.zeros((3, 8))
-            b[:, 4] = -2.6
+            w = w.reshape(k, k, cin, 3, 8) * f32(0.1)     # head logits O(1) on activations that reach |x| ~ 10
+            w[..., 2:4] *= 0.25                            # keep exp(t_wh) tame
+            b = np.zeros((3, 8), f32)
+            b[:, 4] = -2.6                                 # sparse objectness
             b[:, 0:2] = rng.standard_normal((3, 2)) * 0.3
             b[:, 2:4] = rng.standard_normal((3, 2)) * 0.2 - 0.3
             b[:, 5:] = rng.standard_normal((3, 3)) * 0.5
-            out[base + 'weights'] = w.reshape(shape).astype(np.float32)
-            out[base + 'biases'] = b.reshape(24).astype(np.float32)
+            out[base + 'weights'] = w.reshape(shape)
+            out[base + 'biases'] = b.reshape(24).astype(f32)
         else:
-            out[base + 'weights'] = (w * 0.35).astype(np.float32)
-            out[base + 'biases'] = (rng.standard_normal(cout) * 0.5).astype(np.float32)
+            w *= f32(0.35)
+            out[base + 'weights'] = w
+            out[base + 'biases'] = (rng.standard_normal(cout) * 0.5).astype(f32)
     return out
 
 

@@ -101,10 +101,16 @@ class YOLONet(object):
             # the fp32 engine.
             precision = 'bf16' if (not training or all(self.lock[:52])) else 'fp32'
         dev = int(cfg.GPU) if device is None else int(device)
+        if int(cfg.MAX_BOX_PER_IMAGE) != 20:
+            # true_boxes [B,1,1,1,20,5] / true_masks [B,20,H,W] (:56-57): the loss kernels are compiled for 20
+            raise ValueError('cfg.MAX_BOX_PER_IMAGE must be 20 (the shape of true_boxes / true_masks)')
         self.engine = Engine(image_size=self.image_size, max_batch=int(self.batchsize), precision=precision,
                              device=dev, anchors=self.anchors, num_classes=self.num_class, k_map=self.k,
                              alpha=cfg.ALPHA, iou_threshold=cfg.IOU_THRESHOLD,
                              max_detection=cfg.MAX_DETECTION, lock=self.lock)
+        # loss scales / ignore threshold as read from cfg at construction (:30-35, loss_yolo :631-747)
+        self.engine.set_loss_params(self.object_scale, self.noobject_scale, self.class_scale, self.coord_scale,
+                                    self.mask_scale, cfg.IGNORE_THRESH)
 
 
 class Session(object):
@@ -114,6 +120,8 @@ class Session(object):
         self.net = net
         self.restored = False
         self.rng = np.random.default_rng(seed)      # stands in for the unseeded tf.random_shuffle (:781-782)
+        self.init_seed = seed                       # ... and for the unseeded variable initialisers
+        self.initialized_from_init = []
         self.train_ready = False
         self.last_losses = None
 
@@ -130,6 +138,18 @@ class Session(object):
             else:
                 from ..weights import load_npz
                 weights = load_npz(weights)
+        if not self.restored:
+            # The reference runs global_variables_initializer() and THEN assign_from_checkpoint_fn(...,
+            # ignore_missing_vars=True) (train_yolo3_mask.py:63,104-107): variables the checkpoint lacks
+            # (yolov3_3class_coco.ckpt has no convolutional76..82) keep their initial value -- xavier /
+            # zero bias for unlocked layers, truncated normal for locked ones, BatchNorm at identity.
+            from ..weights import init_weights
+            init = init_weights('reference', seed=self.init_seed, lock=self.net.lock)
+            missing = {k: v for k, v in init.items() if k not in weights}
+            if missing:
+                weights = dict(weights)
+                weights.update(missing)
+            self.initialized_from_init = sorted(missing)
         self.net.engine.load_weights(weights)
         self.restored = True
 

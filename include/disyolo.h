@@ -39,6 +39,15 @@ enum dy_precision {
   DY_PRECISION_FP32 = 1  /* verification mode: fp32 CUDA-core convolutions, fp32 activations */
 };
 
+/* What dy_forward_host_begin* brings back besides boxes and counts. */
+enum dy_mask_mode {
+  DY_MASKS_NONE = 0,    /* boxes / counts only                                                            */
+  DY_MASKS_FULL = 1,    /* the reference's layout: det_count[b] maps of [S/2,S/2] fp32 per image          */
+  DY_MASKS_CROPPED = 2  /* only what the reference's consumer reads: det_mask[y1:y2, x1:x2] of every
+                           detection, (y1,x1,y2,x2) = round(box * S/2) (calculate_test_map.py:247-252),
+                           packed back to back -- same floats, a fraction of the PCIe traffic          */
+};
+
 /* Constructor arguments = the constants YOLONet.__init__ reads from yolo/config.py
  * (yolo3_net_pos.py:13-37; config.py:21-22,38,41-46,60-72) plus the per-layer lock flags that are
  * literals inside build_network (yolo3_net_pos.py:155-156). */
@@ -76,7 +85,9 @@ int dy_destroy(dy_net* net);
  * moving_mean|moving_variance", ".../biases".  `host` holds prod(shape) floats. */
 int dy_load_weights(dy_net* net, const char* tf_name, const float* host, const int64_t* shape, int32_t ndim);
 /* Folds BN, packs bf16 operands, builds TMA descriptors.  Must follow the last dy_load_weights and
- * precede dy_forward. */
+ * precede dy_forward.  After dy_train_init the device master copies are the truth: variables loaded since
+ * the previous finalize replace their masters (and restart Adam, whose slots the reference's Saver does
+ * not store either), all others are read back from the masters, so a re-finalize never reverts training. */
 int dy_finalize_weights(dy_net* net);
 
 /* Replaces: sess.run(net.evaluation, {images, clip_window, det_thresh, is_training: False})
@@ -106,11 +117,26 @@ int dy_forward_host(dy_net* net, const float* images_host, int32_t B, const floa
  * bubble (with two slots the next H2D could only start after the previous D2H had finished).
  * dy_forward_host == begin + end. */
 int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, const float* windows_host,
-                          float det_thresh, int32_t want_masks, int32_t* ticket);
+                          float det_thresh, int32_t mask_mode /* enum dy_mask_mode */, int32_t* ticket);
 int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
                         int32_t* det_count_host, float* masks_host);
+/* The same with the image as image_read holds it BEFORE its `/ 255.` (calculate_test_map.py:160-175):
+ * [B,S,S,3] uint8 RGB, letterboxed.  The division happens on the device and yields bit-identical fp32
+ * inputs ((float)(v / 255.0), 256 possible values), with a quarter of the host->device bytes. */
+int dy_forward_host_begin_u8(dy_net* net, const uint8_t* images_host, int32_t B, const float* windows_host,
+                             float det_thresh, int32_t mask_mode, int32_t* ticket);
+/* Completion of a DY_MASKS_CROPPED ticket.  crop_offsets_host [B*max_det + 1] int64: crop (b,d) starts at
+ * float offset crop_offsets_host[b*max_det + d] of crops_host and is (y2-y1) x (x2-x1) row-major with
+ * (y1,x1,y2,x2) = round(det_box[b,d,0:4] * S/2) clamped to the map; the last entry is the total.  All results
+ * of the ticket leave the device in two copies (small block, crops).  crops_capacity in floats;
+ * B*max_det*(S/2)^2 always suffices. */
+int dy_forward_host_end_cropped(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
+                                int32_t* det_count_host, int64_t* crop_offsets_host, float* crops_host,
+                                int64_t crops_capacity);
 
-/* Network only (conv1..82), no decode / NMS / masks: fills the head and score-map buffers. */
+/* Network only (conv1..82), no decode / NMS / masks: fills the head and score-map buffers and materialises
+ * EVERY layer's output (the parity-tap path; dy_forward fuses convolutional82 into convolutional81's
+ * epilogue on the bf16 engine and never writes convolutional81's activation). */
 int dy_forward_network(dy_net* net, const float* images_dev, int32_t B, void* stream);
 
 /* Measurement aid for bench.py: the same launches as dy_forward_network with a CUDA event between
@@ -232,6 +258,11 @@ int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t
  * dy_train_apply: g*grad_scale (+L2) -> Adam -> parameters; updates the BN moving averages
  * (decay 0.997, :74,92-95) and refreshes the inference-mode folded weights. */
 int dy_train_init(dy_net* net);
+/* The loss constants YOLONet.__init__ reads from yolo/config.py:49-57 (OBJECT_SCALE, NOOBJECT_SCALE,
+ * CLASS_SCALE, COORD_SCALE, MASK_SCALE, IGNORE_THRESH; yolo3_net_pos.py:30-35).  Defaults = the reference's
+ * (2, 1, 1, 1, 5, 0.5).  MAX_BOX_PER_IMAGE is fixed at 20 (the shape of true_boxes / true_masks). */
+int dy_set_loss_params(dy_net* net, float object_scale, float noobject_scale, float class_scale, float coord_scale,
+                       float mask_scale, float ignore_thresh);
 int64_t dy_train_param_count(dy_net* net);
 int dy_train_layer_span(dy_net* net, int32_t layer, int64_t* offset, int64_t* count);
 int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const float* yolo3_dev, const float* yolo2_dev,
@@ -258,8 +289,11 @@ uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
  *   "tc_halo"       0 never / 1 whenever legal   -- one halo'd activation box feeds all 3 horizontal taps
  *   "tc_staged", "tc_tma_epi"   epilogue through shared memory / through TMA stores + TMA residual loads
  *   "tc_dual_issue" two MMA-issuer threads with split stage rings (thin tiles)
+ *   "tc_dual_producer" with dual issue: 0 one TMA producer thread feeds both half rings, 1 (default) one each
+ *   "tc_max_stages"    cap of the shared-memory pipeline depth (2..16)
  *   "tc_skip_epilogue"          measurement only: epilogues drain the accumulator and do nothing else
  *   "conv1_tc"      0: the stem on CUDA cores instead of the tcgen05 im2col kernel
+ *   "tc_fuse_tail"  0: convolutional82 as its own launch in dy_forward (default: fused into convolutional81)
  *   "wgrad_fuse_kw" 0 one CTA per tap / 1 (default) fused kernel rows where the N tile is kept / 2 always
  *   "wgrad_lbo_a", "wgrad_sbo_a", "wgrad_lbo_b", "wgrad_sbo_b"  bring-up: UMMA descriptor field overrides
  *   "mask_streaming_stores"     1 (default) st.global.cs in the mask-assembly kernel, 0 plain stores

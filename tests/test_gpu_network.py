@@ -188,7 +188,51 @@ def test_pipelined_host_forward_matches_sync():
             flight.append(eng.forward_host_begin(batches[begun][0], batches[begun][1], 0.2))
             begun += 1
     with pytest.raises(Exception):
-        eng.forward_host_end((0, B, True, None))        # nothing in flight any more
+        eng.forward_host_end((0, B, 'full', None))      # nothing in flight any more
+    eng.close()
+
+
+def test_host_result_modes_agree():
+    """The compact forms of the host call carry exactly the reference-layout results: 'cropped' maps are
+    det_mask[y1:y2, x1:x2] of the 'full' maps (what calculate_test_map.py:247-252 reads; outside the box the
+    full map is sigmoid(0) = 0.5), uint8 images give bit-identical results to their fp32 `/ 255.` form."""
+    import torch
+    import disyolo_b200 as dy
+    B, size = 3, 160
+    eng = dy.Engine(image_size=size, max_batch=B, precision='bf16')
+    eng.load_weights(O.make_weights('lively', 0))
+    rng = np.random.default_rng(31)
+    u8 = rng.integers(0, 256, (B, size, size, 3), dtype=np.uint8)
+    f32 = (u8.astype(np.float64) / 255.).astype(np.float32)          # image_read's division, then the fp32 feed
+    win = np.tile(np.array([[0, 0, 1, 1]], np.float32), (B, 1))
+    win[1] = [0.1, 0.0, 0.9, 1.0]
+    raw, box, cnt, msk = [x.clone() if x is not None else None for x in eng.forward_host(f32, win, 0.2)]
+    assert int(cnt.sum()) > 0
+    sm, md = eng.mask_size, eng.max_detection
+    for images in (f32, u8):
+        r2, b2, c2, (off, crops) = eng.forward_host_end(eng.forward_host_begin(images, win, 0.2, masks='cropped'))
+        assert torch.equal(r2, raw) and torch.equal(b2, box) and torch.equal(c2, cnt)
+        total = 0
+        for b in range(B):
+            for d in range(int(cnt[b])):
+                y1, x1, y2, x2 = eng.crop_rect(box[b, d])
+                assert int(off[b * md + d]) == total
+                total += (y2 - y1) * (x2 - x1)
+                assert torch.equal(eng.crop_view(box, off, crops, b, d), msk[b, d, y1:y2, x1:x2])
+                outside = msk[b, d].clone()
+                outside[y1:y2, x1:x2] = 0.5
+                assert bool((outside == 0.5).all())
+        assert int(off[B * md]) == total == crops.numel()
+        dense = eng.expand_masks(box, cnt, off, crops)
+        for b in range(B):
+            assert np.array_equal(dense[b], msk[b, :int(cnt[b])].numpy())
+    # uint8 + the reference layout
+    r3, b3, c3, m3 = eng.forward_host_end(eng.forward_host_begin(u8, win, 0.2, masks='full'))
+    assert torch.equal(r3, raw) and torch.equal(c3, cnt)
+    for b in range(B):
+        assert torch.equal(m3[b, :int(cnt[b])], msk[b, :int(cnt[b])])
+    r4, b4, c4, m4 = eng.forward_host_end(eng.forward_host_begin(u8, win, 0.2, masks='none'))
+    assert m4 is None and torch.equal(b4, box)
     eng.close()
 
 

@@ -382,3 +382,130 @@ def test_bf16_training_refuses_unlocked_backbone():
     with pytest.raises(_lib.DisYoloError, match='precision=fp32'):
         eng.train_init()
     eng.close()
+
+
+def test_evaluate_after_training_is_ordered_after_the_step():
+    """The reference's validation loop (train_yolo3_mask.py:146-176): sess.run(net.evaluation) right after
+    sess.run([total_loss, optimizer]).  The host-buffer pipeline runs on its own stream: it must wait for
+    the backward pass / Adam / repacking still queued on the caller's stream.  Evaluating immediately
+    must equal evaluating after an explicit device synchronisation."""
+    import torch
+    import disyolo_b200 as dy
+    W, img, labels, tb, tm, pp, pg, thresh = _setup(B=2, size=160, seed=3)
+    win = np.tile(np.array([[0, 0, 1, 1]], np.float32), (2, 1))
+
+    def run(sync):
+        eng = dy.Engine(image_size=160, max_batch=2, precision='bf16')
+        eng.load_weights(W)
+        eng.train_init()
+        outs = []
+        for _ in range(3):
+            eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+            eng.train_backward(82, 1)
+            eng.train_apply(1e-3)
+            if sync:
+                torch.cuda.synchronize()
+            raw, box, cnt, msk = eng.forward_host(img, win, 0.1)
+            outs.append((raw.numpy().copy(), cnt.numpy().copy(),
+                         [msk[b, :int(cnt[b])].numpy().copy() for b in range(2)]))
+        eng.close()
+        return outs
+    a, b = run(False), run(True)
+    for (ra, ca, ma), (rb, cb, mb) in zip(a, b):
+        assert np.array_equal(ca, cb) and np.array_equal(ra, rb)
+        for x, y in zip(ma, mb):
+            assert np.array_equal(x, y)
+
+
+def test_refinalize_after_training_keeps_and_restores_state():
+    """dy_finalize_weights after dy_train_init: (1) with nothing newly loaded it must NOT revert the trained
+    weights to the pre-training host copies; (2) variables loaded afterwards (Saver.restore) replace the
+    training masters, restart Adam, and training continues from THEM."""
+    import disyolo_b200 as dy
+    from disyolo_b200 import _lib
+    W, img, labels, tb, tm, pp, pg, thresh = _setup(B=2, size=128, seed=4)
+    name = 'yolo/convolutional81/weights'
+    for precision in ('bf16', 'fp32'):
+        eng = dy.Engine(image_size=128, max_batch=2, precision=precision)
+        eng.load_weights(W)
+        eng.train_init()
+        for _ in range(2):
+            eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+            eng.train_backward(82, 1)
+            eng.train_apply(1e-3)
+        trained = eng.get_weights(name, W[name].shape)
+        assert not np.array_equal(trained, W[name])
+        win = np.tile(np.array([[0, 0, 1, 1]], np.float32), (2, 1))
+        before = eng.forward_host(img, win, 0.1)
+        before = [x.numpy().copy() for x in before[:3]]
+        _lib.check(eng.lib.dy_finalize_weights(eng.h), 'dy_finalize_weights')          # (1)
+        assert np.array_equal(eng.get_weights(name, W[name].shape), trained)
+        after = [x.numpy().copy() for x in eng.forward_host(img, win, 0.1)[:3]]
+        for x, y in zip(before, after):
+            assert np.array_equal(x, y)
+        # (2) restore the original checkpoint: the masters follow, the next step equals a fresh engine's first step
+        eng.load_weights(W)
+        assert np.array_equal(eng.get_weights(name, W[name].shape), W[name])
+        l_restored = eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+        eng.train_backward(82, 1)
+        eng.train_apply(1e-3)
+        w_restored = eng.get_weights(name, W[name].shape)
+        eng.close()
+        fresh = dy.Engine(image_size=128, max_batch=2, precision=precision)
+        fresh.load_weights(W)
+        fresh.train_init()
+        l_fresh = fresh.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+        fresh.train_backward(82, 1)
+        fresh.train_apply(1e-3)
+        w_fresh = fresh.get_weights(name, W[name].shape)
+        fresh.close()
+        assert np.allclose(l_restored, l_fresh, rtol=1e-5, atol=1e-6), (precision, l_restored, l_fresh)
+        # Adam's first step is lr * g / (|g| + eps): entries whose gradient is ~0 amplify summation-order noise
+        diff = np.abs(w_restored - w_fresh)
+        assert diff.max() <= 2.5e-3 and np.mean(diff < 1e-6) > 0.99, (precision, diff.max(), np.mean(diff < 1e-6))
+
+
+def test_partial_checkpoint_restore_and_loss_params():
+    """Stage 1 of the reference: global_variables_initializer, then assign_from_checkpoint_fn(...,
+    ignore_missing_vars=True) on a checkpoint WITHOUT convolutional76..82 (train_yolo3_mask.py:63,85-107):
+    the mask subnet keeps its initial value.  And the loss scales are the cfg values, not constants."""
+    import disyolo_b200.yolo.config as cfg
+    from disyolo_b200.yolo.yolo3_net_pos import YOLONet, Session
+    from disyolo_b200.weights import init_weights
+    cfg.BATCH_SIZE, cfg.IMAGE_SIZE = 2, 128
+    old_mask_scale = cfg.MASK_SCALE
+    try:
+        rng = np.random.default_rng(8)
+        W = O.make_weights('lively', 2)
+        coco = {k: v for k, v in W.items() if int(k.split('convolutional')[1].split('/')[0]) <= 75}
+        net = YOLONet(True, precision='fp32')
+        sess = Session(net, seed=5)
+        sess.restore(coco)
+        init = init_weights('reference', seed=5, lock=net.lock)
+        assert len(sess.initialized_from_init) == 6 * 5 + 2          # 76..81: w + 4 BN, 82: w + bias
+        got = net.engine.get_weights('yolo/convolutional80/weights', init['yolo/convolutional80/weights'].shape)
+        assert np.array_equal(got, init['yolo/convolutional80/weights'])
+        got = net.engine.get_weights('yolo/convolutional53/weights', W['yolo/convolutional53/weights'].shape)
+        assert np.array_equal(got, W['yolo/convolutional53/weights'])
+        img = rng.random((2, 128, 128, 3), dtype=np.float32)
+        labels, tb, tm = T.make_labels(rng, 2, 128)
+        feed = {net.images: img, net.yolo1: labels[2], net.yolo2: labels[1], net.yolo3: labels[0],
+                net.true_boxes: tb, net.true_masks: tm, net.is_training: True,
+                net.det_thresh: [0.05], net.clip_window: np.tile([[0., 0., 1., 1.]], (2, 1))}
+        sess.rng = np.random.default_rng(77)   # same RoI permutations for both evaluations
+        sess.run(net.total_loss, feed_dict=feed)
+        base = dict(sess.last_losses)
+        net.engine.set_loss_params(object_scale=4.0, noobject_scale=1.0, class_scale=1.0, coord_scale=1.0,
+                                   mask_scale=10.0, ignore_thresh=0.5)
+        sess.rng = np.random.default_rng(77)
+        sess.run(net.total_loss, feed_dict=feed)
+        scaled = dict(sess.last_losses)
+        assert np.isclose(scaled['object'], 2.0 * base['object'], rtol=1e-5)
+        assert np.isclose(scaled['mask'], 2.0 * base['mask'], rtol=1e-5)
+        assert np.isclose(scaled['class'], base['class'], rtol=1e-6)
+        cfg.MAX_BOX_PER_IMAGE = 10
+        with pytest.raises(ValueError):
+            YOLONet(True, precision='fp32')
+    finally:
+        cfg.BATCH_SIZE, cfg.IMAGE_SIZE, cfg.MAX_BOX_PER_IMAGE = 2, 576, 20
+        cfg.MASK_SCALE = old_mask_scale

@@ -156,3 +156,62 @@ def test_forward_shapes_small():
     assert [y.shape for y in yolos] == [(1, 8, 8, 3, 8), (1, 4, 4, 3, 8), (1, 2, 2, 3, 8)]
     assert mp.shape == (1, 32, 32, 9) and len(acts) == 82
     assert np.isfinite(mp).all() and float(np.abs(acts[52]).mean()) < 100.0
+
+
+# --------------------------------------------------------------------------------------------------
+# Independent cross-checks of the TF-side arithmetic the reference keeps no vectors for:
+# the oracle's restatements against torch / torchvision implementations of the same operators.  They do not
+# pin TensorFlow's results, but they break the oracle's self-consistency: a wrong restatement would
+# have to be wrong in the same way in an unrelated code base.
+# --------------------------------------------------------------------------------------------------
+def test_oracle_nms_against_torchvision():
+    import torch
+    torchvision = pytest.importorskip('torchvision')
+    from torchvision.ops import nms
+    rng = np.random.default_rng(12)
+    for trial in range(6):
+        n = int(rng.integers(40, 400))
+        yx = rng.random((n, 2)).astype(np.float32) * 0.8
+        hw = (rng.random((n, 2)).astype(np.float32) * 0.3 + 0.02)
+        boxes = np.concatenate([yx, yx + hw], axis=1)                     # (y1,x1,y2,x2), the reference's order
+        scores = rng.permutation(n).astype(np.float32) / n                # distinct scores: no tie-order question
+        keep = O.nms_tf(boxes, scores, np.arange(n), n, 0.3)
+        tv = nms(torch.from_numpy(boxes[:, [1, 0, 3, 2]].copy()), torch.from_numpy(scores), 0.3).numpy()
+        assert list(keep) == list(tv), trial
+        assert list(O.nms_tf_vectorised(boxes, scores, np.arange(n), n, 0.3)) == list(tv)
+
+
+def test_oracle_batchnorm_and_conv_against_torch_functional():
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal((2, 9, 11, 16)).astype(np.float32)
+    gamma, beta = rng.uniform(0.5, 1.5, 16).astype(np.float32), rng.standard_normal(16).astype(np.float32)
+    mean, var = rng.standard_normal(16).astype(np.float32), rng.uniform(0.5, 2, 16).astype(np.float32)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    want = F.batch_norm(xt, torch.from_numpy(mean), torch.from_numpy(var), torch.from_numpy(gamma),
+                        torch.from_numpy(beta), training=False, eps=O.BN_EPS).permute(0, 2, 3, 1).numpy()
+    assert np.allclose(O.batch_norm_infer(x, gamma, beta, mean, var), want, rtol=1e-5, atol=1e-6)
+    got, m, v = O.batch_norm_train(x, gamma, beta)
+    want = F.batch_norm(xt, None, None, torch.from_numpy(gamma), torch.from_numpy(beta), training=True,
+                        eps=O.BN_EPS).permute(0, 2, 3, 1).numpy()
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-5)
+    assert np.allclose(m, x.mean((0, 1, 2)), atol=1e-6) and np.allclose(v, x.var((0, 1, 2)), rtol=1e-5)
+    # TF 'SAME' stride-2 on an even extent = pad (0 before, 1 after), i.e. F.pad(0,1,0,1) + a VALID conv
+    w = rng.standard_normal((3, 3, 16, 8)).astype(np.float32)
+    wt = torch.from_numpy(w).permute(3, 2, 0, 1)
+    x2 = rng.standard_normal((1, 10, 12, 16)).astype(np.float32)
+    want = F.conv2d(F.pad(torch.from_numpy(x2).permute(0, 3, 1, 2), (0, 1, 0, 1)), wt, stride=2).permute(0, 2, 3, 1)
+    assert np.allclose(O.conv2d_same_numpy(x2, w, 2), want.numpy(), rtol=1e-4, atol=1e-5)
+    assert np.allclose(O.conv2d_same(x2, w, 2), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_product_and_oracle_lively_weights_are_bit_identical():
+    """bench.py / smoke() use disyolo_b200.init_weights('lively', s), the parity tests O.make_weights('lively', s):
+    two independent generators of the same stream -- they must never diverge."""
+    import disyolo_b200 as dy
+    for seed in (0, 3):
+        a, b = dy.init_weights('lively', seed), O.make_weights('lively', seed)
+        assert sorted(a) == sorted(b)
+        for k in a:
+            assert a[k].dtype == b[k].dtype == np.float32 and np.array_equal(a[k], b[k]), k

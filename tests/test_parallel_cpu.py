@@ -19,18 +19,40 @@ def test_plan_buckets_contiguous_and_ordered():
         off += cnt
     assert off == 21070737
     buckets = plan_buckets(spans, 25 << 20)
-    assert buckets[0][0] == 82 and buckets[-1][1] == 53
+    assert buckets[0][0] == 82 and buckets[-1][1] == 1          # the ranges tile 82..1 (frozen layers included)
     covered = 0
     prev_lo = 83
     for hi, lo, o, c in buckets:
         assert hi == prev_lo - 1 and lo <= hi
         prev_lo = lo
         covered += c
-        assert c * 4 >= (25 << 20) or lo == 53
+        assert c * 4 >= (25 << 20) or lo == 1
     assert covered == off
     # descending layers <-> descending offsets: every bucket ends where the previous one starts
     for (h1, l1, o1, c1), (h2, l2, o2, c2) in zip(buckets, buckets[1:]):
         assert o2 + c2 == o1
+
+
+def test_plan_buckets_covers_locked_layers_between_trainable_ones():
+    """A custom lock pattern with frozen layers BETWEEN trainable ones (59-61 locked, 53-58 and 62-82
+    trainable): whatever the bucket boundaries, every layer 82..1 is visited exactly once, so a locked
+    layer's input gradient is still propagated (dy_train_backward plans overwrite / accumulate statically)."""
+    from disyolo_b200.parallel import plan_buckets
+    spans, off = [], 0
+    for n in list(range(53, 59)) + list(range(62, 83)):
+        spans.append((n, off, 1000 + n))
+        off += 1000 + n
+    for bucket_bytes in (4 * 1000, 4 * 3500, 4 * 9000, 1 << 30):
+        buckets = plan_buckets(spans, bucket_bytes)
+        visited = []
+        for hi, lo, o, c in buckets:
+            visited += list(range(hi, lo - 1, -1))
+        assert visited == list(range(82, 0, -1)), bucket_bytes
+        assert sum(c for _, _, _, c in buckets) == off
+        # a bucket's slice holds exactly the trainable layers of its range
+        for hi, lo, o, c in buckets:
+            want = sum(cnt for n, _, cnt in spans if lo <= n <= hi)
+            assert c == want
 
 
 def _free_port():
@@ -79,7 +101,7 @@ def test_bucketed_allreduce_gloo_world2():
     want[0::7] += 0.5
     want[1::7] += 0.5
     assert np.array_equal(res[0], want) and np.array_equal(res[1], want)
-    assert [b[0] for b in buckets] == [10, 7, 4, 1]
+    assert [b[:2] for b in buckets] == [(82, 8), (7, 5), (4, 2), (1, 1)]
 
 
 def test_inference_sharding_is_collective_free():
