@@ -65,6 +65,8 @@ SIGNATURES = {
     'dy_assemble_masks': (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P]),
     'dy_letterbox': (C.c_int, [_P, _I, _I, _I, _P, _P, _P]),
     'dy_postprocess': (C.c_int, [_P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    'dy_letterbox_batch': (C.c_int, [_P, C.c_int64, _I, _I, _I, _I, _P, _P, _P]),
+    'dy_postprocess_batch': (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'dy_mask_overlaps': (C.c_int, [_P, _I, _P, _I, C.c_int64, _P, _P]),
     'dy_assign_labels': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     'dy_postproc_profile': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _F, _P, _I, _P, _P]),

@@ -36,11 +36,12 @@ __device__ __forceinline__ float lerp2(float a, float b, float w0, float w1) {
   return __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
 }
 
-__global__ void letterbox_kernel(const unsigned char* __restrict__ rgb, LetterboxGeom g, double scale_x,
-                                 double scale_y, float* __restrict__ out) {
+__global__ void letterbox_kernel(const unsigned char* __restrict__ rgb, long long rgb_stride, LetterboxGeom g,
+                                 double scale_x, double scale_y, float* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= g.size) return;
-  float* o = out + ((size_t)y * g.size + x) * 3;
+  rgb += (size_t)blockIdx.z * rgb_stride;                        // blockIdx.z = image of a same-shape batch
+  float* o = out + (((size_t)blockIdx.z * g.size + y) * g.size + x) * 3;
   const int dy_ = y - g.top, dx_ = x - g.left;
   if (dy_ < 0 || dy_ >= g.new_h || dx_ < 0 || dx_ >= g.new_w) {
     const float pad = (float)(127.0 / 255.0);
@@ -65,6 +66,10 @@ __global__ void post_prepare_kernel(const float* __restrict__ det_box, const int
                                     int* __restrict__ boxes_out, unsigned char* __restrict__ valid_out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_max) return;
+  {                                                              // blockIdx.y = image of a same-shape batch
+    const size_t b = blockIdx.y;
+    det_box += b * n_max * 6; count += b; ws += b * n_max; boxes_out += b * n_max * 4; valid_out += b * n_max;
+  }
   PostDet d;
   memset(&d, 0, sizeof(d));
   if (k < count[0]) {
@@ -122,6 +127,12 @@ post_pixel_kernel(const PostDet* __restrict__ ws, const int* __restrict__ count,
   __shared__ PostDet sd[kPostMaxSmemDet];
   __shared__ int list[kPostMaxSmemDet];
   __shared__ int nlist;
+  {                                                              // blockIdx.z = image of a same-shape batch
+    const size_t b = blockIdx.z, plane_b = (size_t)image_h * image_w;
+    ws += b * n_max; count += b; masks += b * n_max * S * S;
+    if (full_masks) full_masks += b * n_max * plane_b;
+    if (merged) merged += b * plane_b;
+  }
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   const int xb0 = blockIdx.x * blockDim.x, xb1 = min(xb0 + (int)blockDim.x, image_w);
   const int n = min(count[0], n_max);
@@ -388,24 +399,27 @@ int launch_u8_to_f32(const unsigned char* src, float* dst, long long n, cudaStre
   return DY_OK;
 }
 
-int launch_letterbox(const unsigned char* rgb, const LetterboxGeom& g, float* out, cudaStream_t st) {
+int launch_letterbox(const unsigned char* rgb, long long rgb_stride, int B, const LetterboxGeom& g, float* out,
+                     cudaStream_t st) {
   DY_CHECK(g.src_h > 0 && g.src_w > 0 && g.new_h > 0 && g.new_w > 0 && g.size > 0, "image geometry");
+  DY_CHECK(B >= 1 && B <= 65535 && g.size <= 65535, "batch / grid limits");
   const double scale_x = 1.0 / ((double)g.new_w / (double)g.src_w), scale_y = 1.0 / ((double)g.new_h / (double)g.src_h);
-  dim3 grid((g.size + 127) / 128, g.size);
-  letterbox_kernel<<<grid, 128, 0, st>>>(rgb, g, scale_x, scale_y, out);
+  dim3 grid((g.size + 127) / 128, g.size, B);
+  letterbox_kernel<<<grid, 128, 0, st>>>(rgb, rgb_stride, g, scale_x, scale_y, out);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
 
-int launch_postprocess(const float* det_box, const int* count, int n_max, const float* masks, int S, int image_h,
-                       int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
+int launch_postprocess(const float* det_box, const int* count, int B, int n_max, const float* masks, int S,
+                       int image_h, int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
                        unsigned char* full_masks, unsigned char* merged, cudaStream_t st) {
   DY_CHECK(n_max >= 1 && S >= 1 && image_h >= 1 && image_w >= 1 && net_size >= 1, "geometry");
-  post_prepare_kernel<<<(n_max + 63) / 64, 64, 0, st>>>(det_box, count, n_max, S, image_h, image_w, net_size, ws,
-                                                        boxes_out, valid_out);
+  DY_CHECK(B >= 1 && B <= 65535 && image_h <= 65535, "batch / grid limits");
+  post_prepare_kernel<<<dim3((n_max + 63) / 64, B), 64, 0, st>>>(det_box, count, n_max, S, image_h, image_w, net_size,
+                                                                 ws, boxes_out, valid_out);
   DY_CUDA(cudaGetLastError());
   if (full_masks || merged) {
-    dim3 grid((image_w + 127) / 128, image_h);
+    dim3 grid((image_w + 127) / 128, image_h, B);
     post_pixel_kernel<<<grid, 128, 0, st>>>(ws, count, n_max, masks, S, image_h, image_w, full_masks, merged);
     DY_CUDA(cudaGetLastError());
   }

@@ -21,8 +21,9 @@ LetterboxGeom letterbox_geom(int src_h, int src_w, int size);
 // n uint8 values -> fp32 v/255 (the float64 quotient rounded to float, like image_read's `/ 255.`)
 int launch_u8_to_f32(const unsigned char* src, float* dst, long long n, cudaStream_t st);
 
-// rgb [src_h, src_w, 3] uint8 (device) -> out [size, size, 3] fp32 (device), one image
-int launch_letterbox(const unsigned char* rgb, const LetterboxGeom& g, float* out, cudaStream_t st);
+// B same-shape images: rgb + b*rgb_stride [src_h, src_w, 3] uint8 (device) -> out [B, size, size, 3] fp32 (device)
+int launch_letterbox(const unsigned char* rgb, long long rgb_stride, int B, const LetterboxGeom& g, float* out,
+                     cudaStream_t st);
 
 struct PostDet {        // one detection in original-image coordinates
   int x1, y1, x2, y2;   // corrected box (correct_yolo_boxes)
@@ -32,8 +33,9 @@ struct PostDet {        // one detection in original-image coordinates
   double scale_x, scale_y;   // cv2.resize source step per destination pixel
 };
 // det_box [n_max,6] = (y1,x1,y2,x2 normalised, class, score), count on the device
-int launch_postprocess(const float* det_box, const int* count, int n_max, const float* masks, int S, int image_h,
-                       int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
+// B images of the same original shape in one launch pair (every array is the [B, ...] stack of the one-image form)
+int launch_postprocess(const float* det_box, const int* count, int B, int n_max, const float* masks, int S,
+                       int image_h, int image_w, int net_size, PostDet* ws, int* boxes_out, unsigned char* valid_out,
                        unsigned char* full_masks, unsigned char* merged, cudaStream_t st);
 
 // training labels (utils/train_data.py:134-178, flips :189-228, normalisation :258-262)

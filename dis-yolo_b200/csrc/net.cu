@@ -434,6 +434,9 @@ struct dy_net {
   int* cand_count = nullptr;
   int* sel = nullptr;
   int* sel_cnt = nullptr;
+  float4* nms_box = nullptr;            // NMS overflow scratch [B,num_classes,cap] (postproc.cuh NmsArgs)
+  unsigned long long* nms_key = nullptr;
+  int* nms_pos = nullptr;
   int* edges = nullptr;
   int* raw_count = nullptr;
   float* det_raw_ws = nullptr;
@@ -574,6 +577,9 @@ static int allocate_buffers(dy_net* net) {
   DY_TRY(dev_alloc(net, (void**)&net->cand_count, (size_t)B * 4));
   DY_TRY(dev_alloc(net, (void**)&net->sel, (size_t)B * C * md * 4));
   DY_TRY(dev_alloc(net, (void**)&net->sel_cnt, (size_t)B * C * 4));
+  DY_TRY(dev_alloc(net, (void**)&net->nms_box, (size_t)B * C * net->cap * 16, false));
+  DY_TRY(dev_alloc(net, (void**)&net->nms_key, (size_t)B * C * net->cap * 8, false));
+  DY_TRY(dev_alloc(net, (void**)&net->nms_pos, (size_t)B * C * net->cap * 4, false));
   DY_TRY(dev_alloc(net, (void**)&net->edges, (size_t)B * md * 2 * (kMaxK + 1) * 4));
   DY_TRY(dev_alloc(net, (void**)&net->raw_count, (size_t)B * 4));
   DY_TRY(dev_alloc(net, (void**)&net->det_raw_ws, (size_t)B * md * 6 * 4));
@@ -768,6 +774,7 @@ static int run_detect(dy_net* net, const float* y8, const float* y16, const floa
   na.B = B; na.num_class = net->cfg.num_classes; na.max_det = net->cfg.max_detection;
   na.iou_thr = net->cfg.iou_threshold;
   na.sel = net->sel; na.sel_cnt = net->sel_cnt;
+  na.ovf_box = net->nms_box; na.ovf_key = net->nms_key; na.ovf_pos = net->nms_pos;
   note_launch();
   DY_TRY(launch_nms(na, st));
   FinalizeArgs fa;
@@ -1405,6 +1412,7 @@ int dy_nms(dy_net* net, const float* box_dev, const int32_t* cls_dev, const floa
   na.B = B; na.num_class = net->cfg.num_classes; na.max_det = net->cfg.max_detection;
   na.iou_thr = net->cfg.iou_threshold;
   na.sel = net->sel; na.sel_cnt = net->sel_cnt;
+  na.ovf_box = net->nms_box; na.ovf_key = net->nms_key; na.ovf_pos = net->nms_pos;
   DY_TRY(launch_nms(na, st));
   FinalizeArgs fa;
   fa.cand = net->cand; fa.cap = net->cap; fa.B = B; fa.num_class = net->cfg.num_classes;
@@ -1456,6 +1464,7 @@ int dy_postproc_profile(dy_net* net, const float* yolo8_dev, const float* yolo16
   na.cand = net->cand; na.cand_count = net->cand_count; na.cap = net->cap;
   na.B = B; na.num_class = net->cfg.num_classes; na.max_det = net->cfg.max_detection;
   na.iou_thr = net->cfg.iou_threshold; na.sel = net->sel; na.sel_cnt = net->sel_cnt;
+  na.ovf_box = net->nms_box; na.ovf_key = net->nms_key; na.ovf_pos = net->nms_pos;
   FinalizeArgs fa;
   fa.cand = net->cand; fa.cap = net->cap; fa.B = B; fa.num_class = net->cfg.num_classes;
   fa.max_det = net->cfg.max_detection; fa.sel = net->sel; fa.sel_cnt = net->sel_cnt;
@@ -1489,31 +1498,49 @@ int dy_postproc_profile(dy_net* net, const float* yolo8_dev, const float* yolo16
   return rc;
 }
 
+static void letterbox_window(const LetterboxGeom& g, int image_size, float* window) {
+  // clip window for filter_detections (calculate_test_map.py:163-168)
+  window[0] = (float)((double)g.top / image_size);
+  window[1] = (float)((double)g.left / image_size);
+  window[2] = (float)((double)(g.new_h + g.top) / image_size);
+  window[3] = (float)((double)(g.new_w + g.left) / image_size);
+}
+
 int dy_letterbox(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_size, float* out_dev, float* window_host,
                  void* stream) {
+  return dy_letterbox_batch(rgb_dev, 0, 1, h, w, image_size, out_dev, window_host, stream);
+}
+
+int dy_letterbox_batch(const uint8_t* rgb_dev, int64_t image_stride, int32_t B, int32_t h, int32_t w,
+                       int32_t image_size, float* out_dev, float* windows_host, void* stream) {
   DY_CHECK(rgb_dev && out_dev, "null argument");
-  DY_CHECK(h >= 1 && w >= 1 && image_size >= 1, "image geometry");
+  DY_CHECK(B >= 1 && h >= 1 && w >= 1 && image_size >= 1, "image geometry");
+  DY_CHECK(B == 1 || image_stride >= (int64_t)h * w * 3, "image_stride smaller than one image");
   const LetterboxGeom g = letterbox_geom(h, w, image_size);
-  if (window_host) {     // clip window for filter_detections (calculate_test_map.py:163-168)
-    window_host[0] = (float)((double)g.top / image_size);
-    window_host[1] = (float)((double)g.left / image_size);
-    window_host[2] = (float)((double)(g.new_h + g.top) / image_size);
-    window_host[3] = (float)((double)(g.new_w + g.left) / image_size);
-  }
+  if (windows_host)
+    for (int b = 0; b < B; ++b) letterbox_window(g, image_size, windows_host + 4 * b);
   note_launch();
-  return launch_letterbox(rgb_dev, g, out_dev, (cudaStream_t)stream);
+  return launch_letterbox(rgb_dev, image_stride, B, g, out_dev, (cudaStream_t)stream);
 }
 
 int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32_t max_det, const float* masks_dev,
                    int32_t S, int32_t image_h, int32_t image_w, int32_t net_size, int32_t* boxes_out_dev,
                    uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev, void* stream) {
+  return dy_postprocess_batch(det_box_dev, det_count_dev, 1, max_det, masks_dev, S, image_h, image_w, net_size,
+                              boxes_out_dev, valid_out_dev, full_masks_dev, merged_dev, stream);
+}
+
+int dy_postprocess_batch(const float* det_box_dev, const int32_t* det_count_dev, int32_t B, int32_t max_det,
+                         const float* masks_dev, int32_t S, int32_t image_h, int32_t image_w, int32_t net_size,
+                         int32_t* boxes_out_dev, uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev,
+                         void* stream) {
   DY_CHECK(det_box_dev && det_count_dev && masks_dev && boxes_out_dev && valid_out_dev, "null argument");
-  DY_CHECK(max_det >= 1 && max_det <= 65535, "max_det");
+  DY_CHECK(max_det >= 1 && max_det <= 65535 && B >= 1, "max_det / batch");
   cudaStream_t st = (cudaStream_t)stream;
   PostDet* ws = nullptr;
-  DY_CUDA(cudaMallocAsync((void**)&ws, (size_t)max_det * sizeof(PostDet), st));
+  DY_CUDA(cudaMallocAsync((void**)&ws, (size_t)B * max_det * sizeof(PostDet), st));
   note_launch(2);
-  const int rc = launch_postprocess(det_box_dev, det_count_dev, max_det, masks_dev, S, image_h, image_w, net_size, ws,
+  const int rc = launch_postprocess(det_box_dev, det_count_dev, B, max_det, masks_dev, S, image_h, image_w, net_size, ws,
                                     boxes_out_dev, valid_out_dev, full_masks_dev, merged_dev, st);
   cudaFreeAsync(ws, st);
   return rc;

@@ -139,41 +139,85 @@ __device__ __forceinline__ KeyPos warp_kp_max(KeyPos v) {
   return v;
 }
 
-// One CTA per (class, image).  The class's survivors live as an "alive" bitmask in shared memory,
-// one 32-bit word per 32 candidates, rebuilt with warp ballots.  Each round: block-wide arg-max of
-// the ordering key over alive candidates = next box TF's greedy loop would select; one pass then
-// clears every alive candidate whose IoU with it exceeds the threshold (strict >) while gathering
-// the next round's arg-max.  At most max_det rounds (max_output_size, :566-573).
-__global__ void __launch_bounds__(256) nms_kernel(NmsArgs a) {
-  extern __shared__ uint32_t alive[];
-  __shared__ unsigned long long red_key[8];
-  __shared__ int red_pos[8];
+// One CTA (1024 threads) per (class, image).
+// Phase 0 compacts the class's candidates into structure-of-arrays form -- box (float4), ordering key,
+// position in the candidate list -- the first kNmsSmem of them in shared memory, the overflow (stress
+// configuration: tens of thousands of candidates per class) in a global scratch area.  The survivors then
+// live as an "alive" bitmask in shared memory, one 32-bit word per 32 compacted candidates, rebuilt with
+// warp ballots.  Each round: block-wide arg-max of the ordering key over alive candidates = the next box
+// TF's greedy loop would select; one pass then clears every alive candidate whose IoU with it exceeds the
+// threshold (strict >) while gathering the next round's arg-max.  At most max_det rounds (max_output_size,
+// :566-573).  In the normal configuration everything a round touches is shared memory; in the overflow
+// range every warp keeps kNmsUnroll independent 16-byte loads in flight (the rounds are latency bound).
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsSmem = 2048;       // compacted candidates kept in shared memory
+constexpr int kNmsUnroll = 4;
+
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsArgs a) {
+  extern __shared__ __align__(16) uint8_t nms_smem[];
+  float4* sbox = reinterpret_cast<float4*>(nms_smem);                                    // [kNmsSmem]
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sbox + kNmsSmem);     // [kNmsSmem]
+  int* spos = reinterpret_cast<int*>(skey + kNmsSmem);                                   // [kNmsSmem]
+  uint32_t* alive = reinterpret_cast<uint32_t*>(spos + kNmsSmem);                        // [ceil(cap/32)]
+  __shared__ unsigned long long red_key[32];
+  __shared__ int red_pos[32];
   __shared__ unsigned long long best_key_s;
   __shared__ int best_pos_s;
+  __shared__ int count_s;
 
   const int c = blockIdx.x, b = blockIdx.y;
   int n = a.cand_count[b];
   if (n > a.cap) n = a.cap;
   const Cand* cd = a.cand + (long long)b * a.cap;
-  const int nwords = (n + 31) >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   int* sel = a.sel + ((long long)b * a.num_class + c) * a.max_det;
+  // overflow area of this (image, class): entries kNmsSmem.. of the compacted list
+  const long long ovf = ((long long)b * a.num_class + c) * a.cap;
+  float4* gbox = a.ovf_box + ovf;
+  unsigned long long* gkey = a.ovf_key + ovf;
+  int* gpos = a.ovf_pos + ovf;
+
+  // ---- phase 0: compaction (any order: the ordering key carries the candidate index) ----
+  if (threadIdx.x == 0) count_s = 0;
+  __syncthreads();
+  for (int i0 = warp * 32; i0 < n; i0 += nwarps * 32) {
+    const int i = i0 + lane;
+    Cand ci;
+    bool m = false;
+    if (i < n) {
+      ci = cd[i];
+      m = ci.cls == c;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+    if (bal == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&count_s, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (m) {
+      const int e = base + __popc(bal & ((1u << lane) - 1u));
+      const float4 bx = make_float4(ci.y1, ci.x1, ci.y2, ci.x2);
+      if (e < kNmsSmem) { sbox[e] = bx; skey[e] = cand_key(ci); spos[e] = i; }
+      else { gbox[e - kNmsSmem] = bx; gkey[e - kNmsSmem] = cand_key(ci); gpos[e - kNmsSmem] = i; }
+    }
+  }
+  __syncthreads();
+  const int nc = count_s;
+  const int nwords = (nc + 31) >> 5;
+  auto entry_box = [&](int e) { return e < kNmsSmem ? sbox[e] : gbox[e - kNmsSmem]; };
+  auto entry_key = [&](int e) { return e < kNmsSmem ? skey[e] : gkey[e - kNmsSmem]; };
+  auto entry_pos = [&](int e) { return e < kNmsSmem ? spos[e] : gpos[e - kNmsSmem]; };
 
   KeyPos best;
   best.key = 0ull;
   best.pos = -1;
   for (int w = warp; w < nwords; w += nwarps) {
-    const int i = w * 32 + lane;
-    bool al = false;
-    if (i < n) {
-      const Cand ci = cd[i];
-      al = (ci.cls == c);
-      if (al) {
-        KeyPos t;
-        t.key = cand_key(ci);
-        t.pos = i;
-        best = kp_max(best, t);
-      }
+    const int e = w * 32 + lane;
+    const bool al = e < nc;
+    if (al) {
+      KeyPos t;
+      t.key = entry_key(e);
+      t.pos = e;
+      best = kp_max(best, t);
     }
     const uint32_t m = __ballot_sync(0xffffffffu, al);
     if (lane == 0) alive[w] = m;
@@ -200,36 +244,62 @@ __global__ void __launch_bounds__(256) nms_kernel(NmsArgs a) {
     const unsigned long long bk = best_key_s;
     const int bp = best_pos_s;
     if (bk == 0ull) break;
-    if (threadIdx.x == 0) sel[nsel] = bp;
+    if (threadIdx.x == 0) sel[nsel] = entry_pos(bp);
     ++nsel;
     if (nsel >= a.max_det) break;
-    const Cand sc = cd[bp];
-    const float4 sb = make_float4(sc.y1, sc.x1, sc.y2, sc.x2);
+    const float4 sb = entry_box(bp);
     best.key = 0ull;
     best.pos = -1;
-    for (int w = warp; w < nwords; w += nwarps) {
+    // words of the shared-memory range, then the overflow range kNmsUnroll words at a time
+    const int sm_words = min(nwords, kNmsSmem / 32);
+    for (int w = warp; w < sm_words; w += nwarps) {
       const uint32_t word = alive[w];
       if (word == 0u) continue;                   // warp-uniform
-      const int i = w * 32 + lane;
+      const int e = w * 32 + lane;
       bool al = (word >> lane) & 1u;
       if (al) {
-        if (i == bp) {
+        if (e == bp || iou_tf(sbox[e], sb) > a.iou_thr) {
           al = false;
         } else {
-          const Cand ci = cd[i];
-          if (iou_tf(make_float4(ci.y1, ci.x1, ci.y2, ci.x2), sb) > a.iou_thr) {
-            al = false;
-          } else {
-            KeyPos t;
-            t.key = cand_key(ci);
-            t.pos = i;
-            best = kp_max(best, t);
-          }
+          KeyPos t;
+          t.key = skey[e];
+          t.pos = e;
+          best = kp_max(best, t);
         }
       }
       const uint32_t m = __ballot_sync(0xffffffffu, al);
       __syncwarp();                               // every lane has read alive[w] before lane 0 rewrites it
       if (lane == 0) alive[w] = m;
+    }
+    for (int w0 = sm_words + warp * kNmsUnroll; w0 < nwords; w0 += nwarps * kNmsUnroll) {
+      uint32_t word[kNmsUnroll];
+      float4 bx[kNmsUnroll];
+      bool al[kNmsUnroll];
+#pragma unroll
+      for (int u = 0; u < kNmsUnroll; ++u) {      // all loads first: kNmsUnroll independent requests per lane
+        const int w = w0 + u;
+        word[u] = w < nwords ? alive[w] : 0u;
+        al[u] = (word[u] >> lane) & 1u;
+        if (al[u]) bx[u] = gbox[w * 32 + lane - kNmsSmem];
+      }
+#pragma unroll
+      for (int u = 0; u < kNmsUnroll; ++u) {
+        const int w = w0 + u;
+        if (word[u] == 0u) continue;              // warp-uniform
+        const int e = w * 32 + lane;
+        if (al[u]) {
+          if (e == bp || iou_tf(bx[u], sb) > a.iou_thr) {
+            al[u] = false;
+          } else {
+            KeyPos t;
+            t.key = gkey[e - kNmsSmem];
+            t.pos = e;
+            best = kp_max(best, t);
+          }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, al[u]);
+        if (lane == 0) alive[w] = m;              // (this warp alone owns word w in this pass)
+      }
     }
   }
   if (threadIdx.x == 0) a.sel_cnt[b * a.num_class + c] = nsel;
@@ -511,10 +581,16 @@ int launch_decode(const DecodeArgs& a, cudaStream_t st) {
 }
 
 int launch_nms(const NmsArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)((a.cap + 31) / 32) * 4;
-  DY_CHECK(smem <= 48 * 1024, "candidate capacity too large for the alive bitmask");
+  const size_t smem = (size_t)kNmsSmem * (16 + 8 + 4) + (size_t)((a.cap + 31) / 32) * 4 + 16;
+  DY_CHECK(smem <= 160 * 1024, "candidate capacity too large for the alive bitmask");
+  DY_CHECK(a.ovf_box && a.ovf_key && a.ovf_pos, "NMS overflow scratch missing");
+  static bool attr = false;
+  if (!attr) {
+    DY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr = true;
+  }
   dim3 grid(a.num_class, a.B);
-  nms_kernel<<<grid, 256, smem, st>>>(a);
+  nms_kernel<<<grid, kNmsThreads, smem, st>>>(a);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

@@ -38,6 +38,10 @@ struct NmsArgs {
   float iou_thr;
   int* sel;       // [B,num_class,max_det] positions into cand
   int* sel_cnt;   // [B,num_class]
+  // scratch for classes with more candidates than the kernel keeps in shared memory: [B,num_class,cap] each
+  float4* ovf_box;
+  unsigned long long* ovf_key;
+  int* ovf_pos;
 };
 
 struct FinalizeArgs {

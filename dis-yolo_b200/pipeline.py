@@ -4,6 +4,10 @@ decode + NMS + mask assembly, then per detection correct_yolo_boxes / crop / res
 and the merged semantic mask -- with every step on the GPU and only uint8 images going up and the
 boxes + merged masks (optionally the boolean instance masks) coming back.
 
+A batch whose frames all have the same shape (the usual case: one camera) takes ONE batched letterbox
+launch and ONE post-processing launch pair (dy_letterbox_batch / dy_postprocess_batch) and one D2H copy per
+result array; mixed shapes fall back to one launch per image.
+
 Three streams and `depth` slots: the uint8 H2D copy of batch k+1 and the D2H of batch k-1 overlap the
 convolutions of batch k.  The network's activation buffers are shared, so letterbox / forward /
 post-processing of successive batches are serialised on one compute stream.  (Measured: running the
@@ -76,21 +80,34 @@ class ImagePipeline(object):
                 self.h2d_bytes += h * w * 3
             sl['ev_h2d'].record(self.h2d)
         cs = C.c_void_p(self.comp.cuda_stream)
+        same = len(set(shapes)) == 1                      # one shape: batched launches, compact result layout
         with t.cuda.stream(self.comp):
             self.comp.wait_event(sl['ev_h2d'])
             self.comp.wait_event(sl['ev_d2h'])            # the slot's previous results have left the device
             wh = sl['win_host']
-            for b, (h, w) in enumerate(shapes):
-                _lib.check(lib.dy_letterbox(_p(sl['u8'][b]), h, w, S, _p(sl['batch'][b]),
-                                            C.c_void_p(wh[b].data_ptr()), cs), 'dy_letterbox')
+            if same:
+                h, w = shapes[0]
+                _lib.check(lib.dy_letterbox_batch(_p(sl['u8']), self.max_h * self.max_w * 3, B, h, w, S, _p(sl['batch']),
+                                                  C.c_void_p(wh.data_ptr()), cs), 'dy_letterbox_batch')
+            else:
+                for b, (h, w) in enumerate(shapes):
+                    _lib.check(lib.dy_letterbox(_p(sl['u8'][b]), h, w, S, _p(sl['batch'][b]),
+                                                C.c_void_p(wh[b].data_ptr()), cs), 'dy_letterbox')
             sl['win'][:B].copy_(wh[:B], non_blocking=True)
             _lib.check(lib.dy_forward(eng.h, _p(sl['batch']), B, _p(sl['win']), float(det_thresh), _p(sl['det_raw']),
                                       _p(sl['det_box']), _p(sl['det_count']), _p(sl['masks']), cs), 'dy_forward')
-            for b, (h, w) in enumerate(shapes):
-                _lib.check(lib.dy_postprocess(_p(sl['det_box'][b]), _p(sl['det_count'][b:b + 1]), md, _p(sl['masks'][b]),
-                                              sm, h, w, S, _p(sl['boxes'][b]), _p(sl['valid'][b]),
-                                              _p(sl['full'][b]) if self.want_full else None, _p(sl['merged'][b]), cs),
-                           'dy_postprocess')
+            if same:
+                # [B,h,w] / [B,md,h,w] stacks at the start of the (flat) result buffers
+                _lib.check(lib.dy_postprocess_batch(_p(sl['det_box']), _p(sl['det_count']), B, md, _p(sl['masks']), sm,
+                                                    h, w, S, _p(sl['boxes']), _p(sl['valid']),
+                                                    _p(sl['full']) if self.want_full else None, _p(sl['merged']), cs),
+                           'dy_postprocess_batch')
+            else:
+                for b, (h, w) in enumerate(shapes):
+                    _lib.check(lib.dy_postprocess(_p(sl['det_box'][b]), _p(sl['det_count'][b:b + 1]), md,
+                                                  _p(sl['masks'][b]), sm, h, w, S, _p(sl['boxes'][b]), _p(sl['valid'][b]),
+                                                  _p(sl['full'][b]) if self.want_full else None, _p(sl['merged'][b]), cs),
+                               'dy_postprocess')
             sl['ev_comp'].record(self.comp)
         with t.cuda.stream(self.d2h):
             self.d2h.wait_event(sl['ev_comp'])
@@ -99,14 +116,22 @@ class ImagePipeline(object):
             sl['h_det'][:B].copy_(sl['det_box'][:B], non_blocking=True)
             sl['h_count'][:B].copy_(sl['det_count'][:B], non_blocking=True)
             self.d2h_bytes += B * (md * 16 + md + md * 24 + 4)
-            for b, (h, w) in enumerate(shapes):
-                sl['h_merged'][b, :h * w].copy_(sl['merged'][b, :h * w], non_blocking=True)
-                self.d2h_bytes += h * w
+            if same:
+                h, w = shapes[0]
+                sl['h_merged'].view(-1)[:B * h * w].copy_(sl['merged'].view(-1)[:B * h * w], non_blocking=True)
+                self.d2h_bytes += B * h * w
                 if self.want_full:
-                    sl['h_full'][b, :md * h * w].copy_(sl['full'][b, :md * h * w], non_blocking=True)
-                    self.d2h_bytes += md * h * w
+                    sl['h_full'].view(-1)[:B * md * h * w].copy_(sl['full'].view(-1)[:B * md * h * w], non_blocking=True)
+                    self.d2h_bytes += B * md * h * w
+            else:
+                for b, (h, w) in enumerate(shapes):
+                    sl['h_merged'][b, :h * w].copy_(sl['merged'][b, :h * w], non_blocking=True)
+                    self.d2h_bytes += h * w
+                    if self.want_full:
+                        sl['h_full'][b, :md * h * w].copy_(sl['full'][b, :md * h * w], non_blocking=True)
+                        self.d2h_bytes += md * h * w
             sl['ev_d2h'].record(self.d2h)
-        sl['busy'], sl['shapes'] = True, shapes
+        sl['busy'], sl['shapes'], sl['compact'] = True, shapes, same
         ticket = self.next
         self.next = (self.next + 1) % self.depth
         return ticket
@@ -125,10 +150,15 @@ class ImagePipeline(object):
         for b, (h, w) in enumerate(sl['shapes']):
             n = int(sl['h_count'][b])
             det = sl['h_det'][b, :n].numpy()
+            if sl['compact']:
+                merged = sl['h_merged'].view(-1)[b * h * w:(b + 1) * h * w]
+                full = sl['h_full'].view(-1)[b * md * h * w:(b + 1) * md * h * w] if self.want_full else None
+            else:
+                merged = sl['h_merged'][b, :h * w]
+                full = sl['h_full'][b, :md * h * w] if self.want_full else None
             out.append(dict(boxes=sl['h_boxes'][b, :n].numpy(), valid=sl['h_valid'][b, :n].numpy().astype(bool),
                             classes=det[:, 4].astype(np.int32), scores=det[:, 5],
-                            merged=sl['h_merged'][b, :h * w].numpy().reshape(h, w),
-                            masks=(sl['h_full'][b, :md * h * w].numpy().reshape(md, h, w)[:n].astype(bool)
-                                   if self.want_full else None)))
+                            merged=merged.numpy().reshape(h, w),
+                            masks=(full.numpy().reshape(md, h, w)[:n].astype(bool) if self.want_full else None)))
         sl['busy'] = False
         return out

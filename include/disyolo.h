@@ -184,6 +184,10 @@ int dy_assemble_masks(dy_net* net, const float* score_dev, int32_t layout, int32
  * (may be NULL) receives the clip window (top, left, bottom, right) / image_size. */
 int dy_letterbox(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_size, float* out_dev, float* window_host,
                  void* stream);
+/* The same for B images of one shape in ONE launch: image b starts at rgb_dev + b*image_stride (bytes),
+ * out_dev [B,image_size,image_size,3], windows_host [B,4] (may be NULL). */
+int dy_letterbox_batch(const uint8_t* rgb_dev, int64_t image_stride, int32_t B, int32_t h, int32_t w,
+                       int32_t image_size, float* out_dev, float* windows_host, void* stream);
 /* Replaces the per-detection loop of calculate_test_map.py:233-269 (utils/validation_map.py:137-166)
  * for ONE image: correct_yolo_boxes (:121-138), crop of each [S,S] mask to its box, cv2.resize
  * INTER_LINEAR to the box size in the original image, > 0.5, paste.  det_box_dev [max_det,6] and
@@ -195,6 +199,13 @@ int dy_letterbox(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_siz
 int dy_postprocess(const float* det_box_dev, const int32_t* det_count_dev, int32_t max_det, const float* masks_dev,
                    int32_t S, int32_t image_h, int32_t image_w, int32_t net_size, int32_t* boxes_out_dev,
                    uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev, void* stream);
+/* The same for B images that share one original shape, in ONE launch pair: every array is the [B, ...] stack of
+ * the one-image form (det_box [B,max_det,6], det_count [B], masks [B,max_det,S,S] = dy_forward's outputs as they
+ * stand; boxes_out [B,max_det,4], valid_out [B,max_det], full_masks [B,max_det,h,w], merged [B,h,w]). */
+int dy_postprocess_batch(const float* det_box_dev, const int32_t* det_count_dev, int32_t B, int32_t max_det,
+                         const float* masks_dev, int32_t S, int32_t image_h, int32_t image_w, int32_t net_size,
+                         int32_t* boxes_out_dev, uint8_t* valid_out_dev, uint8_t* full_masks_dev, uint8_t* merged_dev,
+                         void* stream);
 
 /* Replaces compute_overlaps_masks (utils/voc_eval_mask.py:38-56), the inner operation of the mask-level
  * mAP (voc_eval, :58-134): IoU of every mask of set 1 with every mask of set 2.

@@ -111,10 +111,13 @@ def test_letterbox_feeds_the_network(eng):
     e.close()
 
 
-def test_image_pipeline_matches_stepwise_calls():
+@pytest.mark.parametrize('sizes', [[(120, 200), (240, 180), (160, 160)], [(200, 180)] * 3],
+                         ids=['mixed_shapes', 'one_shape_batched_launches'])
+def test_image_pipeline_matches_stepwise_calls(sizes):
     """ImagePipeline (uint8 images in, boxes + merged masks out, two batches in flight) returns exactly what
     letterbox -> forward -> postprocess return when called one after the other, and its instance masks
-    agree with the oracle's loop on the same detections."""
+    agree with the oracle's loop on the same detections.  A batch of same-shape frames goes through
+    dy_letterbox_batch / dy_postprocess_batch (one launch each), mixed shapes through the per-image calls."""
     pytest.importorskip('cv2')
     import torch
     import disyolo_b200 as dy
@@ -123,7 +126,6 @@ def test_image_pipeline_matches_stepwise_calls():
     e = dy.Engine(image_size=S, max_batch=B, precision='bf16')
     e.load_weights(O.make_weights('lively', 0))
     rng = np.random.default_rng(9)
-    sizes = [(120, 200), (240, 180), (160, 160)]
     batches = [[rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes] for _ in range(3)]
     pipe = dy.ImagePipeline(e, 240, 200, depth=2, want_instance_masks=True)
     tickets = [pipe.submit(batches[0], 0.2), pipe.submit(batches[1], 0.2)]

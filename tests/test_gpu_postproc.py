@@ -137,7 +137,7 @@ def test_detect_stress_many_boxes():
     pred = O.interpret_output(yolos)
     want = O.filter_detections(pred, win, 0.05, max_detection=1000)
     n = int((want[0, :, 5] > 0).sum())
-    assert n >= 1000 or n > 300
+    assert n >= 1000, n                                        # the stress bar: >= 1,000 boxes through NMS + masks
     assert np.array_equal(raw[0, :, 4], want[0, :, 4])
     assert np.max(np.abs(raw[0] - want[0])) < 2e-5
     sm = (rng.standard_normal((1, 576, 576, 9))).astype(np.float32)
