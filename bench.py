@@ -448,6 +448,12 @@ def run_ours(args):
         eng.close()                                   # free the batch-64 inference engine first
         torch.cuda.empty_cache()
         train = train_leg(16, 'bf16', max(5, min(args.steps, 20)), 3, rank, local, world, dist)
+        # the reference's stage 2: every layer unlocked (yolo3_net_pos.py:155-156), 61.66 M trainables
+        st2 = train_leg(16, 'bf16', max(3, min(args.steps, 10)), 3, rank, local, world, dist, lock=[0] * 82)
+        train['stage2'] = dict(value=st2['value'], unit='images/s', ms_per_step=st2['ms_per_step'],
+                               trainable_params=st2['trainable_params'], buckets=st2['buckets'],
+                               allreduce_exposed_ms=st2.get('allreduce_exposed_ms'),
+                               gpu_launches_per_step=st2['gpu_launches_per_step'])
     # ---- BASELINE configs[4]: stress (rank 0, N=1) ----
     stress = None
     if not args.no_stress and rank == 0 and world == 1:
@@ -521,12 +527,12 @@ def synth_train_batch(B, rank):
     return img, labels, tb, tm, pp, pg
 
 
-def train_leg(B, precision, steps, warm, rank, local, world, dist, e2e_steps=0):
+def train_leg(B, precision, steps, warm, rank, local, world, dist, e2e_steps=0, lock=None):
     """BASELINE configs[3]: training step (forward + losses + backward + all-reduce + Adam), batch B per GPU at
     576x576, data parallel (bucketed NCCL all-reduce overlapped with backward).  Returns the result dict."""
     import torch
     import disyolo_b200 as dy
-    eng = dy.Engine(image_size=IMAGE, max_batch=B, precision=precision, device=local)
+    eng = dy.Engine(image_size=IMAGE, max_batch=B, precision=precision, device=local, lock=lock)
     eng.load_weights(dy.init_weights('lively', 0))
     tr = dy.DataParallelTrainer(eng, bucket_mb=25)
     img_h, labels_h, tb_h, tm_h, pp_h, pg_h = synth_train_batch(B, rank)
@@ -561,7 +567,8 @@ def train_leg(B, precision, steps, warm, rank, local, world, dist, e2e_steps=0):
     launches = int(eng.lib.dy_launch_count(0))
     res = dict(metric='training images/s @576^2 (fwd+losses+bwd+allreduce+Adam)', value=world * B / (ms_step / 1e3),
                unit='images/s', ms_per_step=ms_step, steps=steps, per_gpu_batch=B, n_gpus=world,
-               dtype='bf16' if precision == 'bf16' else 'f32', stage='1 (layers 53-82 trainable)',
+               dtype='bf16' if precision == 'bf16' else 'f32',
+               stage='1 (layers 53-82 trainable)' if lock is None else 'custom lock (%d layers trainable)' % lock.count(0),
                trainable_params=eng.n_train, buckets=len(tr.buckets),
                gradient_bytes=int(eng.n_train) * 4, losses=[float(v) for v in losses],
                gpu_launches_per_step=launches // max(1, steps))

@@ -71,7 +71,7 @@ SIGNATURES = {
     'dy_assign_labels': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     'dy_postproc_profile': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _F, _P, _I, _P, _P]),
     'dy_conv_layer': (C.c_int, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P]),
-    'dy_conv_backward': (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P, _P, _P]),
+    'dy_conv_backward': (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),
     'dy_train_init': (C.c_int, [_P]),
     'dy_set_loss_params': (C.c_int, [_P, _F, _F, _F, _F, _F, _F]),
     'dy_train_param_count': (C.c_int64, [_P]),

@@ -39,6 +39,23 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, const float (&v
   reinterpret_cast<uint4*>(dst)[1] = b;
 }
 
+// v[0..15] += 16 bf16 residual values (two 16-byte vectors); bf16 -> fp32 is a 16-bit shift / mask
+__device__ __forceinline__ void add_res16(float (&v)[16], const uint4& ra, const uint4& rb) {
+  const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 f = make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xFFFF0000u));
+#ifdef DY_SCALAR_EPILOGUE
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+#else
+    const float2 o = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), f);
+    v[2 * j] = o.x;
+    v[2 * j + 1] = o.y;
+#endif
+  }
+}
+
 __device__ __forceinline__ void write_out16(const ConvParams& p, const OutDesc& o, const PixelInfo& px,
                                             long long m, int gcol, const float (&v)[16]) {
   switch (o.mode) {
@@ -61,6 +78,22 @@ __device__ __forceinline__ void write_out16(const ConvParams& p, const OutDesc& 
       store16_bf16(b + (r + 1) * o.ld, v);
       store16_bf16(b + (r + Wu) * o.ld, v);
       store16_bf16(b + (r + Wu + 1) * o.ld, v);
+      break;
+    }
+    case OUT_UNS2D:
+    case OUT_UNS2D_ACC: {
+      const int Hu = 2 * p.H + 1, Wu = 2 * p.W + 1;
+      const long long r = ((long long)px.n * Hu + 2 * px.y + (o.blk >> 1)) * Wu + 2 * px.x + (o.blk & 1);
+      __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(o.ptr) + r * o.ld + gcol;
+      if (o.mode == OUT_UNS2D_ACC) {
+        float w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = v[j];
+        add_res16(w, reinterpret_cast<const uint4*>(d)[0], reinterpret_cast<const uint4*>(d)[1]);
+        store16_bf16(d, w);
+      } else {
+        store16_bf16(d, v);
+      }
       break;
     }
     case OUT_F32_COMPACT: {
@@ -122,23 +155,6 @@ __device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r
       b.x = fmaxf(tb.x, b.x); b.y = fmaxf(tb.y, b.y);
     }
     v[4 * j4 + 0] = a.x; v[4 * j4 + 1] = a.y; v[4 * j4 + 2] = b.x; v[4 * j4 + 3] = b.y;
-  }
-}
-
-// v[0..15] += 16 bf16 residual values (two 16-byte vectors); bf16 -> fp32 is a 16-bit shift / mask
-__device__ __forceinline__ void add_res16(float (&v)[16], const uint4& ra, const uint4& rb) {
-  const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float2 f = make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xFFFF0000u));
-#ifdef DY_SCALAR_EPILOGUE
-    v[2 * j] += f.x;
-    v[2 * j + 1] += f.y;
-#else
-    const float2 o = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), f);
-    v[2 * j] = o.x;
-    v[2 * j + 1] = o.y;
-#endif
   }
 }
 

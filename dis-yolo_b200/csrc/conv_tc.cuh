@@ -26,13 +26,17 @@ enum OutMode : int {
   OUT_S2D = 2,          // bf16 P1 of the space-to-depth tensor [N, H/2+1, W/2+1, 4*C]
   OUT_UP2 = 3,          // bf16 P1 of the 2x nearest-neighbour upsampled tensor [N, 2H+1, 2W+1, C]
   OUT_F32_COMPACT = 4,  // fp32 [N,H,W,cout]          (detection heads)
-  OUT_F32_PLANAR = 5    // fp32 [N,cout,H,W]          (position-sensitive score maps)
+  OUT_F32_PLANAR = 5,   // fp32 [N,cout,H,W]          (position-sensitive score maps)
+  OUT_UNS2D = 6,        // bf16 P1 [N, 2H+1, 2W+1, cout]: GEMM row (n,y,x) -> pixel (2y + blk/2, 2x + blk%2); the
+                        // inverse of OUT_S2D for ONE parity block (dgrad of a stride-2 conv, train_tc.cuh)
+  OUT_UNS2D_ACC = 7     // the same, accumulating into the destination (a second consumer's gradient)
 };
 
 struct OutDesc {
   void* ptr;
   int mode;
-  int ld;  // destination row pitch in elements
+  int ld;   // destination row pitch in elements
+  int blk;  // OUT_UNS2D*: parity block (y&1)*2 + (x&1) this launch produces
 };
 
 constexpr int kHaloRows = 136;   // 128 + 2 halo rows, rounded up to the 8-row swizzle atom

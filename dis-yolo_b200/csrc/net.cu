@@ -128,6 +128,10 @@ struct TcConvDesc {
   float alpha = 0.1f;
   const __nv_bfloat16* residual = nullptr;
   OutDesc out[2];
+  // explicit tap list (k must be 1): K = ntaps_custom * cin0, tap t reads the A rows shifted by tap_shift_custom[t]
+  // against weight K-chunks [t*cin0, (t+1)*cin0) -- the per-parity-block dgrad of a stride-2 conv
+  int ntaps_custom = 0;
+  int tap_shift_custom[4] = {0, 0, 0, 0};
   // fused 1x1 linear tail (ConvParams::fuse_*)
   int fuse_n = 0, fuse_cout = 0, fuse_store = 0;
   const __nv_bfloat16* fuse_w = nullptr;
@@ -172,7 +176,8 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   const int Hp = d.H + 1, Wp = d.W + 1;
   const long long rows_max = (long long)d.max_batch * Hp * Wp;
   const long long m_tiles = (rows_max + kBlockM - 1) / kBlockM;
-  const int K = d.k * d.k * d.cin0 + d.cin1;
+  DY_CHECK(d.ntaps_custom == 0 || (d.k == 1 && d.s == 1 && d.cin1 == 0 && d.ntaps_custom <= 4), "custom taps");
+  const int K = d.ntaps_custom ? d.ntaps_custom * d.cin0 : d.k * d.k * d.cin0 + d.cin1;
   ConvParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   plan->kchunk = kchunk;
@@ -252,7 +257,9 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
     g.tap_row[0] = 0; g.tap_b0[0] = b0;
     p.seg[ns++] = g;
   };
-  if (d.k == 1) {
+  if (d.ntaps_custom) {
+    for (int t = 0; t < d.ntaps_custom; ++t) seg1(0, d.tap_shift_custom[t], 0, cpt, t * cpt);
+  } else if (d.k == 1) {
     seg1(0, 0, 0, cpt, 0);
     if (d.cin1 > 0) seg1(1, 0, 0, d.cin1 / kchunk, cpt);
   } else if (d.s == 1) {
@@ -412,8 +419,10 @@ struct LayerState {
   __nv_bfloat16* wdg0 = nullptr;    // dgrad operand towards src0: [cin0][k*k*Cg], taps rotated by 180 degrees
   __nv_bfloat16* wdg1 = nullptr;    // dgrad operand towards src1 (concat branch, 1x1): [cin1][Cg]
   TcPlan plan_z, plan_dg0, plan_dg1;
+  TcPlan plan_dg_s2[4];             // stride-2 conv: dgrad of the four parity blocks of the space-to-depth input
   WgradPlan plan_wg;
   bool dg0 = false, dg1 = false;    // which input gradients this layer produces
+  bool dg_s2 = false;
   bool res_acc = false;             // shortcut gradient: accumulate (true) or first write (copy)
 };
 
@@ -485,6 +494,7 @@ struct dy_net {
   int* mask_assign = nullptr;
   int* mask_npos = nullptr;
   float* train_windows = nullptr;
+  const float* train_images = nullptr;   // images of the current training step (convolutional1's weight gradient)
   float* ones_dev = nullptr;       // [1024] identity scale for "conv only" passes
   float* zeros_dev = nullptr;
   __nv_bfloat16* dzb_scratch = nullptr;   // bf16 engine: dz of the layer being differentiated (P1)
@@ -1719,9 +1729,11 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
 }
 
 int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
-                     const float* w_host, int32_t k, int32_t cout, float* dx_dev, float* dw_dev, void* stream) {
+                     const float* w_host, int32_t k, int32_t stride, int32_t cout, float* dx_dev, float* dw_dev,
+                     void* stream) {
   DY_CHECK(x_dev && dz_dev && w_host && (dx_dev || dw_dev), "null argument");
   DY_CHECK(k == 1 || k == 3, "k");
+  DY_CHECK(stride == 1 || (stride == 2 && k == 3 && H % 2 == 0 && W % 2 == 0), "stride 2 needs a 3x3 kernel and even extents");
   DY_CHECK(cin % 32 == 0 && cin >= 32, "the bf16 engine needs cin % 32 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = DY_OK;
@@ -1739,14 +1751,17 @@ int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t
   int dev = 0, num_sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int Ho = H / stride, Wo = W / stride;            // dz / GEMM row space
   const int Cg = (cout + 31) / 32 * 32, K = k * k * cin;
-  const size_t rows_pad = (size_t)B * (H + 1) * (W + 1) + 64;
+  const size_t rows_in = (size_t)B * (H + 1) * (W + 1) + 64, rows_out = (size_t)B * (Ho + 1) * (Wo + 1) + 64;
   __nv_bfloat16 *d_x = nullptr, *d_dz = nullptr, *d_dx = nullptr, *d_wdg = nullptr;
   float *d_w = nullptr, *d_one = nullptr, *d_zero = nullptr;
   const int npad = cin > 1024 ? cin : 1024;
   std::vector<float> ones(npad, 1.f);
-  if ((rc = talloc((void**)&d_x, rows_pad * cin * 2)) || (rc = talloc((void**)&d_dz, rows_pad * Cg * 2)) ||
-      (rc = talloc((void**)&d_dx, rows_pad * cin * 2)) || (rc = talloc((void**)&d_wdg, (size_t)cin * k * k * Cg * 2)) ||
+  // x: P1 (stride 1) or the space-to-depth copy [B, Ho+1, Wo+1, 4*cin] (stride 2): what the forward consumed
+  const size_t x_elems = stride == 2 ? rows_out * 4 * cin : rows_in * cin;
+  if ((rc = talloc((void**)&d_x, x_elems * 2)) || (rc = talloc((void**)&d_dz, rows_out * Cg * 2)) ||
+      (rc = talloc((void**)&d_dx, rows_in * cin * 2)) || (rc = talloc((void**)&d_wdg, (size_t)cin * k * k * Cg * 2)) ||
       (rc = talloc((void**)&d_w, (size_t)K * cout * 4)) || (rc = talloc((void**)&d_one, (size_t)npad * 4)) ||
       (rc = talloc((void**)&d_zero, (size_t)npad * 4))) {
     cleanup();
@@ -1755,9 +1770,9 @@ int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t
   cudaMemcpyAsync(d_w, w_host, (size_t)K * cout * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_one, ones.data(), (size_t)npad * 4, cudaMemcpyHostToDevice, st);
   note_launch(2);
-  rc = launch_nhwc_to_p1(x_dev, d_x, B, H, W, cin, FORM_SAME, st);
-  if (rc == DY_OK) rc = launch_f32_to_p1(dz_dev, B, H, W, cout, d_dz, Cg, nullptr, st);
-  if (rc == DY_OK && dx_dev) {
+  rc = launch_nhwc_to_p1(x_dev, d_x, B, H, W, cin, stride == 2 ? FORM_S2D : FORM_SAME, st);
+  if (rc == DY_OK) rc = launch_f32_to_p1(dz_dev, B, Ho, Wo, cout, d_dz, Cg, nullptr, st);
+  if (rc == DY_OK && dx_dev && stride == 1) {
     note_launch(3);
     rc = launch_pack_dgrad_bf16(d_w, k, cin, 0, cin, cout, Cg, d_wdg, st);
     TcConvDesc c;
@@ -1770,12 +1785,37 @@ int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t
     if (rc == DY_OK) rc = run_tc_plan(plan, B, num_sms, st);
     if (rc == DY_OK) rc = launch_p1_to_nhwc(d_dx, dx_dev, B, H, W, cin, FORM_SAME, st);
   }
+  if (rc == DY_OK && dx_dev && stride == 2) {
+    // four parity-block GEMMs over the output row space, scattered into the P1 input gradient (train_init_tc)
+    note_launch(6);
+    rc = launch_pack_dgrad_s2_bf16(d_w, cin, cout, Cg, d_wdg, st);
+    static const int kRegion[4] = {0, 4, 6, 8};
+    for (int b = 0; b < 4 && rc == DY_OK; ++b) {
+      const int by = b >> 1, bx = b & 1, nkw = bx == 0 ? 2 : 1, nkh = by == 0 ? 2 : 1;
+      TcConvDesc c;
+      c.a0 = d_dz; c.cin0 = Cg; c.cout = cin; c.k = 1; c.s = 1; c.H = Ho; c.W = Wo; c.max_batch = B;
+      c.ntaps_custom = nkh * nkw;
+      for (int tt = 0; tt < c.ntaps_custom; ++tt) {
+        const int kh = by == 0 ? 2 * (tt / nkw) : 1, kw = bx == 0 ? 2 * (tt % nkw) : 1;
+        c.tap_shift_custom[tt] = -((kh >> 1) * (Wo + 1) + (kw >> 1));
+      }
+      c.wpk = d_wdg + (size_t)kRegion[b] * cin * Cg;
+      c.cout_pad = cin; c.scale = d_one; c.shift = d_zero; c.act = 0; c.alpha = 0.1f;
+      c.out[0] = OutDesc{d_dx, OUT_UNS2D, cin, b};
+      c.out[1] = OutDesc{nullptr, OUT_NONE, 0, 0};
+      TcPlan plan;
+      rc = build_tc_plan(c, num_sms, &plan);
+      if (rc == DY_OK) rc = run_tc_plan(plan, B, num_sms, st);
+    }
+    if (rc == DY_OK) rc = launch_p1_to_nhwc(d_dx, dx_dev, B, H, W, cin, FORM_SAME, st);
+  }
   if (rc == DY_OK && dw_dev) {
     note_launch();
     cudaMemsetAsync(dw_dev, 0, (size_t)K * cout * 4, st);
     WgradPlan wp;
-    rc = build_wgrad_plan(d_x, cin, nullptr, 0, d_dz, Cg, cout, k, H, W, (long long)B * (H + 1) * (W + 1), dw_dev, &wp);
-    if (rc == DY_OK) rc = run_wgrad_plan(wp, B, H, W, num_sms, st);
+    rc = build_wgrad_plan(d_x, cin, nullptr, 0, d_dz, Cg, cout, k, Ho, Wo, (long long)B * (Ho + 1) * (Wo + 1), dw_dev,
+                          &wp, stride);
+    if (rc == DY_OK) rc = run_wgrad_plan(wp, B, Ho, Wo, num_sms, st);
   }
   cleanup();
   return rc;
@@ -1835,12 +1875,8 @@ static int train_init(dy_net* net) {
     }
     if (!s.in_bwd) continue;
     if (bf16) {
-      // tensor-core engine: the backward pass differentiates stride-1 convs fed by P1 activations
-      if (d.s != 1 || d.src0 == 0 || s.need_s2d) {
-        set_error("bf16 training needs convolutional1 and the stride-2 convolutions (2, 5, 10, 27, 44) and every "
-                  "layer feeding them locked (the reference's stage 1); use precision=fp32 for a fully unlocked net");
-        return DY_ERR_UNSUPPORTED;
-      }
+      // tensor-core engine: any lock pattern -- stride-1 convs over P1 activations, stride-2 convs over the
+      // space-to-depth copies, convolutional1 (K = 27) with a CUDA-core weight gradient
       s.Cg = (C + 31) / 32 * 32;
       const size_t rows_pad = (size_t)B * (d.H + 1) * (d.H + 1) + 64;
       if (d.bn) DY_TRY(dev_alloc(net, (void**)&s.zb, rows_pad * C * 2));
@@ -1908,7 +1944,10 @@ static int train_init(dy_net* net) {
       ps.push_back(ParamSeg{s.d_bias, s.off_b, C, kL2, 0});
     }
     if (bf16) {
-      ks.push_back(PackSeg{s.d_w_f32, s.d_wpk, s.wdg0, s.wdg1, s.K, C, s.cout_pad, d.k, d.cin0, d.cin1, s.Cg, 0});
+      if (n == 1) continue;               // the stem kernel packs its fp32 weights itself
+      // (a stride-2 conv's dgrad operands have their own layout: re-packed by repack_s2 after every step)
+      ks.push_back(PackSeg{s.d_w_f32, s.d_wpk, d.s == 2 ? nullptr : s.wdg0, s.wdg1, s.K, C, s.cout_pad, d.k, d.cin0,
+                           d.cin1, s.Cg, 0});
       const int tiles = ((s.K + 31) / 32) * ((s.cout_pad + 31) / 32);
       if (tiles > net->max_pack_tiles) net->max_pack_tiles = tiles;
     }
@@ -2040,12 +2079,15 @@ static int train_backward_layer(dy_net* net, int n, int B, float* grad_flat, cud
 static int repack_tc(dy_net* net, int n, cudaStream_t st) {
   LayerState& s = net->L[n];
   const LayerDef& d = s.def;
-  if (s.unlocked) {
+  if (s.unlocked && n != 1) {
     note_launch();
     DY_TRY(launch_pack_fwd_bf16(s.d_w_f32, s.K, d.cout, s.cout_pad, s.d_wpk, st));
   }
   const float* w = s.d_w_f32;
-  if (s.wdg0) {
+  if (s.wdg0 && d.s == 2) {
+    note_launch();
+    DY_TRY(launch_pack_dgrad_s2_bf16(w, d.cin0, d.cout, s.Cg, s.wdg0, st));
+  } else if (s.wdg0) {
     note_launch();
     DY_TRY(launch_pack_dgrad_bf16(w, d.k, d.cin0 + d.cin1, 0, d.cin0, d.cout, s.Cg, s.wdg0, st));
   }
@@ -2088,23 +2130,49 @@ static int train_init_tc(dy_net* net) {
       s.res_acc = written[d.res] != 0;
       written[d.res] = 1;
     }
-    if (d.bn) {      // forward: z = conv(x), identity epilogue
+    if (d.bn && n != 1) {      // forward: z = conv(x), identity epilogue (convolutional1: the stem kernel)
       TcConvDesc c;
-      c.a0 = L[d.src0].same;
+      c.a0 = d.s == 2 ? L[d.src0].s2d : L[d.src0].same;
       c.a1 = d.src1 > 0 ? L[d.src1].up : nullptr;
       DY_CHECK(c.a0 != nullptr && (d.src1 == 0 || c.a1 != nullptr), "layer input buffer missing");
-      c.cin0 = d.cin0; c.cin1 = d.cin1; c.cout = d.cout; c.k = d.k; c.s = 1; c.H = c.W = d.H; c.max_batch = B;
+      c.cin0 = d.cin0; c.cin1 = d.cin1; c.cout = d.cout; c.k = d.k; c.s = d.s; c.H = c.W = d.H; c.max_batch = B;
       c.wpk = s.d_wpk; c.cout_pad = s.cout_pad; c.scale = net->ones_dev; c.shift = net->zeros_dev; c.act = 0;
       c.alpha = net->cfg.alpha;
       c.out[0] = OutDesc{s.zb, OUT_SAME, d.cout};
       c.out[1] = OutDesc{nullptr, OUT_NONE, 0};
       DY_TRY(build_tc_plan(c, net->num_sms, &s.plan_z));
     }
-    if (s.unlocked) {
-      DY_TRY(build_wgrad_plan(L[d.src0].same, d.cin0, d.src1 > 0 ? L[d.src1].up : nullptr, d.cin1, dz, s.Cg, d.cout,
-                              d.k, d.H, d.H, rows_max, nullptr, &s.plan_wg));
+    if (s.unlocked && n != 1) {
+      DY_TRY(build_wgrad_plan(d.s == 2 ? L[d.src0].s2d : L[d.src0].same, d.cin0, d.src1 > 0 ? L[d.src1].up : nullptr,
+                              d.cin1, dz, s.Cg, d.cout, d.k, d.H, d.H, rows_max, nullptr, &s.plan_wg, d.s));
     }
-    if (d.src0 > 0 && L[d.src0].in_bwd) {
+    if (d.src0 > 0 && L[d.src0].in_bwd && d.s == 2) {
+      // dgrad of a stride-2 conv: one GEMM per parity block of the space-to-depth input over the OUTPUT row space,
+      // A = dz shifted back by the tap's (kh>>1, kw>>1), output scattered to pixel (2y + by, 2x + bx) of the
+      // producer's P1 gradient (OUT_UNS2D); a producer with an earlier consumer accumulates
+      LayerState& t = L[d.src0];
+      DY_CHECK(t.Cg == d.cin0, "producer gradient width");
+      s.dg_s2 = true;
+      DY_TRY(dev_alloc(net, (void**)&s.wdg0, (size_t)d.cin0 * 9 * s.Cg * 2));
+      const int Wp = d.H + 1;
+      static const int kRegion[4] = {0, 4, 6, 8};
+      for (int b = 0; b < 4; ++b) {
+        const int by = b >> 1, bx = b & 1, nkw = bx == 0 ? 2 : 1, nkh = by == 0 ? 2 : 1;
+        TcConvDesc c;
+        c.a0 = dz; c.cin0 = s.Cg; c.cout = d.cin0; c.k = 1; c.s = 1; c.H = c.W = d.H; c.max_batch = B;
+        c.ntaps_custom = nkh * nkw;
+        for (int tt = 0; tt < c.ntaps_custom; ++tt) {
+          const int kh = by == 0 ? 2 * (tt / nkw) : 1, kw = bx == 0 ? 2 * (tt % nkw) : 1;
+          c.tap_shift_custom[tt] = -((kh >> 1) * Wp + (kw >> 1));
+        }
+        c.wpk = s.wdg0 + (size_t)kRegion[b] * d.cin0 * s.Cg;
+        c.cout_pad = d.cin0; c.scale = net->ones_dev; c.shift = net->zeros_dev; c.act = 0; c.alpha = net->cfg.alpha;
+        c.out[0] = OutDesc{t.dyb, written[d.src0] ? OUT_UNS2D_ACC : OUT_UNS2D, d.cin0, b};
+        c.out[1] = OutDesc{nullptr, OUT_NONE, 0, 0};
+        DY_TRY(build_tc_plan(c, net->num_sms, &s.plan_dg_s2[b]));
+      }
+      written[d.src0] = 1;
+    } else if (d.src0 > 0 && L[d.src0].in_bwd) {
       LayerState& t = L[d.src0];
       DY_CHECK(t.Cg == d.cin0, "producer gradient width");
       s.dg0 = true;
@@ -2180,14 +2248,21 @@ static int train_forward_layer_tc(dy_net* net, int n, const float* images, int B
   auto& L = net->L;
   LayerState& s = L[n];
   const LayerDef& d = s.def;
-  if (n == 1) {
+  if (n == 1 && !s.in_bwd) {
     note_launch();
     return launch_conv1(images, s.d_w_f32, s.d_scale, s.d_shift, net->cfg.alpha, B, net->S, net->S, s.s2d, s.same,
                         g_opt_conv1_tc != 0, net->num_sms, st);
   }
   // frozen prefix and the biased linear convs (bias lives in d_shift): the inference plan
-  if (!s.in_bwd || !d.bn) return run_tc_plan(s.plan, B, net->num_sms, st);
-  DY_TRY(run_tc_plan(s.plan_z, B, net->num_sms, st));
+  if (n != 1 && (!s.in_bwd || !d.bn)) return run_tc_plan(s.plan, B, net->num_sms, st);
+  if (n == 1) {
+    // trained stem: z = conv(x) through the same kernel with an identity epilogue (scale 1, shift 0, slope 1)
+    note_launch();
+    DY_TRY(launch_conv1(images, s.d_w_f32, net->ones_dev, net->zeros_dev, 1.0f, B, net->S, net->S, nullptr, s.zb,
+                        g_opt_conv1_tc != 0, net->num_sms, st));
+  } else {
+    DY_TRY(run_tc_plan(s.plan_z, B, net->num_sms, st));
+  }
   const long long rows = (long long)B * (d.H + 1) * (d.H + 1);
   const long long M = (long long)B * d.H * d.H;
   note_launch(2);
@@ -2197,10 +2272,10 @@ static int train_forward_layer_tc(dy_net* net, int n, const float* images, int B
     DY_TRY(launch_bn_stats_p1(s.zb, rows, d.cout, s.stat, s.stat + d.cout, st));
     return launch_bn_finalize_act_p1(s.zb, s.stat, s.stat + d.cout, M, s.d_gamma, s.d_beta, net->cfg.bn_eps, s.bn_a,
                                      s.bn_b, s.bmean, s.bvar, s.binvstd, res, B, d.H, d.H, d.cout, net->cfg.alpha, 1,
-                                     s.same, s.up, st);
+                                     s.same, s.up, st, s.s2d);
   }
   DY_TRY(launch_refold(s.d_gamma, s.d_beta, s.d_mean, s.d_var, net->cfg.bn_eps, d.cout, s.bn_a, s.bn_b, st));
-  return launch_bn_act_p1(s.zb, s.bn_a, s.bn_b, res, B, d.H, d.H, d.cout, net->cfg.alpha, 1, s.same, s.up, st);
+  return launch_bn_act_p1(s.zb, s.bn_a, s.bn_b, res, B, d.H, d.H, d.cout, net->cfg.alpha, 1, s.same, s.up, st, s.s2d);
 }
 
 static int train_backward_layer_tc(dy_net* net, int n, int B, float* grad_flat, cudaStream_t st) {
@@ -2235,12 +2310,18 @@ static int train_backward_layer_tc(dy_net* net, int n, int B, float* grad_flat, 
     DY_TRY(launch_f32_to_p1(s.dyf, B, d.H, d.H, C, s.dyb, s.Cg, s.unlocked ? grad_flat + s.off_b : nullptr, st));
     note_launch();
   }
-  if (s.unlocked) {
+  if (s.unlocked && n == 1) {
+    DY_CHECK(net->train_images != nullptr, "dy_train_forward has not run");
+    note_launch();
+    DY_TRY(launch_conv1_wgrad(net->train_images, net->dzb_scratch, B, d.H, d.H, grad_flat + s.off_w, st));
+  } else if (s.unlocked) {
     DY_CUDA(cudaMemsetAsync(grad_flat + s.off_w, 0, (size_t)s.K * C * 4, st));
     s.plan_wg.p.dw = grad_flat + s.off_w;
     note_launch();
     DY_TRY(run_wgrad_plan(s.plan_wg, B, d.H, d.H, net->num_sms, st));
   }
+  if (s.dg_s2)
+    for (int b = 0; b < 4; ++b) DY_TRY(run_tc_plan(s.plan_dg_s2[b], B, net->num_sms, st));
   if (s.dg0) DY_TRY(run_tc_plan(s.plan_dg0, B, net->num_sms, st));
   if (s.dg1) {
     note_launch();
@@ -2284,6 +2365,7 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
   net->last_fused = false;
   auto& L = net->L;
   const bool tc = net->cfg.precision == DY_PRECISION_BF16;
+  net->train_images = images_dev;
   if (tc) {
     for (int n = 1; n <= 82; ++n) DY_TRY(train_forward_layer_tc(net, n, images_dev, B, st));
     // only the loss kernels' fp32 targets need clearing: every bf16 gradient buffer is fully rewritten
@@ -2377,6 +2459,13 @@ int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad
   if (net->cfg.precision == DY_PRECISION_BF16) {
     note_launch(2);
     DY_TRY(launch_pack_multi(net->kseg_dev, net->n_kseg, net->max_pack_tiles, st));
+    for (int n = 2; n <= 82; ++n) {      // stride-2 convs: their per-parity-block dgrad operands
+      LayerState& s = L[n];
+      if (s.unlocked && s.dg_s2) {
+        note_launch();
+        DY_TRY(launch_pack_dgrad_s2_bf16(s.d_w_f32, s.def.cin0, s.def.cout, s.Cg, s.wdg0, st));
+      }
+    }
   }
   return user_end(net, st);      // the host-buffer pipeline must not read weights Adam is still rewriting
 }

@@ -161,7 +161,8 @@ struct BnFinalize {
 __global__ void __launch_bounds__(kT)
 bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
                  BnFinalize fin, const __nv_bfloat16* __restrict__ residual, uint32_t rows, int H, int W, int C,
-                 float alpha, int act, __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up) {
+                 float alpha, int act, __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up,
+                 __nv_bfloat16* __restrict__ out_s2d) {
   const int cv = C >> 3;
   const uint32_t Hp = H + 1, Wp = W + 1;
   const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
@@ -238,6 +239,11 @@ bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ 
         reinterpret_cast<uint4*>(out_up + (ru + 1) * C)[v] = q;
         reinterpret_cast<uint4*>(out_up + (ru + Wu) * C)[v] = q;
         reinterpret_cast<uint4*>(out_up + (ru + Wu + 1) * C)[v] = q;
+      }
+      if (out_s2d) {      // space-to-depth copy for a stride-2 consumer: [N, H/2+1, W/2+1, 4C], block (y&1)*2+(x&1)
+        const size_t Hq = H / 2 + 1, Wq = W / 2 + 1;
+        const size_t rs = ((size_t)pn[k] * Hq + (py[k] >> 1)) * Wq + (px[k] >> 1);
+        reinterpret_cast<uint4*>(out_s2d + rs * 4 * C + (((py[k] & 1) << 1) | (px[k] & 1)) * C)[v] = q;
       }
     }
   }
@@ -429,6 +435,85 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, int k, int cin_to
   }
 }
 
+// dgrad operands of a 3x3 stride-2 conv (TF 'SAME': input pixel (2oy+kh, 2ox+kw)).  In the space-to-depth view of
+// the input, parity block (by,bx) receives the taps with (kh&1, kw&1) == (by,bx): 4 / 2 / 2 / 1 taps for blocks
+// 0..3, listed kh-major.  Region of block b: [cin][ntap_b * Cg], element (ci, t*Cg + co) = w[kh_t][kw_t][ci][co]
+// (no rotation: dX[q, b] = sum_t dz[q - (kh_t>>1, kw_t>>1)] . W[tap_t]^T).  The four regions are concatenated.
+__global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, int cin, int cout, int Cg,
+                                     __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)cin * 9 * Cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // region starts (in units of cin*Cg): block 0 -> 0 (4 taps), 1 -> 4 (2), 2 -> 6 (2), 3 -> 8 (1)
+    const long long unit = (long long)cin * Cg;
+    const int u = (int)(i / unit);
+    const int b = u < 4 ? 0 : (u < 6 ? 1 : (u < 8 ? 2 : 3));
+    const int ubase = b == 0 ? 0 : (b == 1 ? 4 : (b == 2 ? 6 : 8));
+    const int nt = b == 0 ? 4 : (b == 3 ? 1 : 2);
+    const long long j = i - (long long)ubase * unit;           // offset inside the region [cin][nt*Cg]
+    const int co = (int)(j % Cg);
+    const int t = (int)((j / Cg) % nt);
+    const int ci = (int)(j / ((long long)nt * Cg));
+    const int by = b >> 1, bx = b & 1;
+    const int nkw = bx == 0 ? 2 : 1;
+    const int kh = by == 0 ? 2 * (t / nkw) : 1;
+    const int kw = bx == 0 ? 2 * (t % nkw) : 1;
+    float v = 0.f;
+    if (co < cout) v = w[((size_t)(kh * 3 + kw) * cin + ci) * cout + co];
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+// convolutional1 weight gradient (3 -> 32, 3x3 stride 1, TF 'SAME' pad 1): dW[k][c] = sum_p patch_k(p) * dz[p][c],
+// k = (kh*3+kw)*3 + ci.  K = 27 does not make a tensor-core operand; 9 GFLOP per 16 images on CUDA cores.
+// The image taps are rounded to bf16 first: that is the operand the forward's tcgen05 kernel multiplied with.
+// Block = 216 threads = 27 taps x 8 groups of 4 channels; a tile of 64 pixels is staged in shared memory.
+constexpr int kC1wPix = 64;
+__global__ void __launch_bounds__(216)
+conv1_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dz, int B, int H, int W,
+                   float* __restrict__ dw) {
+  __shared__ float s_patch[kC1wPix][28];
+  __shared__ __align__(16) float s_dz[kC1wPix][32];
+  const int k = threadIdx.x / 8, cg = threadIdx.x % 8;
+  const long long total = (long long)B * H * W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long p0 = (long long)blockIdx.x * kC1wPix; p0 < total; p0 += (long long)gridDim.x * kC1wPix) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kC1wPix * 27; i += 216) {
+      const int pp = i / 27, kk = i % 27;
+      const long long p = p0 + pp;
+      float v = 0.f;
+      if (p < total) {
+        const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
+        const int yy = y + kk / 9 - 1, xx = x + (kk / 3) % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v = __bfloat162float(__float2bfloat16(img[(((long long)n * H + yy) * W + xx) * 3 + kk % 3]));
+      }
+      s_patch[pp][kk] = v;
+    }
+    for (int i = threadIdx.x; i < kC1wPix * 32; i += 216) {
+      const int pp = i / 32, c = i % 32;
+      const long long p = p0 + pp;
+      float v = 0.f;
+      if (p < total) {
+        const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
+        v = __bfloat162float(dz[(((long long)n * (H + 1) + y) * (W + 1) + x) * 32 + c]);
+      }
+      s_dz[pp][c] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pp = 0; pp < kC1wPix; ++pp) {
+      const float a = s_patch[pp][k];
+      const float4 g = *reinterpret_cast<const float4*>(&s_dz[pp][cg * 4]);
+      acc[0] = fmaf(a, g.x, acc[0]); acc[1] = fmaf(a, g.y, acc[1]);
+      acc[2] = fmaf(a, g.z, acc[2]); acc[3] = fmaf(a, g.w, acc[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) atomicAdd(dw + k * 32 + cg * 4 + j, acc[j]);
+}
+
 __global__ void pack_fwd_multi_kernel(const PackSeg* __restrict__ segs) {
   __shared__ float tile[32][33];
   const PackSeg sg = segs[blockIdx.y];
@@ -561,7 +646,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant
         mbar_expect_tx(&full_bar[stage], tx);
         uint8_t* sa = smem_gen + (size_t)stage * stage_bytes;
         const int row = c * kWgradRows;
-        for (int j = 0; j < a_valid; ++j) tma_load_2d(sa + (size_t)j * a_box, xm, &full_bar[stage], ci0 + j * aw, row + shift);
+        const int col = p.tap_col[p.fuse_kw ? tap * 3 : tap] + ci0;
+        for (int j = 0; j < a_valid; ++j) tma_load_2d(sa + (size_t)j * a_box, xm, &full_bar[stage], col + j * aw, row + shift);
         for (int j = 0; j < b_boxes; ++j)
           tma_load_2d(sa + a_bytes + (size_t)j * b_box, &mapZ, &full_bar[stage], n0 + j * p.z_aw, row);
         if (++stage == (uint32_t)p.num_stages) {
@@ -706,13 +792,13 @@ int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, con
 
 int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, const __nv_bfloat16* residual, int B,
                      int H, int W, int C, float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up,
-                     cudaStream_t st) {
+                     cudaStream_t st, __nv_bfloat16* out_s2d) {
   const long long rows = (long long)B * (H + 1) * (W + 1);
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
   BnFinalize fin;
   memset(&fin, 0, sizeof(fin));
   bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, a, b, fin, residual, (uint32_t)rows, H, W, C, alpha, act,
-                                                     out_same, out_up);
+                                                     out_same, out_up, out_s2d);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -720,12 +806,13 @@ int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, con
 int launch_bn_finalize_act_p1(const __nv_bfloat16* z, const double* sum, const double* sumsq, long long M,
                               const float* gamma, const float* beta, float eps, float* a, float* b, float* mean,
                               float* var, float* invstd, const __nv_bfloat16* residual, int B, int H, int W, int C,
-                              float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up, cudaStream_t st) {
+                              float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up, cudaStream_t st,
+                              __nv_bfloat16* out_s2d) {
   const long long rows = (long long)B * (H + 1) * (W + 1);
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
   BnFinalize fin{sum, sumsq, gamma, beta, a, b, mean, var, invstd, M, eps};
   bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, nullptr, nullptr, fin, residual, (uint32_t)rows, H, W, C, alpha,
-                                                     act, out_same, out_up);
+                                                     act, out_same, out_up, out_s2d);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -796,6 +883,19 @@ int launch_pack_dgrad_bf16(const float* w, int k, int cin_total, int ci0, int ci
   return DY_OK;
 }
 
+int launch_pack_dgrad_s2_bf16(const float* w, int cin, int cout, int Cg, __nv_bfloat16* out, cudaStream_t st) {
+  pack_dgrad_s2_kernel<<<grid_for((long long)cin * 9 * Cg), kT, 0, st>>>(w, cin, cout, Cg, out);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
+int launch_conv1_wgrad(const float* images, const __nv_bfloat16* dz, int B, int H, int W, float* dw, cudaStream_t st) {
+  DY_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * 4, st));
+  conv1_wgrad_kernel<<<148 * 4, 216, 0, st>>>(images, dz, B, H, W, dw);
+  DY_CUDA(cudaGetLastError());
+  return DY_OK;
+}
+
 int launch_pack_multi(const PackSeg* segs_dev, int nseg, int max_tiles, cudaStream_t st) {
   if (nseg <= 0) return DY_OK;
   pack_fwd_multi_kernel<<<dim3(max_tiles, nseg), dim3(32, 8), 0, st>>>(segs_dev);
@@ -806,8 +906,9 @@ int launch_pack_multi(const PackSeg* segs_dev, int nseg, int max_tiles, cudaStre
 }
 
 int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, int c1, const __nv_bfloat16* dz,
-                     int zc, int cout, int k, int H, int W, long long rows_max, float* dw, WgradPlan* plan) {
+                     int zc, int cout, int k, int H, int W, long long rows_max, float* dw, WgradPlan* plan, int stride) {
   DY_CHECK(k == 1 || k == 3, "kernel size");
+  DY_CHECK(stride == 1 || (stride == 2 && k == 3 && c1 == 0), "stride 2 only for 3x3 without concat");
   DY_CHECK(c0 % 32 == 0 && c1 % 32 == 0 && zc % 32 == 0 && c0 > 0, "channel counts must be multiples of 32");
   DY_CHECK(c1 == 0 || k == 1, "concat only feeds 1x1 convs");
   DY_CHECK(cout <= zc, "dz must hold at least cout channels");
@@ -823,7 +924,14 @@ int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, i
   p.ntap = k * k;
   const int Wp = W + 1;
   for (int kh = 0; kh < k; ++kh)
-    for (int kw = 0; kw < k; ++kw) p.tap_shift[kh * k + kw] = k == 3 ? (kh - 1) * Wp + (kw - 1) : 0;
+    for (int kw = 0; kw < k; ++kw) {
+      if (stride == 2) {     // TF 'SAME', even input: in (2oy+kh, 2ox+kw) = s2d pixel (oy+(kh>>1), ox+(kw>>1)), block (kh&1, kw&1)
+        p.tap_shift[kh * k + kw] = (kh >> 1) * Wp + (kw >> 1);
+        p.tap_col[kh * k + kw] = (((kh & 1) << 1) | (kw & 1)) * c0;
+      } else {
+        p.tap_shift[kh * k + kw] = k == 3 ? (kh - 1) * Wp + (kw - 1) : 0;
+      }
+    }
   p.cin_total = c0 + c1;
   p.cout = cout;
   p.zc = zc;
@@ -832,7 +940,7 @@ int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, i
   // accumulators, 3 * block_n <= 512 TMEM columns) -- X and dz are read from L2 3 times instead of 9
   // Measured (ncu, batch 16): fusing wins where it keeps the N tile (dz <= 128 channels: conv81 912 -> 567 us,
   // conv78 248 -> 154 us) and loses where it would halve it (dz >= 256 channels); option value 2 forces it.
-  p.fuse_kw = (k == 3 && (g_wgrad_fuse == 2 || (g_wgrad_fuse == 1 && zc <= 128))) ? 1 : 0;
+  p.fuse_kw = (k == 3 && stride == 1 && (g_wgrad_fuse == 2 || (g_wgrad_fuse == 1 && zc <= 128))) ? 1 : 0;
   const int bn_max = p.fuse_kw ? 128 : 256;
   p.block_n = zc >= bn_max ? bn_max : zc;    // zc in {32, 64, 128, 256, 512, 1024}
   DY_CHECK(zc % p.block_n == 0 && p.block_n % p.z_aw == 0 && p.block_n % 16 == 0, "dz channel tiling");
@@ -843,7 +951,8 @@ int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, i
   if (ns > kWgradMaxStages) ns = kWgradMaxStages;
   p.num_stages = ns;
   p.dw = dw;
-  DY_TRY(make_tmap_2d(&plan->x[0], x0, rows_max, c0, c0, p.src_aw[0], a_rows));
+  const int x0_cols = stride == 2 ? 4 * c0 : c0;
+  DY_TRY(make_tmap_2d(&plan->x[0], x0, rows_max, x0_cols, x0_cols, p.src_aw[0], a_rows));
   if (c1 > 0) DY_TRY(make_tmap_2d(&plan->x[1], x1, rows_max, c1, c1, p.src_aw[1], a_rows));
   else plan->x[1] = plan->x[0];
   DY_TRY(make_tmap_2d(&plan->z, dz, rows_max, zc, zc, p.z_aw, kWgradRows));

@@ -22,13 +22,15 @@ int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* su
 // (P1 of the 2x nearest-upsampled tensor); pad pixels are never written (they stay zero)
 int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, const __nv_bfloat16* residual, int B,
                      int H, int W, int C, float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up,
-                     cudaStream_t st);
+                     cudaStream_t st, __nv_bfloat16* out_s2d = nullptr);
+// (out_s2d: the space-to-depth copy [N, H/2+1, W/2+1, 4C] a stride-2 consumer reads)
 // the same with bn_finalize fused in: a, b, mean, biased var, invstd are derived from the per-channel sums
 // (and written out for the backward pass by block 0)
 int launch_bn_finalize_act_p1(const __nv_bfloat16* z, const double* sum, const double* sumsq, long long M,
                               const float* gamma, const float* beta, float eps, float* a, float* b, float* mean,
                               float* var, float* invstd, const __nv_bfloat16* residual, int B, int H, int W, int C,
-                              float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up, cudaStream_t st);
+                              float alpha, int act, __nv_bfloat16* out_same, __nv_bfloat16* out_up, cudaStream_t st,
+                              __nv_bfloat16* out_s2d = nullptr);
 // g = dy * leaky'(z*a+b);  s1 = sum g, s2 = sum g*xhat
 int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, const float* a, const float* b,
                             const float* mean, const float* invstd, float alpha, int act, long long rows, int C,
@@ -57,6 +59,12 @@ int launch_pack_fwd_bf16(const float* w, int K, int cout, int cout_pad, __nv_bfl
 int launch_pack_dgrad_bf16(const float* w, int k, int cin_total, int ci0, int cin_sel, int cout, int Cg,
                            __nv_bfloat16* out, cudaStream_t st);
 
+// dgrad operands of a 3x3 stride-2 conv: four regions (parity blocks 0..3 with 4 / 2 / 2 / 1 taps), region b =
+// [cin][ntap_b * Cg]; starts at cin*Cg*{0, 4, 6, 8}
+int launch_pack_dgrad_s2_bf16(const float* w, int cin, int cout, int Cg, __nv_bfloat16* out, cudaStream_t st);
+// convolutional1's weight gradient [27][32] from the fp32 image and dz (P1 bf16, 32 channels); zeroes dw first
+int launch_conv1_wgrad(const float* images, const __nv_bfloat16* dz, int B, int H, int W, float* dw, cudaStream_t st);
+
 // all trained layers in ONE launch each (blockIdx.y = layer): forward operand and dgrad operands
 struct PackSeg {
   const float* w;          // fp32 master HWIO
@@ -78,6 +86,8 @@ struct WgradParams {
   int fuse_kw;         // 3x3 only: 1 = one CTA per kernel ROW, three accumulators (kw = 0,1,2) share the dz boxes
   int ntap;            // 1 or 9
   int tap_shift[9];    // pixel-row shift of X for each tap: (kh-1)*(W+1)+(kw-1)
+  int tap_col[9];      // first channel of X for each tap: 0, or the parity block ((kh&1)*2+(kw&1))*cin of the
+                       // space-to-depth source of a stride-2 conv (row shift (kh>>1)*(W+1)+(kw>>1) then)
   int cin_total;       // dW rows per tap
   int cout;            // real output channels (dW row pitch)
   int zc, z_aw;        // dz channels (multiple of 32) and its box width
@@ -92,8 +102,10 @@ struct WgradPlan {
 };
 // x0/x1: P1 activations (x1 = the materialised 2x-upsampled tensor of the concat branch or null),
 // dz: P1 gradient w.r.t. the conv output with zc channels; rows_max = max_batch*(H+1)*(W+1)
+// stride 2 (3x3, no concat): x0 is the space-to-depth copy [rows, 4*c0] the forward consumes; H, W = OUTPUT extent
 int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, int c1, const __nv_bfloat16* dz,
-                     int zc, int cout, int k, int H, int W, long long rows_max, float* dw, WgradPlan* plan);
+                     int zc, int cout, int k, int H, int W, long long rows_max, float* dw, WgradPlan* plan,
+                     int stride = 1);
 int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream_t st);
 // measurement / bring-up aid: descriptor field overrides (0 = computed value)
 void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b);

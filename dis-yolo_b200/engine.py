@@ -565,9 +565,9 @@ def conv_layer(x, w, stride, scale, shift, act, alpha=0.1, residual=None, precis
     return out
 
 
-def conv_backward(x, dz, w, want_dx=True, want_dw=True):
-    """Backward of one stride-1 conv through the tensor-core training engine (dy_conv_backward).
-    x [B,H,W,cin], dz [B,H,W,cout] cuda fp32, w HWIO numpy -> (dx [B,H,W,cin], dw [k,k,cin,cout])."""
+def conv_backward(x, dz, w, want_dx=True, want_dw=True, stride=1):
+    """Backward of one conv through the tensor-core training engine (dy_conv_backward), stride 1 or 2 (TF 'SAME').
+    x [B,H,W,cin], dz [B,H/stride,W/stride,cout] cuda fp32, w HWIO numpy -> (dx [B,H,W,cin], dw [k,k,cin,cout])."""
     import torch
     lib = _lib.lib()
     _lib.require_gpu()
@@ -579,6 +579,6 @@ def conv_backward(x, dz, w, want_dx=True, want_dw=True):
     dw = torch.zeros((k, k, cin, cout), dtype=torch.float32, device=x.device) if want_dw else None
     with torch.cuda.device(x.device):
         st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        _lib.check(lib.dy_conv_backward(_ptr(x), _ptr(dz), B, H, W, cin, w.ctypes.data_as(C.c_void_p), k, cout,
-                                        _ptr(dx), _ptr(dw), st), 'dy_conv_backward')
+        _lib.check(lib.dy_conv_backward(_ptr(x), _ptr(dz), B, H, W, cin, w.ctypes.data_as(C.c_void_p), k, int(stride),
+                                        cout, _ptr(dx), _ptr(dw), st), 'dy_conv_backward')
     return dx, dw

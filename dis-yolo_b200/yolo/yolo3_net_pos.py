@@ -96,10 +96,10 @@ class YOLONet(object):
         self.evaluation = Handle('evaluation', 'fetch')
 
         if precision is None:
-            # The tensor-core (bf16) training step differentiates layers 53..82 (the reference's stage 1:
-            # backbone locked, yolo3_net_pos.py:155-156); a net with unlocked backbone layers trains on
-            # the fp32 engine.
-            precision = 'bf16' if (not training or all(self.lock[:52])) else 'fp32'
+            # inference and training both run on the tensor-core (bf16) engine, whatever the lock pattern: the
+            # reference's stage 1 (backbone locked) and stage 2 ("lock=False for all layers", :155-156);
+            # precision='fp32' selects the CUDA-core verification engine
+            precision = 'bf16'
         dev = int(cfg.GPU) if device is None else int(device)
         if int(cfg.MAX_BOX_PER_IMAGE) != 20:
             # true_boxes [B,1,1,1,20,5] / true_masks [B,20,H,W] (:56-57): the loss kernels are compiled for 20

@@ -243,13 +243,15 @@ int dy_conv_layer(int32_t precision, const float* x_dev, int32_t B, int32_t H, i
                   const float* shift_host, int32_t act, float alpha, const float* residual_dev, float* out_dev,
                   void* stream);
 
-/* Backward of one stride-1 convolution through the tensor-core training engine (what TF's autodiff
- * emits for tf.nn.conv2d, yolo3_net_pos.py:125,142: Conv2DBackpropInput / Conv2DBackpropFilter):
- * x [B,H,W,cin], dz [B,H,W,cout] fp32 NHWC (device), w HWIO (host) ->
+/* Backward of one convolution through the tensor-core training engine (what TF's autodiff emits for
+ * tf.nn.conv2d, yolo3_net_pos.py:125,142: Conv2DBackpropInput / Conv2DBackpropFilter), stride 1 or 2 with
+ * TensorFlow 'SAME' padding (stride 2: 3x3 kernel, even extents -- the five down-sampling convs):
+ * x [B,H,W,cin], dz [B,H/stride,W/stride,cout] fp32 NHWC (device), w HWIO (host) ->
  * dx [B,H,W,cin] fp32 NHWC (device, may be NULL), dw [k,k,cin,cout] fp32 (device, may be NULL).
  * bf16 operands, fp32 accumulation.  Used by the per-layer gradient parity tests. */
 int dy_conv_backward(const float* x_dev, const float* dz_dev, int32_t B, int32_t H, int32_t W, int32_t cin,
-                     const float* w_host, int32_t k, int32_t cout, float* dx_dev, float* dw_dev, void* stream);
+                     const float* w_host, int32_t k, int32_t stride, int32_t cout, float* dx_dev, float* dw_dev,
+                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training step.  Replaces sess.run([net.total_loss, optimizer], feed_dict) of

@@ -27,6 +27,36 @@ CASES = [
 ]
 
 
+# the five down-sampling convs (3x3 stride 2, TF 'SAME' = pad 0 before / 1 after on even extents): wgrad over the
+# space-to-depth copy of the input, dgrad as four parity-block GEMMs scattered back (OUT_UNS2D)
+CASES_S2 = [
+    (2, 32, 32, 32, 64),           # conv2 (32-channel source, SWIZZLE_64B boxes)
+    (2, 24, 24, 64, 128),          # conv5
+    (1, 20, 12, 128, 256),         # conv10, non-square
+    (3, 12, 12, 256, 512),         # conv27
+    (2, 8, 8, 512, 1024),          # conv44
+]
+
+
+@pytest.mark.parametrize('case', CASES_S2, ids=lambda c: 'B%d_%dx%d_%d-%d_s2' % c)
+def test_conv_backward_stride2_tc(case):
+    import torch
+    import disyolo_b200.engine as E
+    B, H, W, cin, cout = case
+    rng = np.random.default_rng(sum(case))
+    x = bf16_round(rng.standard_normal((B, H, W, cin)).astype(np.float32))
+    dz = bf16_round((rng.standard_normal((B, H // 2, W // 2, cout)) * 0.1).astype(np.float32))
+    w = bf16_round((rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32))
+    dx_ref, dw_ref = T.conv_backward(x, dz, w, stride=2)
+    dx, dw = E.conv_backward(torch.from_numpy(x).cuda(), torch.from_numpy(dz).cuda(), w, stride=2)
+    torch.cuda.synchronize()
+    e_dw = rel_err(dw.cpu().numpy(), dw_ref)
+    e_dx = rel_err(dx.cpu().numpy(), dx_ref)
+    print('stride 2: dw rel err %.3g  dx rel err %.3g' % (e_dw, e_dx))
+    assert e_dw < 2e-3, 'wgrad rel err %.3g' % e_dw
+    assert e_dx < 1e-2, 'dgrad rel err %.3g' % e_dx
+
+
 @pytest.mark.parametrize('case', CASES, ids=lambda c: 'B%d_%dx%d_%d-%d_k%d' % c)
 def test_conv_backward_tc(case):
     import torch
