@@ -669,7 +669,8 @@ def run_train(args):
         dist = None
     B = args.batch if args.batch != PER_GPU_BATCH else 16
     steps, warm = max(1, args.steps), max(3, args.warmup)
-    res = train_leg(B, args.train_precision, steps, warm, rank, local, world, dist, e2e_steps=max(2, min(steps, 5)))
+    res = train_leg(B, args.train_precision, steps, warm, rank, local, world, dist, e2e_steps=max(2, min(steps, 5)),
+                    lock=[0] * 82 if args.train_stage == 2 else None)
     if rank == 0:
         e2e = res.pop('e2e')
         print(json.dumps(dict(metric=res.pop('metric'), value=res.pop('value'), unit='images/s', n_gpus=world,
@@ -698,6 +699,8 @@ def main():
     ap.add_argument('--workload', default='inference', choices=['inference', 'train'])
     ap.add_argument('--train-precision', default='bf16', choices=['bf16', 'fp32'],
                     help='training engine: bf16 = tcgen05 dgrad/wgrad (mixed precision), fp32 = verification engine')
+    ap.add_argument('--train-stage', type=int, default=1, choices=[1, 2],
+                    help='--workload train: 1 = layers 53-82 trainable (reference stage 1), 2 = every layer unlocked')
     ap.add_argument('--traffic', type=float, default=None,
                     help='DRAM bytes per step of the conv kernel (sum over its launches) from an ncu launch list of '
                          'THIS build (profiles/); omitted -> roofline.traffic is null (never a stale constant)')

@@ -14,12 +14,12 @@ PyTorch is used only for device/pinned buffers and streams.  There is no CPU fal
 works anywhere, but constructing a net without the built library or without a GPU raises.
 """
 from . import _lib                                    # noqa: F401
-from .engine import Engine, layer_table               # noqa: F401
+from .engine import Engine, TrainData, layer_table    # noqa: F401
 from .weights import init_weights, save_npz, load_npz, variable_names  # noqa: F401
 from .yolo.yolo3_net_pos import YOLONet, Session, AdamOptimizer      # noqa: F401
 from .parallel import DataParallelTrainer, plan_buckets, BucketedAllReduce   # noqa: F401
 from .pipeline import ImagePipeline                   # noqa: F401
 from . import tf_checkpoint                           # noqa: F401
 
-__all__ = ['Engine', 'ImagePipeline', 'YOLONet', 'Session', 'AdamOptimizer', 'DataParallelTrainer', 'plan_buckets', 'init_weights', 'save_npz', 'load_npz',
+__all__ = ['Engine', 'TrainData', 'ImagePipeline', 'YOLONet', 'Session', 'AdamOptimizer', 'DataParallelTrainer', 'plan_buckets', 'init_weights', 'save_npz', 'load_npz',
            'variable_names', 'layer_table']

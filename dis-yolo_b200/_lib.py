@@ -69,6 +69,14 @@ SIGNATURES = {
     'dy_postprocess_batch': (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'dy_mask_overlaps': (C.c_int, [_P, _I, _P, _I, C.c_int64, _P, _P]),
     'dy_assign_labels': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    'dy_polygon_masks': (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    'dy_mask_boxes': (C.c_int, [_P, _I, _I, _I, _P, _P]),
+    'dy_augment_image': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'dy_augment_masks': (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    'dy_salt_pepper': (C.c_int, [_P, _I, _P, _I, _P, _I, _P]),
+    'dy_change_light': (C.c_int, [_P, C.c_int64, C.c_double, _P]),
+    'dy_motion_blur3': (C.c_int, [_P, _I, _P, _P, _P]),
+    'dy_u8_to_unit_float': (C.c_int, [_P, _P, C.c_int64, _P]),
     'dy_postproc_profile': (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _F, _P, _I, _P, _P]),
     'dy_conv_layer': (C.c_int, [_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P]),
     'dy_conv_backward': (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P]),

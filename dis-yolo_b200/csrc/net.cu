@@ -17,6 +17,7 @@
 #include "train.cuh"
 #include "train_tc.cuh"
 #include "imgproc.cuh"
+#include "augment.cuh"
 
 namespace dy {
 
@@ -1585,6 +1586,69 @@ int dy_assign_labels(dy_net* net, const float* boxes_dev, const int32_t* nbox_de
   a.B = B; a.max_box = max_box; a.num_class = net->cfg.num_classes; a.net = net->S;
   note_launch();
   return launch_assign_labels(a, (cudaStream_t)stream);
+}
+
+// ---- training data pipeline on the device (utils/train_data.py) ----------------------
+int dy_polygon_masks(const double* verts_dev, const int32_t* poly_dev, const int32_t* inst_dev, int32_t n_inst,
+                     int32_t h, int32_t w, uint8_t* masks_dev, void* stream) {
+  DY_CHECK(verts_dev && poly_dev && inst_dev && masks_dev, "null argument");
+  note_launch();
+  return launch_polygon_masks(verts_dev, poly_dev, inst_dev, n_inst, h, w, masks_dev, (cudaStream_t)stream);
+}
+
+int dy_mask_boxes(const uint8_t* masks_dev, int32_t n, int32_t h, int32_t w, int32_t* boxes_dev, void* stream) {
+  DY_CHECK(masks_dev && boxes_dev, "null argument");
+  note_launch(3);
+  return launch_mask_boxes(masks_dev, n, h, w, boxes_dev, (cudaStream_t)stream);
+}
+
+static PlaceGeom place_geom(int32_t h, int32_t w, int32_t image_size, int32_t new_w, int32_t new_h, int32_t dx, int32_t dy_,
+                            int32_t flip) {
+  PlaceGeom g;
+  g.src_h = h; g.src_w = w; g.new_w = new_w; g.new_h = new_h; g.dx = dx; g.dy = dy_; g.size = image_size; g.flip = flip;
+  return g;
+}
+
+int dy_augment_image(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_size, int32_t new_w, int32_t new_h,
+                     int32_t dx, int32_t dy_, int32_t flip, uint8_t* out_dev, void* stream) {
+  DY_CHECK(rgb_dev && out_dev, "null argument");
+  note_launch();
+  return launch_place_image_u8(rgb_dev, place_geom(h, w, image_size, new_w, new_h, dx, dy_, flip), out_dev,
+                               (cudaStream_t)stream);
+}
+
+int dy_augment_masks(const uint8_t* masks_dev, int32_t n, int32_t h, int32_t w, int32_t image_size, int32_t new_w,
+                     int32_t new_h, int32_t dx, int32_t dy_, int32_t flip, uint8_t* out_dev, void* stream) {
+  DY_CHECK(masks_dev && out_dev, "null argument");
+  note_launch();
+  return launch_place_masks(masks_dev, n, place_geom(h, w, image_size, new_w, new_h, dx, dy_, flip), out_dev,
+                            (cudaStream_t)stream);
+}
+
+int dy_salt_pepper(uint8_t* img_dev, int32_t image_size, const int32_t* salt_rc_dev, int32_t n_salt,
+                   const int32_t* pepper_rc_dev, int32_t n_pepper, void* stream) {
+  DY_CHECK(img_dev && (n_salt == 0 || salt_rc_dev) && (n_pepper == 0 || pepper_rc_dev), "null argument");
+  DY_CHECK(n_salt >= 0 && n_pepper >= 0 && image_size >= 1, "counts");
+  note_launch(2);
+  return launch_salt_pepper(img_dev, image_size, salt_rc_dev, n_salt, pepper_rc_dev, n_pepper, (cudaStream_t)stream);
+}
+
+int dy_change_light(uint8_t* img_dev, int64_t npix, double coeff, void* stream) {
+  DY_CHECK(img_dev, "null argument");
+  note_launch();
+  return launch_change_light(img_dev, npix, coeff, (cudaStream_t)stream);
+}
+
+int dy_motion_blur3(const uint8_t* img_dev, int32_t image_size, const float* kernel9_host, uint8_t* out_dev, void* stream) {
+  DY_CHECK(img_dev && kernel9_host && out_dev && img_dev != out_dev, "null / aliased argument");
+  note_launch();
+  return launch_motion_blur3(img_dev, image_size, kernel9_host, out_dev, (cudaStream_t)stream);
+}
+
+int dy_u8_to_unit_float(const uint8_t* src_dev, float* dst_dev, int64_t n, void* stream) {
+  DY_CHECK(src_dev && dst_dev && n >= 1, "null argument");
+  note_launch();
+  return launch_u8_div255_f32(src_dev, dst_dev, n, (cudaStream_t)stream);
 }
 
 // CRC-32C (Castagnoli), slicing-by-8: checksums of TensorFlow checkpoint-V2 bundles (tf_checkpoint.py).

@@ -467,44 +467,47 @@ __global__ void pack_dgrad_s2_kernel(const float* __restrict__ w, int cin, int c
 // convolutional1 weight gradient (3 -> 32, 3x3 stride 1, TF 'SAME' pad 1): dW[k][c] = sum_p patch_k(p) * dz[p][c],
 // k = (kh*3+kw)*3 + ci.  K = 27 does not make a tensor-core operand; 9 GFLOP per 16 images on CUDA cores.
 // The image taps are rounded to bf16 first: that is the operand the forward's tcgen05 kernel multiplied with.
-// Block = 216 threads = 27 taps x 8 groups of 4 channels; a tile of 64 pixels is staged in shared memory.
+// A block works on segments of kC1wPix pixels of one image row: the three image rows it needs (with a one-pixel
+// halo, zero outside the image) and the dz segment are staged once, coalesced, and every patch element is then a
+// direct shared-memory read -- no per-element index arithmetic.  216 threads = 27 taps x 8 groups of 4 channels,
+// fp32 partial sums in registers across all of the block's segments, one atomic per (tap, channel) per block.
 constexpr int kC1wPix = 64;
 __global__ void __launch_bounds__(216)
 conv1_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dz, int B, int H, int W,
                    float* __restrict__ dw) {
-  __shared__ float s_patch[kC1wPix][28];
+  __shared__ float s_img[3][(kC1wPix + 2) * 3];
   __shared__ __align__(16) float s_dz[kC1wPix][32];
   const int k = threadIdx.x / 8, cg = threadIdx.x % 8;
-  const long long total = (long long)B * H * W;
+  const int kh = k / 9, koff = k % 9;                    // patch_k(x) = s_img[kh][x*3 + (kw*3 + ci)], kw*3+ci = k % 9
+  const int segs_per_row = (W + kC1wPix - 1) / kC1wPix;
+  const long long nseg = (long long)B * H * segs_per_row;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long p0 = (long long)blockIdx.x * kC1wPix; p0 < total; p0 += (long long)gridDim.x * kC1wPix) {
+  for (long long sg = blockIdx.x; sg < nseg; sg += gridDim.x) {
+    const int x0 = (int)(sg % segs_per_row) * kC1wPix;
+    const int y = (int)((sg / segs_per_row) % H), n = (int)(sg / ((long long)segs_per_row * H));
+    const int npx = min(kC1wPix, W - x0);
     __syncthreads();
-    for (int i = threadIdx.x; i < kC1wPix * 27; i += 216) {
-      const int pp = i / 27, kk = i % 27;
-      const long long p = p0 + pp;
+    for (int i = threadIdx.x; i < 3 * (kC1wPix + 2) * 3; i += 216) {
+      const int r = i / ((kC1wPix + 2) * 3), e = i % ((kC1wPix + 2) * 3);
+      const int yy = y + r - 1, xx = x0 - 1 + e / 3;
       float v = 0.f;
-      if (p < total) {
-        const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
-        const int yy = y + kk / 9 - 1, xx = x + (kk / 3) % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-          v = __bfloat162float(__float2bfloat16(img[(((long long)n * H + yy) * W + xx) * 3 + kk % 3]));
-      }
-      s_patch[pp][kk] = v;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+        v = __bfloat162float(__float2bfloat16(__ldg(img + (((long long)n * H + yy) * W + xx) * 3 + e % 3)));
+      s_img[r][e] = v;
     }
-    for (int i = threadIdx.x; i < kC1wPix * 32; i += 216) {
-      const int pp = i / 32, c = i % 32;
-      const long long p = p0 + pp;
-      float v = 0.f;
-      if (p < total) {
-        const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((long long)W * H));
-        v = __bfloat162float(dz[(((long long)n * (H + 1) + y) * (W + 1) + x) * 32 + c]);
-      }
-      s_dz[pp][c] = v;
+    const __nv_bfloat16* zrow = dz + (((long long)n * (H + 1) + y) * (W + 1) + x0) * 32;
+    for (int i = threadIdx.x; i < kC1wPix * 4; i += 216) {      // 16-byte vectors: 8 channels each
+      const int pp = i >> 2, v8 = i & 3;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (pp < npx) unpack8(__ldg(reinterpret_cast<const uint4*>(zrow + (size_t)pp * 32) + v8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_dz[pp][v8 * 8 + j] = f[j];
     }
     __syncthreads();
-#pragma unroll 8
+    const float* prow = &s_img[kh][koff];
+#pragma unroll 16
     for (int pp = 0; pp < kC1wPix; ++pp) {
-      const float a = s_patch[pp][k];
+      const float a = prow[pp * 3];
       const float4 g = *reinterpret_cast<const float4*>(&s_dz[pp][cg * 4]);
       acc[0] = fmaf(a, g.x, acc[0]); acc[1] = fmaf(a, g.y, acc[1]);
       acc[2] = fmaf(a, g.z, acc[2]); acc[3] = fmaf(a, g.w, acc[3]);
@@ -891,7 +894,7 @@ int launch_pack_dgrad_s2_bf16(const float* w, int cin, int cout, int Cg, __nv_bf
 
 int launch_conv1_wgrad(const float* images, const __nv_bfloat16* dz, int B, int H, int W, float* dw, cudaStream_t st) {
   DY_CUDA(cudaMemsetAsync(dw, 0, 27 * 32 * 4, st));
-  conv1_wgrad_kernel<<<148 * 4, 216, 0, st>>>(images, dz, B, H, W, dw);
+  conv1_wgrad_kernel<<<148 * 8, 216, 0, st>>>(images, dz, B, H, W, dw);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

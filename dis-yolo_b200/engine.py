@@ -536,6 +536,120 @@ class Engine(object):
         return ys[0], ys[1], ys[2], tb
 
 
+# ---- the training data pipeline on the device (utils/train_data.py) ---------------------------------
+class TrainData(object):
+    """Device side of defect_train.get() for ONE image (utils/train_data.py:44-276): polygons -> masks -> boxes,
+    random scale / crop / flip of image and masks, noise / light / blur, / 255.  The caller makes the reference's
+    random draws (scale_crop, flip, bnl and the draws inside the three effects) and passes them in; label
+    assignment is Engine.assign_labels.  All arrays are CUDA tensors; nothing is computed on the host."""
+
+    def __init__(self, image_size=576, device=0):
+        import torch
+        self.t, self.lib, self.S = torch, _lib.lib(), int(image_size)
+        _lib.require_gpu()
+        self.device = torch.device('cuda', int(device))
+
+    def _st(self):
+        return C.c_void_p(self.t.cuda.current_stream(self.device).cuda_stream)
+
+    def _u8(self, x):
+        t = self.t
+        x = x if isinstance(x, t.Tensor) else t.from_numpy(np.ascontiguousarray(x).astype(np.uint8, copy=False))
+        return x.to(self.device).to(t.uint8).contiguous()
+
+    def polygon_masks(self, polygons, h, w):
+        """load_mask (:321-338).  polygons: per instance a list of {'type', 'all_points_x', 'all_points_y'} (VIA
+        shape_attributes) -> uint8 cuda tensor [n_inst, h, w]."""
+        t = self.t
+        verts, poly, inst = [], [], [0]
+        for each_instance in polygons:
+            for p in each_instance:
+                poly.append((len(verts), len(p['all_points_x']), 1 if p['type'] == 'out' else 0))
+                verts += list(zip(p['all_points_x'], p['all_points_y']))
+            inst.append(len(poly))
+        n = len(polygons)
+        out = t.empty((n, h, w), dtype=t.uint8, device=self.device)
+        if n == 0:
+            return out
+        v = t.tensor(verts if verts else [(0, 0)], dtype=t.float64, device=self.device)
+        pl = t.tensor(poly if poly else [(0, 0, 0)], dtype=t.int32, device=self.device)
+        it = t.tensor(inst, dtype=t.int32, device=self.device)
+        _lib.check(self.lib.dy_polygon_masks(_ptr(v), _ptr(pl), _ptr(it), n, int(h), int(w), _ptr(out), self._st()),
+                   'dy_polygon_masks')
+        return out
+
+    def mask_boxes(self, masks):
+        """extract_bboxes (:358-374) for every mask: int32 [n,4] (x1,y1,x2,y2), zeros for an empty mask."""
+        t = self.t
+        masks = self._u8(masks)
+        n, h, w = [int(v) for v in masks.shape]
+        out = t.empty((n, 4), dtype=t.int32, device=self.device)
+        _lib.check(self.lib.dy_mask_boxes(_ptr(masks), n, h, w, _ptr(out), self._st()), 'dy_mask_boxes')
+        return out
+
+    def place_image(self, image, new_w, new_h, dx, dy, flip=1):
+        """apply_random_scale_and_crop(mode='image') + flip: uint8 [h,w,3] -> uint8 [S,S,3]."""
+        t = self.t
+        image = self._u8(image)
+        h, w = int(image.shape[0]), int(image.shape[1])
+        out = t.empty((self.S, self.S, 3), dtype=t.uint8, device=self.device)
+        _lib.check(self.lib.dy_augment_image(_ptr(image), h, w, self.S, int(new_w), int(new_h), int(dx), int(dy),
+                                             int(flip), _ptr(out), self._st()), 'dy_augment_image')
+        return out
+
+    def place_masks(self, masks, new_w, new_h, dx, dy, flip=1):
+        """resize_mask (:403-421): uint8 / bool [n,h,w] -> uint8 (0/1) [n,S,S]."""
+        t = self.t
+        masks = self._u8(masks)
+        n, h, w = [int(v) for v in masks.shape]
+        out = t.empty((n, self.S, self.S), dtype=t.uint8, device=self.device)
+        if n:
+            _lib.check(self.lib.dy_augment_masks(_ptr(masks), n, h, w, self.S, int(new_w), int(new_h), int(dx), int(dy),
+                                                 int(flip), _ptr(out), self._st()), 'dy_augment_masks')
+        return out
+
+    def salt_pepper(self, image, salt_rc, pepper_rc):
+        """add_salt_pepper_noise (:494-509), in place on a uint8 [S,S,3] cuda tensor; *_rc int32 [n,2] (row, col)."""
+        t = self.t
+        s = t.as_tensor(np.ascontiguousarray(salt_rc, np.int32)).to(self.device).contiguous()
+        p = t.as_tensor(np.ascontiguousarray(pepper_rc, np.int32)).to(self.device).contiguous()
+        _lib.check(self.lib.dy_salt_pepper(_ptr(image), int(image.shape[0]), _ptr(s), int(s.shape[0]), _ptr(p),
+                                           int(p.shape[0]), self._st()), 'dy_salt_pepper')
+        return image
+
+    def change_light(self, image, coeff):
+        """change_light (:511-521), in place on a uint8 [...,3] cuda tensor."""
+        _lib.check(self.lib.dy_change_light(_ptr(image), int(image.numel() // 3), float(coeff), self._st()),
+                   'dy_change_light')
+        return image
+
+    def motion_blur3(self, image, kernel):
+        """linearmotion_blur3C (:452-481) with the 3x3 line kernel pyblur builds (numpy [3,3] float32)."""
+        k = np.ascontiguousarray(kernel, np.float32).reshape(9)
+        out = self.t.empty_like(image)
+        _lib.check(self.lib.dy_motion_blur3(_ptr(image), int(image.shape[0]), k.ctypes.data_as(C.c_void_p), _ptr(out),
+                                            self._st()), 'dy_motion_blur3')
+        return out
+
+    def to_unit_float(self, image):
+        """image.astype(np.float32) / 255.0 (:399-400)."""
+        out = self.t.empty(image.shape, dtype=self.t.float32, device=self.device)
+        _lib.check(self.lib.dy_u8_to_unit_float(_ptr(image), _ptr(out), int(image.numel()), self._st()),
+                   'dy_u8_to_unit_float')
+        return out
+
+    def image_read(self, image, new_w, new_h, dx, dy, flip, bnl, salt_rc=None, pepper_rc=None, coeff=None, kernel=None):
+        """image_read (:376-401): place + flip, then bnl 1 none / 2 salt & pepper / 3 light / 4 motion blur, / 255."""
+        im = self.place_image(image, new_w, new_h, dx, dy, flip)
+        if bnl == 2:
+            im = self.salt_pepper(im, salt_rc, pepper_rc)
+        elif bnl == 3:
+            im = self.change_light(im, coeff)
+        elif bnl == 4:
+            im = self.motion_blur3(im, kernel)
+        return self.to_unit_float(im)
+
+
 def set_option(name, value):
     """dy_set_option: planning overrides of the conv engine ('tc_resident', 'tc_halo'; -1 = auto)."""
     _lib.check(_lib.lib().dy_set_option(name.encode(), int(value)), 'dy_set_option')

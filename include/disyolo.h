@@ -224,6 +224,39 @@ int dy_assign_labels(dy_net* net, const float* boxes_dev, const int32_t* nbox_de
                      const int32_t* flip_dev, int32_t B, int32_t max_box, float* yolo3_dev, float* yolo2_dev,
                      float* yolo1_dev, float* true_boxes_dev, void* stream);
 
+/* ---- the training data pipeline on the device (utils/train_data.py) -----------------
+ * Every random draw of the reference (np.random in get(), add_salt_pepper_noise, change_light,
+ * linearmotion_blur3C) is an ARGUMENT: the host draws, the device executes.
+ * dy_polygon_masks  load_mask (:321-338): the VIA polygons of one image -> one byte mask per instance.
+ *     verts [nv,2] float64 (x, y); poly [np,3] int32 = (first vertex, vertex count, type: 1 = 'out', 0 = an inner
+ *     background region); inst [n_inst+1] int32 = polygon range of each instance.  A polygon fills the pixels
+ *     skimage.draw.polygon returns (interior + boundary, O'Rourke's test) with 1 ('out') or 0, then sets its
+ *     vertices to 1, in annotation order.
+ * dy_mask_boxes     extract_bboxes (:358-374): (x1, y1, x2, y2) int32 per mask, x2 / y2 one past the last set pixel;
+ *     (0,0,0,0) for an empty mask (load_box skips those).
+ * dy_augment_image  apply_random_scale_and_crop (:423-450, mode 'image') + the flip of image_read (:388-393):
+ *     cv2.resize(uint8, (new_w,new_h), INTER_LINEAR) bit for bit, placed at (dx,dy) in a 127-filled
+ *     image_size square (negative offsets crop), flip 1 none / 2 columns reversed / 3 rows reversed.
+ * dy_augment_masks  the same for n byte masks as resize_mask does it (:403-421): float32 bilinear, pad 0,
+ *     flip, np.around -> bool.
+ * dy_salt_pepper    add_salt_pepper_noise (:494-509): all channels of the (row, col) pairs set to 1, then to 0.
+ * dy_change_light   change_light (:511-521): cv2 RGB->HLS, L = min(L*coeff, 255) truncated, HLS->RGB; in place.
+ * dy_motion_blur3   linearmotion_blur3C (:452-481) for the 3x3 line kernel pyblur builds (9 floats, host):
+ *     per channel scipy.signal.convolve2d(float32, kernel, 'same', fillvalue=255).astype(uint8).
+ * dy_u8_to_unit_float  image.astype(np.float32) / 255.0 (:399-400). */
+int dy_polygon_masks(const double* verts_dev, const int32_t* poly_dev, const int32_t* inst_dev, int32_t n_inst,
+                     int32_t h, int32_t w, uint8_t* masks_dev, void* stream);
+int dy_mask_boxes(const uint8_t* masks_dev, int32_t n, int32_t h, int32_t w, int32_t* boxes_dev, void* stream);
+int dy_augment_image(const uint8_t* rgb_dev, int32_t h, int32_t w, int32_t image_size, int32_t new_w, int32_t new_h,
+                     int32_t dx, int32_t dy, int32_t flip, uint8_t* out_dev, void* stream);
+int dy_augment_masks(const uint8_t* masks_dev, int32_t n, int32_t h, int32_t w, int32_t image_size, int32_t new_w,
+                     int32_t new_h, int32_t dx, int32_t dy, int32_t flip, uint8_t* out_dev, void* stream);
+int dy_salt_pepper(uint8_t* img_dev, int32_t image_size, const int32_t* salt_rc_dev, int32_t n_salt,
+                   const int32_t* pepper_rc_dev, int32_t n_pepper, void* stream);
+int dy_change_light(uint8_t* img_dev, int64_t npix, double coeff, void* stream);
+int dy_motion_blur3(const uint8_t* img_dev, int32_t image_size, const float* kernel9_host, uint8_t* out_dev, void* stream);
+int dy_u8_to_unit_float(const uint8_t* src_dev, float* dst_dev, int64_t n, void* stream);
+
 /* Measurement aid for bench.py: device milliseconds of each post-processing kernel (decode+threshold,
  * per-class NMS, top-k/finalize, mask assembly), each launched `reps` times back to back between two
  * CUDA events on `stream`; ms_host[4] receives the per-launch averages.  Same inputs as dy_detect +
