@@ -148,6 +148,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap mapImg, const __grid_constan
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_sc[32], s_sh[32];
 
+  pdl_launch_dependents();            // convolutional2's CTAs may take over SMs as this grid's CTAs retire
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x < 32) {
     s_sc[threadIdx.x] = __ldg(scale + threadIdx.x);

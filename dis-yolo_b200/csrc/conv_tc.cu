@@ -283,6 +283,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __shared__ uint32_t tap_a16[kMaxSeg][3];                        // A start offset inside the stage, >>4
   __shared__ uint32_t tap_b16[kMaxSeg][3];                        // B start (absolute if resident, else in-stage), >>4
 
+  pdl_launch_dependents();            // the next layer's CTAs may take over SMs as this grid's CTAs retire
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t b_bytes = (uint32_t)p.block_n * KCHUNK * 2;            // one weight K chunk
@@ -352,6 +353,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
+  // from here on this grid reads what that layer wrote
+  pdl_wait();
 
   if (warp == 0 || (warp == 2 && p.dual_issue && p.dual_producer)) {
     // ================================ TMA producers ================================
@@ -871,9 +875,13 @@ int conv_tc_pick_stages(int kchunk, const ConvParams& p) {
   return s;
 }
 
+static int g_conv_pdl = 1;
+void conv_tc_set_pdl(int on) { g_conv_pdl = on; }
+
 int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                    const CUtensorMap& r, const CUtensorMap& o, const ConvParams& p, int num_sms,
                    cudaStream_t stream) {
+  const bool pdl = g_conv_pdl != 0;
   DY_CHECK(kchunk == 64 || kchunk == 32, "kchunk");
   DY_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n");
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
@@ -902,21 +910,21 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32f = true;
     }
-    conv_tc_kernel<32, true><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, true>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
   } else if (kchunk == 64) {
     static bool attr64 = false;
     if (!attr64) {
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr64 = true;
     }
-    conv_tc_kernel<64, false><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<64, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
   } else {
     static bool attr32 = false;
     if (!attr32) {
       DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32 = true;
     }
-    conv_tc_kernel<32, false><<<grid, kNumThreads, smem, stream>>>(a0, a1, b, r, o, p);
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
   }
   DY_CUDA(cudaGetLastError());
   return DY_OK;

@@ -109,6 +109,10 @@ int make_tmap_image_f32(CUtensorMap* out, const float* base, int N, int H, int W
 size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p);
 int conv_tc_pick_stages(int kchunk, const ConvParams& p);
 
+// 1 (default): conv launches carry the programmatic-stream-serialization attribute (their prologue overlaps the
+// previous layer's tail); 0: ordinary stream order (A/B)
+void conv_tc_set_pdl(int on);
+
 // kchunk in {32, 64}
 int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                    const CUtensorMap& r, const CUtensorMap& o, const ConvParams& p, int num_sms,

@@ -932,6 +932,7 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_tma_epi") g_opt_tma_epi = value;
   else if (n == "conv1_tc") g_opt_conv1_tc = value;
   else if (n == "tc_fuse_tail") g_opt_fuse_tail = value;
+  else if (n == "tc_pdl") conv_tc_set_pdl(value < 0 ? 1 : value);
   else if (n == "tc_dual_producer") g_opt_dual_producer = value;
   else if (n == "tc_max_stages") g_opt_max_stages = value;
   else if (n == "tc_skip_epilogue") g_opt_skip_epi = value;
