@@ -258,7 +258,12 @@ __device__ __forceinline__ void store_vec(const ConvParams& p, const OutDesc& o,
   }
 }
 
-template <int KCHUNK, bool FUSE>
+// CTA2: the grid is made of 2-CTA clusters (one TPC each).  A cluster works on a PAIR tile of 256 GEMM rows x
+// block_n columns: CTA r stages rows [128 r, 128 r + 128) of A and rows [r block_n/2, (r+1) block_n/2) of the weight
+// tile; the even CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256) for both, each CTA's epilogue drains its
+// own 128 accumulator rows from its own TMEM.  Per SM this halves the weight bytes that cross L2 -> shared memory
+// and that the tensor core reads back, and doubles the pipeline depth a given amount of shared memory buys.
+template <int KCHUNK, bool FUSE, bool CTA2>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
@@ -286,7 +291,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   pdl_launch_dependents();            // the next layer's CTAs may take over SMs as this grid's CTAs retire
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t b_bytes = (uint32_t)p.block_n * KCHUNK * 2;            // one weight K chunk
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // first (pair) tile of this CTA (cluster)
+  const int tstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;    // (pair) tiles between two iterations
+  constexpr int kTileM = CTA2 ? 2 * kBlockM : kBlockM;                  // GEMM rows of one (pair) tile
+  const int m_off = (int)cta_rank * kBlockM;                            // this CTA's rows inside the pair tile
+  const int b_rows = CTA2 ? p.block_n >> 1 : p.block_n;                 // weight rows this CTA stages
+  const uint32_t b_bytes = (uint32_t)b_rows * KCHUNK * 2;               // one weight K chunk (this CTA's part)
   const uint32_t a_tx = (uint32_t)p.a_rows * KCHUNK * 2;                // bytes one A box delivers
   const uint32_t a_bytes = (a_tx + 1023u) & ~1023u;
   const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : (uint32_t)p.max_ntap * b_bytes);
@@ -298,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   // staging row pitch: padded for the cooperative path, dense (hardware-swizzled) for the TMA path
   const uint32_t epi_pitch = p.tma_epi ? (uint32_t)p.slab * 2 : (uint32_t)p.slab * 2 + 16;
   const uint32_t epi_off = stages_off + (uint32_t)p.num_stages * stage_bytes;
-  const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+  const int num_tiles = (CTA2 ? (p.n_tiles_m + 1) >> 1 : p.n_tiles_m) * p.n_tiles_n;
   const bool has_res = p.residual != nullptr;
   // fused tail: its weights [fuse_n x 64] bf16 (SWIZZLE_128B rows) sit behind the epilogue staging buffers
   const uint32_t fuse_off = epi_off + 2u * 2u * (uint32_t)kBlockM * 64u * 2u;
@@ -317,7 +328,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp of the owning warpgroup
+      // one arrive per epilogue warp that drains the accumulator (a CTA pair: the warps of BOTH CTAs arrive on the
+      // leader's barrier, where the MMA thread waits)
+      mbar_init(&tempty_bar[i], (p.split_n ? 8 : 4) * (CTA2 ? 2 : 1));
     }
     mbar_init(&bres_bar, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i >> 1][i & 1], 1);
@@ -325,8 +338,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_cta2(&tmem_base_smem, (uint32_t)p.tmem_cols);
+      tmem_relinquish_cta2();
+    } else {
+      tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   if (warp == 3 && lane < kMaxSeg * 3) {
     // per-(segment, tap) descriptor offsets for the MMA issuers (tile-invariant)
@@ -350,7 +368,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();      // the peer's mbarriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous layer's tail;
@@ -378,12 +397,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       int rstage[2] = {0, 0};
       uint32_t rphase[2] = {0u, 0u};
       int it = my_ring;
-      for (int tile = blockIdx.x + my_ring * gridDim.x; tile < num_tiles; tile += it_step * gridDim.x, it += it_step) {
+      for (int tile = tile0 + my_ring * tstride; tile < num_tiles; tile += it_step * tstride, it += it_step) {
         const int ring = p.dual_issue ? (it & 1) : 0;
         int stage = ring ? rstage[1] : rstage[0];
         uint32_t phase = ring ? rphase[1] : rphase[0];
-        const int m0 = (tile / p.n_tiles_n) * kBlockM;
+        const int m0 = (tile / p.n_tiles_n) * kTileM + m_off;
         const int n0 = (tile % p.n_tiles_n) * p.block_n;
+        const int nb0 = n0 + (CTA2 ? (int)cta_rank * b_rows : 0);   // first weight row this CTA stages
         if (has_res) {
           // pull the residual tile towards L2 now; the epilogue reads it a few microseconds later
           const int step = p.slab ? p.slab : 64;
@@ -396,13 +416,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           for (int c = 0; c < sg.nchunk; ++c) {
             const int gs = ring * ring_sz + stage;                   // global stage slot
             mbar_wait(&empty_bar[gs], phase ^ 1u);
-            mbar_expect_tx(&full_bar[gs], tx);
             uint8_t* sa = smem_gen + stages_off + (size_t)gs * stage_bytes;
-            tma_load_2d(sa, am, &full_bar[gs], sg.col0 + c * KCHUNK, m0 + sg.shift);
-            if (!p.b_resident) {
+            if constexpr (CTA2) {
+              // the leader's barrier counts the bytes of both CTAs (complete_tx may precede expect_tx within a phase)
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[gs], 2u * tx);
+              tma_load_2d_cta2(sa, am, &full_bar[gs], sg.col0 + c * KCHUNK, m0 + sg.shift);
               for (int t = 0; t < sg.ntap; ++t)
-                tma_load_2d(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[gs],
-                            (sg.tap_b0[t] + c) * KCHUNK, n0);
+                tma_load_2d_cta2(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[gs],
+                                 (sg.tap_b0[t] + c) * KCHUNK, nb0);
+            } else {
+              mbar_expect_tx(&full_bar[gs], tx);
+              tma_load_2d(sa, am, &full_bar[gs], sg.col0 + c * KCHUNK, m0 + sg.shift);
+              if (!p.b_resident) {
+                for (int t = 0; t < sg.ntap; ++t)
+                  tma_load_2d(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[gs],
+                              (sg.tap_b0[t] + c) * KCHUNK, nb0);
+              }
             }
             if (++stage == ring_sz) {
               stage = 0;
@@ -418,10 +447,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // Two issuing threads: issuer i owns accumulator stage i, i.e. every other tile of this CTA.
     // For thin layers (N <= 64: 32-cycle MMAs) the per-stage wait/commit and per-MMA descriptor work
     // of a single thread is the bottleneck; the smem ring is consumed in tile order either way.
-    if ((warp == 1 || p.dual_issue) && elect_one()) {
+    if ((warp == 1 || p.dual_issue) && (!CTA2 || cta_rank == 0) && elect_one()) {
       const int issuer = (warp == 3) ? 1 : 0;
       const int it_step = p.dual_issue ? 2 : 1;
-      const uint32_t idesc = umma_idesc_bf16(p.block_n);
+      const uint32_t idesc = umma_idesc_bf16(p.block_n, kTileM);
       // descriptor bits that never change: LBO=1, SBO, version, layout
       const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46) | ((uint64_t)kLayout << 61);
       const uint32_t S = (uint32_t)(p.dual_issue ? p.num_stages / 2 : p.num_stages);   // this issuer's ring
@@ -434,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       const int acc_sh = p.num_acc == 4 ? 2 : 1;
       int it = issuer;
-      for (int tile = blockIdx.x + issuer * gridDim.x; tile < num_tiles; tile += it_step * gridDim.x, it += it_step) {
+      for (int tile = tile0 + issuer * tstride; tile < num_tiles; tile += it_step * tstride, it += it_step) {
         const int acc = it & (p.num_acc - 1);           // num_acc is 2 or 4: parity(acc) == parity(it) == issuer
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
         mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> acc_sh) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -446,7 +475,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const uint32_t gs = ring_base + stage;
             mbar_wait(&full_bar[gs], phase);            // TMA bytes have landed
             tc_fence_after();
-            const uint32_t sa16 = (smem_base + stages_off + gs * stage_bytes) >> 4;
+            // (a clustered CTA's shared-window addresses carry its rank above bit 18: keep the descriptor's 14 bits)
+            const uint32_t sa16 = ((smem_base + stages_off + gs * stage_bytes) & 0x3FFFFu) >> 4;
             for (int t = 0; t < ntap; ++t) {
               // same box, start address advanced by whole rows: tap t of the shared halo'd segment
               const uint64_t adesc = desc_hi | (uint64_t)(sa16 + tap_a16[s][t]);
@@ -455,18 +485,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < KCHUNK / 16; ++k) {
                 // +32 bytes (16 bf16) along K inside the swizzle row: +2 in the (addr>>4) field
-                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc_flag);
+                if constexpr (CTA2) umma_bf16_cta2(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc_flag);
+                else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, acc_flag);
                 acc_flag = 1u;
               }
             }
-            umma_commit(&empty_bar[gs]);                // frees the smem slot when the MMAs retire
+            if constexpr (CTA2) umma_commit_cta2(&empty_bar[gs]);   // (both CTAs' slots)
+            else umma_commit(&empty_bar[gs]);           // frees the smem slot when the MMAs retire
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
-        umma_commit(&tfull_bar[acc]);                   // accumulator complete -> epilogue
+        if constexpr (CTA2) umma_commit_cta2(&tfull_bar[acc]);    // (both CTAs' epilogues)
+        else umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
       }
     }
   } else if (warp >= 4) {
@@ -502,11 +535,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if (j < p.fuse_cout) __stcs(d + j * plane, __uint_as_float(fr[j]) + s_fbias[j]);
       }
     };
-    int it = wg;
-    for (int tile = blockIdx.x + wg * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
-      const int acc = it & (p.num_acc - 1);             // this warpgroup owns the accumulators of its tile parity
+    // split_n: BOTH warpgroups drain EVERY tile, half of its columns each -- the accumulator is handed back to
+    // the MMA issuer after half the tcgen05.ld / residual round trips (a 256-column tile only has two TMEM
+    // stages, so the drain time of one tile bounds the start of the tile after next)
+    const int t_first = p.split_n ? 0 : wg, t_step = p.split_n ? 1 : 2;
+    const int cbase = p.split_n ? wg * (p.block_n >> 1) : 0;       // first column of this warpgroup inside the tile
+    const int ncols = p.split_n ? (p.block_n >> 1) : p.block_n;    // columns this warpgroup drains
+    int it = t_first;
+    for (int tile = tile0 + t_first * tstride; tile < num_tiles; tile += t_step * tstride, it += t_step) {
+      const int acc = it & (p.num_acc - 1);             // (no split: this warpgroup owns the accumulators of its tile parity)
       const uint32_t acc_phase = (uint32_t)(it >> (p.num_acc == 4 ? 2 : 1)) & 1u;
-      const int m0 = (tile / p.n_tiles_n) * kBlockM;
+      const int m0 = (tile / p.n_tiles_n) * kTileM + m_off;
       const int n0 = (tile % p.n_tiles_n) * p.block_n;
       const long long m = (long long)m0 + q * 32 + lane;
       PixelInfo px;
@@ -529,7 +568,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
         cached_n0 = n0;
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n + cbase);
       uint32_t r0[16], r1[16];
       if (p.debug_skip == 1) {
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -575,7 +614,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int row = q * 32 + lane;
         const int rsw = (p.slab == 64) ? (row & 7) : ((row >> 1) & 3);      // this row's swizzle XOR
         const int vpr = p.slab >> 3, vsh = (p.slab == 64) ? 3 : 2;
-        const int nslab = p.block_n / p.slab;
+        const int nslab = ncols / p.slab;
+        const int nb = n0 + cbase;                           // first global column of this warpgroup
         const bool elected = wg_tid == 0;
         const bool dual = p.out[1].mode != OUT_NONE;
         // Double buffered by tile parity: a warp that has finished this tile's cooperative stores writes
@@ -583,12 +623,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // is no warpgroup barrier between two tiles; within a tile every slab has one, so nobody can be
         // two tiles ahead).
         // (the TMA path needs no table for out[0], so s_dst[wg][0..1] serve as the two parities)
-        long long* dst2 = s_dst[wg][(it >> 1) & 1];
+        long long* dst2 = s_dst[wg][(p.split_n ? it : (it >> 1)) & 1];
         if (dual) dst2[row] = dest_offset(p, p.out[1], px, m);
         if (elected && has_res && !res_primed) {
           // very first slab of this warpgroup: nothing has used the buffers yet
           mbar_expect_tx(&res_full[wg][sc & 1], buf_bytes);
-          tma_load_2d(stg0 + (size_t)(sc & 1) * buf_bytes, &mapR, &res_full[wg][sc & 1], n0, m0);
+          tma_load_2d(stg0 + (size_t)(sc & 1) * buf_bytes, &mapR, &res_full[wg][sc & 1], nb, m0);
         }
         res_primed = true;
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -611,12 +651,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const bool more1 = c0 + 16 < p.slab;
             if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
             if (p.debug_skip != 2)
-              epilogue_chunk_swz(p, r0, my_scale, my_shift, slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
+              epilogue_chunk_swz(p, r0, my_scale, my_shift, cbase + slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
             if (more1) {
               tmem_ld_wait();
               if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
               if (p.debug_skip != 2)
-                epilogue_chunk_swz(p, r1, my_scale, my_shift, slab0 + c0 + 16, has_res, px.valid, srow,
+                epilogue_chunk_swz(p, r1, my_scale, my_shift, cbase + slab0 + c0 + 16, has_res, px.valid, srow,
                                    (c0 + 16) >> 3, rsw);
             }
           }
@@ -625,13 +665,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             // now, before the store phases
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+              if constexpr (CTA2) mbar_arrive_leader(&tempty_bar[acc]);
+              else mbar_arrive(&tempty_bar[acc]);
+            }
           }
           fence_proxy_async_smem();                          // generic-proxy smem writes -> async proxy (TMA)
           asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           if (elected) {
             if (p.debug_skip == 0 && (!FUSE || p.fuse_store)) {
-              tma_store_2d(&mapO, stg, n0 + slab0, m0);
+              tma_store_2d(&mapO, stg, nb + slab0, m0);
               bulk_commit();
             }
             if constexpr (FUSE) {
@@ -649,14 +692,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (has_res) {
               // request the residual of the NEXT slab (this tile's, or the first one of this
               // warpgroup's next tile) into the other buffer, whose last store is one slab old
-              int nm0 = m0, nn0 = n0 + slab0 + p.slab;
+              int nm0 = m0, nn0 = nb + slab0 + p.slab;
               bool have = sidx + 1 < nslab;
               if (!have) {
-                const int ntile = tile + 2 * (int)gridDim.x;
+                const int ntile = tile + t_step * tstride;
                 if (ntile < num_tiles) {
                   have = true;
-                  nm0 = (ntile / p.n_tiles_n) * kBlockM;
-                  nn0 = (ntile % p.n_tiles_n) * p.block_n;
+                  nm0 = (ntile / p.n_tiles_n) * kTileM + m_off;
+                  nn0 = (ntile % p.n_tiles_n) * p.block_n + cbase;
                 }
               }
               if (have) {
@@ -679,7 +722,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if (d1 < 0) continue;
               const int sw = (p.slab == 64) ? (rr & 7) : ((rr >> 1) & 3);
               const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + ((cj ^ sw) << 4));
-              store_vec(p, p.out[1], d1, n0 + slab0 + cj * 8, v);
+              store_vec(p, p.out[1], d1, nb + slab0 + cj * 8, v);
             }
           }
         }
@@ -703,7 +746,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (i < vpr) {
               const int rr = idx >> vsh, cj = idx & (vpr - 1);
               const long long mm = (long long)m0 + rr;
-              rres[i] = (mm < p.M) ? __ldg(reinterpret_cast<const uint4*>(p.residual + mm * p.res_ld + n0 + slab0 +
+              rres[i] = (mm < p.M) ? __ldg(reinterpret_cast<const uint4*>(p.residual + mm * p.res_ld + n0 + cbase + slab0 +
                                                                           cj * 8))
                                    : make_uint4(0, 0, 0, 0);
             }
@@ -712,7 +755,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (has_res) fetch_res(0);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        for (int slab0 = 0; slab0 < p.block_n; slab0 += p.slab) {
+        for (int slab0 = 0; slab0 < ncols; slab0 += p.slab) {
           if (has_res) {
             // phase 0: park this slab's residual in the staging rows, start fetching the next slab's
 #pragma unroll
@@ -723,7 +766,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 *reinterpret_cast<uint4*>(stg + (size_t)rr * epi_pitch + cj * 16) = rres[i];
               }
             }
-            if (slab0 + p.slab < p.block_n) fetch_res(slab0 + p.slab);
+            if (slab0 + p.slab < ncols) fetch_res(slab0 + p.slab);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           // phase 1: accumulator -> BN/leaky (+ residual) -> bf16, thread per row
@@ -733,11 +776,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tmem_ld_wait();
             const bool more1 = c0 + 16 < p.slab;
             if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
-            epilogue_chunk_staged(p, r0, my_scale, my_shift, slab0 + c0, has_res, srow + c0 * 2);
+            epilogue_chunk_staged(p, r0, my_scale, my_shift, cbase + slab0 + c0, has_res, srow + c0 * 2);
             if (more1) {
               tmem_ld_wait();
               if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
-              epilogue_chunk_staged(p, r1, my_scale, my_shift, slab0 + c0 + 16, has_res, srow + (c0 + 16) * 2);
+              epilogue_chunk_staged(p, r1, my_scale, my_shift, cbase + slab0 + c0 + 16, has_res, srow + (c0 + 16) * 2);
             }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
@@ -747,7 +790,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             const long long d0 = s_dst[wg][0][rr];
             if (d0 < 0) continue;                         // pad pixel / beyond M: never written
             const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + cj * 16);
-            const int gcol = n0 + slab0 + cj * 8;
+            const int gcol = n0 + cbase + slab0 + cj * 8;
             store_vec(p, p.out[0], d0, gcol, v);
             const long long d1 = s_dst[wg][1][rr];
             if (d1 >= 0) store_vec(p, p.out[1], d1, gcol, v);
@@ -758,7 +801,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       if (!(p.tma_epi && p.slab != 0 && p.debug_skip != 1)) {   // (the TMA path released it after its last tcgen05.ld)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if constexpr (CTA2) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       }
     }
     if constexpr (FUSE) {
@@ -768,10 +814,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();      // neither CTA frees TMEM / retires while the pair's MMAs or arrivals are in flight
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if constexpr (CTA2) tmem_dealloc_cta2(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -826,7 +874,8 @@ static size_t a_stage_bytes(int kchunk, const ConvParams& p) {
   return ((size_t)p.a_rows * kchunk * 2 + 1023) & ~(size_t)1023;
 }
 static size_t stage_bytes_of(int kchunk, const ConvParams& p) {
-  return a_stage_bytes(kchunk, p) + (p.b_resident ? 0 : (size_t)p.max_ntap * p.block_n * kchunk * 2);
+  const size_t b_rows = p.cta2 ? p.block_n / 2 : p.block_n;     // a CTA pair: each CTA stages half of the weight tile
+  return a_stage_bytes(kchunk, p) + (p.b_resident ? 0 : (size_t)p.max_ntap * b_rows * kchunk * 2);
 }
 static size_t resident_bytes_of(int kchunk, const ConvParams& p) {
   return p.b_resident ? (size_t)p.num_chunks * p.block_n * kchunk * 2 : 0;
@@ -894,6 +943,8 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
   DY_CHECK(p.a_rows == kBlockM || p.a_rows == kHaloRows, "a_rows");
   DY_CHECK(p.max_ntap >= 1 && p.max_ntap <= 3, "max_ntap");
   DY_CHECK(p.slab == 0 || ((p.slab == 32 || p.slab == 64) && p.block_n % p.slab == 0), "slab");
+  DY_CHECK(!p.split_n || (p.slab != 0 && !p.dual_issue && !p.fuse_n && p.num_acc == 2 && (p.block_n / 2) % p.slab == 0),
+           "split-N epilogue needs a staged epilogue, one MMA issuer and a whole number of slabs per half tile");
   const size_t smem = conv_tc_smem_bytes(kchunk, p);
   DY_CHECK(smem <= (size_t)kConvTcMaxSmem, "pipeline does not fit in shared memory");
   const int tiles = p.n_tiles_m * p.n_tiles_n;
@@ -904,27 +955,56 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
     DY_CHECK(grid >= p.n_tiles_n, "grid too small for resident weights");
   }
   DY_CHECK(!p.fuse_n || kchunk == 32, "the fused tail is instantiated for 32-wide K chunks (convolutional81)");
+  if (p.cta2) {
+    DY_CHECK(kchunk == 64 && !p.b_resident && !p.dual_issue && !p.fuse_n && p.slab != 0 && p.tma_epi && p.num_acc == 2 &&
+                 p.block_n % 32 == 0 && p.block_n >= 32,
+             "CTA-pair plan: 64-wide K chunks, streamed weights, one issuer, TMA staged epilogue");
+    static bool attr2 = false;
+    if (!attr2) {
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      attr2 = true;
+    }
+    const int pair_tiles = ((p.n_tiles_m + 1) / 2) * p.n_tiles_n;
+    int g2 = 2 * pair_tiles < num_sms ? 2 * pair_tiles : (num_sms & ~1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g2);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 2 : 1;
+    DY_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, true>, a0, a1, b, r, o, p));
+    DY_CUDA(cudaGetLastError());
+    return DY_OK;
+  }
   if (p.fuse_n) {
     static bool attr32f = false;
     if (!attr32f) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32f = true;
     }
-    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, true>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, true, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
   } else if (kchunk == 64) {
     static bool attr64 = false;
     if (!attr64) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr64 = true;
     }
-    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<64, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<64, false, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
   } else {
     static bool attr32 = false;
     if (!attr32) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr32 = true;
     }
-    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, false, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
   }
   DY_CUDA(cudaGetLastError());
   return DY_OK;

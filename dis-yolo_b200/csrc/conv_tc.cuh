@@ -76,6 +76,10 @@ struct ConvParams {
   int b_resident;  // 1: the CTA's whole [block_n x K] weight slab is loaded to smem once
   int slab;        // epilogue staging width in columns (64 or 32); 0 = direct per-thread stores
   int debug_skip;  // measurement aid: 1 = epilogue only drains the accumulator barrier (no math, no stores)
+  int cta2;        // 1: CTA-pair plan -- 2-CTA clusters, tcgen05.mma.cta_group::2 with M = 256, each CTA stages half of the
+                   // weight tile (64-wide K chunks, streamed weights, TMA staged epilogue)
+  int split_n;     // staged epilogue only: 1 = both epilogue warpgroups drain every tile, half of its columns each
+                   // (0: they take alternate tiles)
   int tma_epi;     // staged epilogue only: out[0] (P1 layout) leaves through TMA stores, the residual
                    // arrives through TMA loads into the same swizzled staging buffers
   int tmem_cols;   // power of two >= 2*block_n, >= 32

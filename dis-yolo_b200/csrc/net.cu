@@ -150,6 +150,10 @@ static int g_opt_skip_epi = 0;      // measurement only: conv epilogues do nothi
 static int g_opt_conv1_tc = -1;     // 0: conv1 on CUDA cores, otherwise the tcgen05 im2col stem kernel
 static int g_opt_dual_producer = -1; // with dual issue: 0 one TMA producer thread for both half rings, 1 one per half ring
 static int g_opt_max_stages = -1;   // cap of the shared-memory pipeline depth (default kMaxStages)
+static int g_opt_split_n = -1;      // 0: epilogue warpgroups take alternate tiles, 1: both drain every tile (half the columns each) where legal
+static int g_opt_kchunk = -1;       // 32: 32-wide K chunks (SWIZZLE_64B) even where 64 divides the channel counts (A/B)
+static int g_opt_slab = -1;         // 32: 32-column staging slabs in the TMA epilogue (A/B)
+static int g_opt_cta2 = -1;         // 0: never plan CTA pairs (cta_group::2), 1: wherever legal, -1: planner's choice
 static int g_opt_fuse_tail = -1;    // 0: convolutional82 as its own launch, otherwise fused into convolutional81's epilogue
 static int g_wg_dbg[4] = {0, 0, 0, 0};   // bring-up aid: wgrad UMMA descriptor overrides (0 = computed)
 
@@ -173,7 +177,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   DY_CHECK(d.s == 1 || (d.s == 2 && d.k == 3 && d.cin1 == 0), "stride 2 only for 3x3 without concat");
   DY_CHECK(d.cin0 % 32 == 0 && d.cin1 % 32 == 0, "input channels must be multiples of 32");
   DY_CHECK(d.cin1 == 0 || d.k == 1, "concat only feeds 1x1 convs");
-  const int kchunk = (d.cin0 % 64 == 0 && d.cin1 % 64 == 0) ? 64 : 32;
+  const int kchunk = (d.cin0 % 64 == 0 && d.cin1 % 64 == 0 && g_opt_kchunk != 32) ? 64 : 32;
   const int Hp = d.H + 1, Wp = d.W + 1;
   const long long rows_max = (long long)d.max_batch * Hp * Wp;
   const long long m_tiles = (rows_max + kBlockM - 1) / kBlockM;
@@ -221,8 +225,20 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   } else {
     staged = up2;
   }
+  // CTA pairs (cta_group::2, M = 256): the wide 3x3 layers, whose 128 x 256 single-CTA tiles are bound by the bytes
+  // that cross L2 -> shared memory (48 KB per 512 tensor-pipe cycles); a pair halves the weight part of that
+  const bool cta2_ok = kchunk == 64 && d.ntaps_custom == 0 && d.out[0].mode == OUT_SAME && d.cout_pad % 128 == 0 &&
+                       !d.fuse_n && m_tiles >= 2;
+  bool cta2 = cta2_ok && enough_work && d.k == 3 && !fits && d.cout_pad >= 256;
+  if (g_opt_cta2 == 0) cta2 = false;
+  if (g_opt_cta2 == 1) cta2 = cta2_ok;
+  if (cta2) {
+    resident = false;
+    staged = tma = true;
+    block_n = d.cout_pad % 256 == 0 ? 256 : 128;
+  }
   if (g_opt_resident == 0) resident = false;
-  if (g_opt_resident == 1 && fits) resident = true;
+  if (g_opt_resident == 1 && fits && !cta2) resident = true;
   if (g_opt_halo == 0) halo = false;
   if (g_opt_halo == 1 && d.k == 3) halo = true;
   if (g_opt_staged >= 0) staged = g_opt_staged != 0;
@@ -230,11 +246,12 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (resident) block_n = d.cout_pad;
   if (halo && !resident) {
     // three streamed weight chunks per stage: keep a stage <= ~64 KB so that >= 3 stages fit
-    while (block_n > 64 && 3 * (size_t)block_n * kchunk * 2 > 48 * 1024) block_n /= 2;
+    while (block_n > 64 && 3 * (size_t)(cta2 ? block_n / 2 : block_n) * kchunk * 2 > 48 * 1024) block_n /= 2;
   }
   p.block_n = block_n;
   p.n_tiles_n = d.cout_pad / p.block_n;
   p.b_resident = resident ? 1 : 0;
+  p.cta2 = cta2 ? 1 : 0;
   p.a_rows = halo ? kHaloRows : kBlockM;
   int tc = 32;
   while (tc < 2 * p.block_n) tc <<= 1;
@@ -312,6 +329,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   p.tma_epi = (staged && tma && d.out[0].mode == OUT_SAME) ? 1 : 0;
   p.debug_skip = g_opt_skip_epi > 0 ? g_opt_skip_epi : 0;
   if (p.tma_epi && p.block_n % 64 == 0) p.slab = 64;
+  if (p.tma_epi && g_opt_slab == 32 && !d.fuse_n) p.slab = 32;
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
   p.fuse_n = d.fuse_n;      // (sizes the epilogue staging area)
   p.num_stages = conv_tc_pick_stages(kchunk, p);
@@ -324,12 +342,20 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   bool dual_issue = enough_work && p.block_n <= 64 && p.num_stages >= 6;
   if (g_opt_dual == 0) dual_issue = false;
   if (g_opt_dual == 1) dual_issue = p.num_stages >= 4;
+  if (cta2) dual_issue = false;
   if (dual_issue) p.num_stages &= ~1;
   p.dual_issue = dual_issue ? 1 : 0;
   p.dual_producer = (dual_issue && g_opt_dual_producer != 0) ? 1 : 0;
   // four TMEM accumulator stages (two per issuer) when they fit: otherwise each issuer would be
   // serialised with its own epilogue warpgroup
   p.num_acc = (dual_issue && 4 * p.block_n <= 512) ? 4 : 2;
+  // wide tiles (two TMEM stages only): both epilogue warpgroups drain every tile, half of its columns each, so the
+  // accumulator returns to the MMA issuer after half the tcgen05.ld / residual round trips
+  const bool split_ok = !dual_issue && p.slab != 0 && !d.fuse_n && p.num_acc == 2 && (p.block_n / 2) % p.slab == 0;
+  bool split_n = split_ok && enough_work && p.block_n == 256;     // (measured: 128-column tiles lose 4 %)
+  if (g_opt_split_n == 0) split_n = false;
+  if (g_opt_split_n == 1) split_n = split_ok;
+  p.split_n = split_n ? 1 : 0;
   if (d.fuse_n) {
     DY_CHECK(p.tma_epi && p.slab == 64 && p.block_n == 64 && d.cout == 64 && !has_res && d.out[1].mode == OUT_NONE,
              "fused tail: the producer must be a 64-channel layer on the TMA staged epilogue");
@@ -347,7 +373,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   } else {
     plan->a1 = plan->a0;
   }
-  DY_TRY(make_tmap_2d(&plan->b, d.wpk, d.cout_pad, K, K, kchunk, p.block_n));
+  DY_TRY(make_tmap_2d(&plan->b, d.wpk, d.cout_pad, K, K, kchunk, cta2 ? p.block_n / 2 : p.block_n));
   const int rbox = p.slab ? p.slab : 64;
   if (d.residual != nullptr) {
     DY_CHECK(d.cout % 64 == 0 && p.block_n % 64 == 0, "residual layers need cout % 64 == 0");
@@ -932,6 +958,10 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_tma_epi") g_opt_tma_epi = value;
   else if (n == "conv1_tc") g_opt_conv1_tc = value;
   else if (n == "tc_fuse_tail") g_opt_fuse_tail = value;
+  else if (n == "tc_split_n") g_opt_split_n = value;
+  else if (n == "tc_cta2") g_opt_cta2 = value;
+  else if (n == "tc_kchunk") g_opt_kchunk = value;
+  else if (n == "tc_slab") g_opt_slab = value;
   else if (n == "tc_pdl") conv_tc_set_pdl(value < 0 ? 1 : value);
   else if (n == "tc_dual_producer") g_opt_dual_producer = value;
   else if (n == "tc_max_stages") g_opt_max_stages = value;
