@@ -229,13 +229,16 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   // that cross L2 -> shared memory (48 KB per 512 tensor-pipe cycles); a pair halves the weight part of that
   const bool cta2_ok = kchunk == 64 && d.ntaps_custom == 0 && d.out[0].mode == OUT_SAME && d.cout_pad % 128 == 0 &&
                        !d.fuse_n && m_tiles >= 2;
-  bool cta2 = cta2_ok && enough_work && d.k == 3 && !fits && d.cout_pad >= 256;
+  // (measured per layer, scripts/ab_opts.py: every 3x3 and plain 1x1 layer with >= 128 output channels gains 4-18 %;
+  // the 1x1s over a concat and the ones that also write an upsampled copy do not)
+  bool cta2 = cta2_ok && enough_work && d.cin1 == 0 && !up2 && d.cout_pad >= 128;
   if (g_opt_cta2 == 0) cta2 = false;
   if (g_opt_cta2 == 1) cta2 = cta2_ok;
   if (cta2) {
     resident = false;
     staged = tma = true;
     block_n = d.cout_pad % 256 == 0 ? 256 : 128;
+    if (d.k == 3 && d.s == 1) halo = true;     // one 136-row box feeds the three horizontal taps (measured: -4..-8 %)
   }
   if (g_opt_resident == 0) resident = false;
   if (g_opt_resident == 1 && fits && !cta2) resident = true;
@@ -330,6 +333,9 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   p.debug_skip = g_opt_skip_epi > 0 ? g_opt_skip_epi : 0;
   if (p.tma_epi && p.block_n % 64 == 0) p.slab = 64;
   if (p.tma_epi && g_opt_slab == 32 && !d.fuse_n) p.slab = 32;
+  // CTA-pair plans without a shared halo box (the stride-2 convs: nine 32 KB stages per K chunk group): the smaller
+  // staging area buys a fifth pipeline stage (measured -6..-9 %)
+  if (p.tma_epi && cta2 && !halo && d.k == 3 && g_opt_slab < 0) p.slab = 32;
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
   p.fuse_n = d.fuse_n;      // (sizes the epilogue staging area)
   p.num_stages = conv_tc_pick_stages(kchunk, p);
