@@ -716,13 +716,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           }
           if (dual) {
             // second destination form (space-to-depth / upsampled): cooperative vector stores
-            for (int idx = wg_tid; idx < kBlockM * vpr; idx += 128) {
-              const int rr = idx >> vsh, cj = idx & (vpr - 1);
-              const long long d1 = dst2[rr];
-              if (d1 < 0) continue;
-              const int sw = (p.slab == 64) ? (rr & 7) : ((rr >> 1) & 3);
-              const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + ((cj ^ sw) << 4));
-              store_vec(p, p.out[1], d1, nb + slab0 + cj * 8, v);
+            // (vpr passes of 128 vectors; four passes at a time with all shared-memory loads ahead of the stores:
+            // the dependent LDS -> LDS -> STG chain of a rolled loop was the hottest spot of the dual-output layers)
+            for (int i0 = 0; i0 < vpr; i0 += 4) {
+              long long d1[4];
+              uint4 v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d1[i] = dst2[((i0 + i) * 128 + wg_tid) >> vsh];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int idx = (i0 + i) * 128 + wg_tid;
+                const int rr = idx >> vsh, cj = idx & (vpr - 1);
+                const int sw = (p.slab == 64) ? (rr & 7) : ((rr >> 1) & 3);
+                v[i] = *reinterpret_cast<const uint4*>(stg + (size_t)rr * epi_pitch + ((cj ^ sw) << 4));
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int cj = ((i0 + i) * 128 + wg_tid) & (vpr - 1);
+                if (d1[i] >= 0) store_vec(p, p.out[1], d1[i], nb + slab0 + cj * 8, v[i]);
+              }
             }
           }
         }

@@ -121,64 +121,55 @@ __device__ __forceinline__ float iou_tf(const float4 a, const float4 b) {  // (y
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
 }
 
-struct KeyPos {
-  unsigned long long key;
-  int pos;
-};
-
-__device__ __forceinline__ KeyPos kp_max(KeyPos a, KeyPos b) { return (b.key > a.key) ? b : a; }
-
-__device__ __forceinline__ KeyPos warp_kp_max(KeyPos v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    KeyPos t;
-    t.key = __shfl_xor_sync(0xffffffffu, v.key, o);
-    t.pos = __shfl_xor_sync(0xffffffffu, v.pos, o);
-    v = kp_max(v, t);
-  }
-  return v;
-}
-
-// One CTA (1024 threads) per (class, image).
-// Phase 0 compacts the class's candidates into structure-of-arrays form -- box (float4), ordering key,
-// position in the candidate list -- the first kNmsSmem of them in shared memory, the overflow (stress
-// configuration: tens of thousands of candidates per class) in a global scratch area.  The survivors then
-// live as an "alive" bitmask in shared memory, one 32-bit word per 32 compacted candidates, rebuilt with
-// warp ballots.  Each round: block-wide arg-max of the ordering key over alive candidates = the next box
-// TF's greedy loop would select; one pass then clears every alive candidate whose IoU with it exceeds the
-// threshold (strict >) while gathering the next round's arg-max.  At most max_det rounds (max_output_size,
-// :566-573).  In the normal configuration everything a round touches is shared memory; in the overflow
-// range every warp keeps kNmsUnroll independent 16-byte loads in flight (the rounds are latency bound).
+// One CTA (1024 threads) per (class, image): exact greedy NMS (= tf.image.non_max_suppression, :566-573) in
+// BATCHES of the best kNmsBatch remaining candidates.
+//   phase 0  the class's candidates are compacted (warp ballots) into structure-of-arrays form -- box, ordering
+//            key, position in the candidate list; up to kNmsBatch of them live in shared memory, a larger class
+//            (stress configuration: tens of thousands per class) goes to a global scratch area;
+//   batch    a multi-level 12-bit radix select over the keys finds the threshold T such that the not yet
+//            examined candidates with key >= T number at most kNmsBatch (whole histogram bins; a bin that is too
+//            large on its own is refined by the next 12 key bits -- keys are unique, so this terminates); they are
+//            loaded into shared memory, each one tested against the boxes kept so far (a candidate suppressed by
+//            an earlier batch's selection never enters), and sorted by key (bitonic, in shared memory);
+//   rounds   the greedy scan of the sorted batch: every warp finds the first alive bit of a ping-pong bitmask by
+//            itself (two words per lane, ballot + ffs -- no block-wide arg-max), the box is appended to the keep
+//            list, every thread clears its own candidates with IoU > threshold against it: ONE __syncthreads per
+//            selected box.
+// A candidate of a later batch has a smaller key than everything in the current one, so it can neither be
+// selected before nor suppress anything in it: the batches reproduce the sequential algorithm exactly, ties
+// included (the key carries the candidate index).  Stops at max_det selections (max_output_size).
 constexpr int kNmsThreads = 1024;
-constexpr int kNmsSmem = 2048;       // compacted candidates kept in shared memory
-constexpr int kNmsUnroll = 4;
+constexpr int kNmsBatch = 2048;
+constexpr int kNmsBins = 4096;
 
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsArgs a) {
   extern __shared__ __align__(16) uint8_t nms_smem[];
-  float4* sbox = reinterpret_cast<float4*>(nms_smem);                                    // [kNmsSmem]
-  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sbox + kNmsSmem);     // [kNmsSmem]
-  int* spos = reinterpret_cast<int*>(skey + kNmsSmem);                                   // [kNmsSmem]
-  uint32_t* alive = reinterpret_cast<uint32_t*>(spos + kNmsSmem);                        // [ceil(cap/32)]
-  __shared__ unsigned long long red_key[32];
-  __shared__ int red_pos[32];
-  __shared__ unsigned long long best_key_s;
-  __shared__ int best_pos_s;
+  float4* bbox = reinterpret_cast<float4*>(nms_smem);                                    // [kNmsBatch] arrival order
+  float4* sbox = bbox + kNmsBatch;                                                       // [kNmsBatch] sorted order
+  float4* kbox = sbox + kNmsBatch;                                                       // [max_det] kept boxes
+  unsigned long long* bkey = reinterpret_cast<unsigned long long*>(kbox + ((a.max_det + 3) & ~3));   // [kNmsBatch]
+  int* bpos = reinterpret_cast<int*>(bkey + kNmsBatch);                                  // [kNmsBatch] by arrival slot
+  int* bslot = bpos + kNmsBatch;                                                         // [kNmsBatch] slot of sorted pos
+  uint32_t* hist = reinterpret_cast<uint32_t*>(bslot + kNmsBatch);                       // [kNmsBins]
+  __shared__ uint32_t abits[2][kNmsBatch / 32];
+  __shared__ uint32_t wsum[32];
   __shared__ int count_s;
+  __shared__ int sel_bin_s;
+  __shared__ uint32_t sel_above_s;
 
   const int c = blockIdx.x, b = blockIdx.y;
   int n = a.cand_count[b];
   if (n > a.cap) n = a.cap;
   const Cand* cd = a.cand + (long long)b * a.cap;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kNmsThreads >> 5;
   int* sel = a.sel + ((long long)b * a.num_class + c) * a.max_det;
-  // overflow area of this (image, class): entries kNmsSmem.. of the compacted list
   const long long ovf = ((long long)b * a.num_class + c) * a.cap;
   float4* gbox = a.ovf_box + ovf;
   unsigned long long* gkey = a.ovf_key + ovf;
   int* gpos = a.ovf_pos + ovf;
 
   // ---- phase 0: compaction (any order: the ordering key carries the candidate index) ----
-  if (threadIdx.x == 0) count_s = 0;
+  if (tid == 0) count_s = 0;
   __syncthreads();
   for (int i0 = warp * 32; i0 < n; i0 += nwarps * 32) {
     const int i = i0 + lane;
@@ -196,113 +187,203 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsArgs a) {
     if (m) {
       const int e = base + __popc(bal & ((1u << lane) - 1u));
       const float4 bx = make_float4(ci.y1, ci.x1, ci.y2, ci.x2);
-      if (e < kNmsSmem) { sbox[e] = bx; skey[e] = cand_key(ci); spos[e] = i; }
-      else { gbox[e - kNmsSmem] = bx; gkey[e - kNmsSmem] = cand_key(ci); gpos[e - kNmsSmem] = i; }
+      if (e < kNmsBatch) { bbox[e] = bx; bkey[e] = cand_key(ci); bpos[e] = i; }
+      else { gbox[e - kNmsBatch] = bx; gkey[e - kNmsBatch] = cand_key(ci); gpos[e - kNmsBatch] = i; }
     }
   }
   __syncthreads();
   const int nc = count_s;
-  const int nwords = (nc + 31) >> 5;
-  auto entry_box = [&](int e) { return e < kNmsSmem ? sbox[e] : gbox[e - kNmsSmem]; };
-  auto entry_key = [&](int e) { return e < kNmsSmem ? skey[e] : gkey[e - kNmsSmem]; };
-  auto entry_pos = [&](int e) { return e < kNmsSmem ? spos[e] : gpos[e - kNmsSmem]; };
-
-  KeyPos best;
-  best.key = 0ull;
-  best.pos = -1;
-  for (int w = warp; w < nwords; w += nwarps) {
-    const int e = w * 32 + lane;
-    const bool al = e < nc;
-    if (al) {
-      KeyPos t;
-      t.key = entry_key(e);
-      t.pos = e;
-      best = kp_max(best, t);
+  const bool big = nc > kNmsBatch;
+  if (big) {
+    // more than one batch: everything lives in the global scratch; the shared-memory part goes behind the overflow
+    const int tail = nc - kNmsBatch;
+    for (int e = tid; e < kNmsBatch; e += kNmsThreads) {
+      gbox[tail + e] = bbox[e];
+      gkey[tail + e] = bkey[e];
+      gpos[tail + e] = bpos[e];
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, al);
-    if (lane == 0) alive[w] = m;
+    __syncthreads();
   }
+
   int nsel = 0;
+  unsigned long long upper = ~0ull;          // keys >= upper have been examined already
+  bool last = !big;
+  int nb = big ? 0 : nc;                      // candidates of the current batch (arrival slots 0..nb-1)
   while (true) {
-    best = warp_kp_max(best);
-    if (lane == 0) {
-      red_key[warp] = best.key;
-      red_pos[warp] = best.pos;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      KeyPos v;
-      v.key = lane < nwarps ? red_key[lane] : 0ull;
-      v.pos = lane < nwarps ? red_pos[lane] : -1;
-      v = warp_kp_max(v);
-      if (lane == 0) {
-        best_key_s = v.key;
-        best_pos_s = v.pos;
-      }
-    }
-    __syncthreads();
-    const unsigned long long bk = best_key_s;
-    const int bp = best_pos_s;
-    if (bk == 0ull) break;
-    if (threadIdx.x == 0) sel[nsel] = entry_pos(bp);
-    ++nsel;
-    if (nsel >= a.max_det) break;
-    const float4 sb = entry_box(bp);
-    best.key = 0ull;
-    best.pos = -1;
-    // words of the shared-memory range, then the overflow range kNmsUnroll words at a time
-    const int sm_words = min(nwords, kNmsSmem / 32);
-    for (int w = warp; w < sm_words; w += nwarps) {
-      const uint32_t word = alive[w];
-      if (word == 0u) continue;                   // warp-uniform
-      const int e = w * 32 + lane;
-      bool al = (word >> lane) & 1u;
-      if (al) {
-        if (e == bp || iou_tf(sbox[e], sb) > a.iou_thr) {
-          al = false;
-        } else {
-          KeyPos t;
-          t.key = skey[e];
-          t.pos = e;
-          best = kp_max(best, t);
+    if (big) {
+      // ---- threshold T of the next batch: multi-level radix select over keys < upper ----
+      unsigned long long T = 0ull;
+      unsigned long long prefix = 0ull;      // value of the key bits fixed so far
+      int fixed = 0;                         // number of high key bits fixed
+      last = false;
+      while (true) {
+        const int bits = (64 - fixed) < 12 ? (64 - fixed) : 12;
+        const int shift = 64 - fixed - bits;
+        const uint32_t dmask = (1u << bits) - 1u;
+        for (int i = tid; i < kNmsBins; i += kNmsThreads) hist[i] = 0u;
+        __syncthreads();
+        for (int e = tid; e < nc; e += kNmsThreads) {
+          const unsigned long long k = gkey[e];
+          if (k < upper && (fixed == 0 || (k >> (64 - fixed)) == prefix))
+            atomicAdd(&hist[(uint32_t)(k >> shift) & dmask], 1u);
         }
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, al);
-      __syncwarp();                               // every lane has read alive[w] before lane 0 rewrites it
-      if (lane == 0) alive[w] = m;
-    }
-    for (int w0 = sm_words + warp * kNmsUnroll; w0 < nwords; w0 += nwarps * kNmsUnroll) {
-      uint32_t word[kNmsUnroll];
-      float4 bx[kNmsUnroll];
-      bool al[kNmsUnroll];
+        __syncthreads();
+        // scan the bins from the top: thread t owns reversed bins 4t..4t+3 (bin = kNmsBins-1 - r)
+        uint32_t h[4], mine = 0u;
 #pragma unroll
-      for (int u = 0; u < kNmsUnroll; ++u) {      // all loads first: kNmsUnroll independent requests per lane
-        const int w = w0 + u;
-        word[u] = w < nwords ? alive[w] : 0u;
-        al[u] = (word[u] >> lane) & 1u;
-        if (al[u]) bx[u] = gbox[w * 32 + lane - kNmsSmem];
-      }
+        for (int j = 0; j < 4; ++j) {
+          h[j] = hist[kNmsBins - 1 - (4 * tid + j)];
+          mine += h[j];
+        }
+        uint32_t incl = mine;
 #pragma unroll
-      for (int u = 0; u < kNmsUnroll; ++u) {
-        const int w = w0 + u;
-        if (word[u] == 0u) continue;              // warp-uniform
-        const int e = w * 32 + lane;
-        if (al[u]) {
-          if (e == bp || iou_tf(bx[u], sb) > a.iou_thr) {
-            al[u] = false;
-          } else {
-            KeyPos t;
-            t.key = gkey[e - kNmsSmem];
-            t.pos = e;
-            best = kp_max(best, t);
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        if (tid == 0) sel_bin_s = -1;
+        __syncthreads();
+        if (warp == 0) {
+          uint32_t v = wsum[lane], w = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+          }
+          wsum[lane] = w - v;                // exclusive warp offsets
+        }
+        __syncthreads();
+        uint32_t above = wsum[warp] + incl - mine;     // candidates in bins above this thread's first bin
+        if (above <= (uint32_t)kNmsBatch && above + mine > (uint32_t)kNmsBatch) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (above <= (uint32_t)kNmsBatch && above + h[j] > (uint32_t)kNmsBatch) {
+              sel_bin_s = kNmsBins - 1 - (4 * tid + j);   // the first bin (from the top) that no longer fits
+              sel_above_s = above;
+            }
+            above += h[j];
           }
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, al[u]);
-        if (lane == 0) alive[w] = m;              // (this warp alone owns word w in this pass)
+        __syncthreads();
+        const int d = sel_bin_s;
+        if (d < 0) {                           // everything that is left fits (only possible at level 0)
+          T = 0ull;
+          last = true;
+          break;
+        }
+        if (sel_above_s > 0u) {                // whole bins above d form the batch
+          T = ((prefix << bits) | (unsigned long long)(d + 1)) << shift;
+          break;
+        }
+        prefix = (prefix << bits) | (unsigned long long)d;   // the top bin alone is too large: refine inside it
+        fixed += bits;
+        __syncthreads();
+      }
+      // ---- load the batch: keys in [T, upper), minus everything an earlier selection suppresses ----
+      if (tid == 0) count_s = 0;
+      __syncthreads();
+      for (int e0 = warp * 32; e0 < nc; e0 += nwarps * 32) {
+        const int e = e0 + lane;
+        bool m = false;
+        unsigned long long k = 0ull;
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < nc) {
+          k = gkey[e];
+          m = k >= T && k < upper;
+        }
+        if (m) {
+          bx = gbox[e];
+          for (int i = 0; i < nsel; ++i)
+            if (iou_tf(bx, kbox[i]) > a.iou_thr) { m = false; break; }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, m);
+        if (bal == 0u) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&count_s, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (m) {
+          const int slot = base + __popc(bal & ((1u << lane) - 1u));
+          bbox[slot] = bx; bkey[slot] = k; bpos[slot] = gpos[e];
+        }
+      }
+      __syncthreads();
+      nb = count_s;
+      upper = T;
+    }
+    // ---- sort the batch by key, descending (bitonic network over the next power of two) ----
+    int ns = 32;
+    while (ns < nb) ns <<= 1;
+    for (int i = tid; i < ns; i += kNmsThreads) {
+      bslot[i] = i;
+      if (i >= nb) bkey[i] = 0ull;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= ns; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (ns >> 1); t += kNmsThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+          const unsigned long long ka = bkey[i], kb = bkey[ixj];
+          const bool desc = (i & k2) == 0;
+          if (desc ? (ka < kb) : (ka > kb)) {
+            bkey[i] = kb; bkey[ixj] = ka;
+            const int sa = bslot[i];
+            bslot[i] = bslot[ixj]; bslot[ixj] = sa;
+          }
+        }
+        __syncthreads();
       }
     }
+    for (int i = tid; i < nb; i += kNmsThreads) sbox[i] = bbox[bslot[i]];
+    if (tid < kNmsBatch / 32) {
+      const int lo = tid * 32;
+      abits[0][tid] = nb >= lo + 32 ? 0xffffffffu : (nb > lo ? ((1u << (nb - lo)) - 1u) : 0u);
+    }
+    __syncthreads();
+    // ---- greedy rounds over the sorted batch ----
+    int cur = 0;
+    const int nhalf = nb > 1024 ? 2 : 1;
+    while (true) {
+      const uint32_t w0 = abits[cur][lane], w1 = nhalf == 2 ? abits[cur][lane + 32] : 0u;
+      const uint32_t nz0 = __ballot_sync(0xffffffffu, w0 != 0u), nz1 = __ballot_sync(0xffffffffu, w1 != 0u);
+      if ((nz0 | nz1) == 0u) break;
+      int pp;
+      if (nz0) {
+        const int l = __ffs(nz0) - 1;
+        pp = l * 32 + __ffs(__shfl_sync(0xffffffffu, w0, l)) - 1;
+      } else {
+        const int l = __ffs(nz1) - 1;
+        pp = (32 + l) * 32 + __ffs(__shfl_sync(0xffffffffu, w1, l)) - 1;
+      }
+      const float4 sb = sbox[pp];
+      if (tid == 0) {
+        sel[nsel] = bpos[bslot[pp]];
+        kbox[nsel] = sb;
+      }
+      ++nsel;
+      if (nsel >= a.max_det) break;
+      // thread t owns sorted positions t (word `warp`) and 1024 + t (word 32 + `warp`)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (hh < nhalf) {
+          const uint32_t word = __shfl_sync(0xffffffffu, hh ? w1 : w0, warp);
+          uint32_t m = 0u;
+          if (word != 0u) {                       // warp-uniform
+            const int e = (hh * 32 + warp) * 32 + lane;
+            bool al = (word >> lane) & 1u;
+            if (al && (e == pp || iou_tf(sbox[e], sb) > a.iou_thr)) al = false;
+            m = __ballot_sync(0xffffffffu, al);
+          }
+          if (lane == 0) abits[cur ^ 1][hh * 32 + warp] = m;
+        }
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+    if (last || nsel >= a.max_det) break;
+    __syncthreads();                              // (kbox / batch arrays are rewritten by the next batch)
   }
-  if (threadIdx.x == 0) a.sel_cnt[b * a.num_class + c] = nsel;
+  if (tid == 0) a.sel_cnt[b * a.num_class + c] = nsel;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -328,7 +409,7 @@ __device__ __forceinline__ void box_edges(const Cand& c, int S, int k, float (&p
   gy[k] = (int)pb[2];
 }
 
-__global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
+__global__ void __launch_bounds__(1024) finalize_kernel(FinalizeArgs a) {
   extern __shared__ unsigned long long fin_smem[];
   const int Emax = a.num_class * a.max_det;
   unsigned long long* keys = fin_smem;                       // [Emax]
@@ -581,12 +662,12 @@ int launch_decode(const DecodeArgs& a, cudaStream_t st) {
 }
 
 int launch_nms(const NmsArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)kNmsSmem * (16 + 8 + 4) + (size_t)((a.cap + 31) / 32) * 4 + 16;
-  DY_CHECK(smem <= 160 * 1024, "candidate capacity too large for the alive bitmask");
+  const size_t smem = (size_t)kNmsBatch * (16 + 16 + 8 + 4 + 4) + (size_t)((a.max_det + 3) & ~3) * 16 + (size_t)kNmsBins * 4 + 16;
+  DY_CHECK(smem <= 200 * 1024, "max_detection too large for the NMS keep list");
   DY_CHECK(a.ovf_box && a.ovf_key && a.ovf_pos, "NMS overflow scratch missing");
   static bool attr = false;
   if (!attr) {
-    DY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid(a.num_class, a.B);
@@ -605,7 +686,8 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
     DY_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
-  finalize_kernel<<<a.B, 256, smem, st>>>(a);
+  // (the rank pass is O(E^2 / threads): 1024 threads for the stress configuration's 3 x 1000 entries)
+  finalize_kernel<<<a.B, Emax > 512 ? 1024 : 256, smem, st>>>(a);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
