@@ -974,6 +974,7 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_skip_epilogue") g_opt_skip_epi = value;
   else if (n == "tc_dual_issue") g_opt_dual = value;
   else if (n == "mask_streaming_stores") masks_set_streaming(value);
+  else if (n == "mask_work_list") masks_set_work_list(value < 0 ? 0 : value);
   else if (n == "wgrad_fuse_kw") wgrad_set_fuse(value);
   else if (n == "wgrad_lbo_a") { g_wg_dbg[0] = value; wgrad_set_debug(g_wg_dbg[0], g_wg_dbg[1], g_wg_dbg[2], g_wg_dbg[3]); }
   else if (n == "wgrad_sbo_a") { g_wg_dbg[1] = value; wgrad_set_debug(g_wg_dbg[0], g_wg_dbg[1], g_wg_dbg[2], g_wg_dbg[3]); }

@@ -508,18 +508,16 @@ constexpr int kMaskRowsPerCta = 96;    // fat CTAs: the two dependent global loa
 // box?  which horizontal bin?  gather offsets) is computed once per thread; a row outside the box or a
 // column quad outside it costs one streaming store of 0.5 -- the kernel is a 436 MB fill at batch 64
 // with a gather inside the boxes, and every warp store instruction writes 512 contiguous bytes.
+// one (96-row slab, detection, image) work item
 template <bool kStream>
-__global__ void __launch_bounds__(512) mask_kernel(MaskArgs a, int rpi) {
-  const int d = blockIdx.y, b = blockIdx.z;
+__device__ __forceinline__ void mask_slab(const MaskArgs& a, int rpi, int slab, int d, int b) {
   const int* ed = a.edges + ((long long)b * a.max_det + d) * (2 * (kMaxK + 1));
   int gx[kMaxK + 1], gy[kMaxK + 1];
-  const int count = __ldg(a.det_count + b);          // issued together with the edge loads (independent)
 #pragma unroll
   for (int j = 0; j <= kMaxK; ++j) {
     gx[j] = (j <= a.k) ? __ldg(ed + j) : 0x7fffffff;
     gy[j] = (j <= a.k) ? __ldg(ed + kMaxK + 1 + j) : 0x7fffffff;
   }
-  if (d >= count) return;
   const int x_lo = gx[0], x_hi = gx[a.k], y_lo = gy[0], y_hi = gy[a.k];
   const int qpr = a.S >> 2;
   const int q = threadIdx.x % qpr, rl = threadIdx.x / qpr;
@@ -538,31 +536,97 @@ __global__ void __launch_bounds__(512) mask_kernel(MaskArgs a, int rpi) {
     xoff[t] = (long long)bx * a.s_ch + (long long)x * a.s_pix;
   }
   const bool any_x = inx[0] || inx[1] || inx[2] || inx[3];
-  const int y0 = blockIdx.x * kMaskRowsPerCta;
+  const int y0 = slab * kMaskRowsPerCta;
   const int y1 = min(a.S, y0 + kMaskRowsPerCta);
   const float* sbase = a.score + b * a.s_img;
   float4* op = reinterpret_cast<float4*>(a.out + (((long long)b * a.max_det + d) * a.S + y0 + rl) * a.S) + q;
   const long long ostep = (long long)rpi * qpr;
   const float4 half4 = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-  for (int y = y0 + rl; y < y1; y += rpi, op += ostep) {
-    float4 o = half4;
-    if (any_x && y >= y_lo && y < y_hi) {
-      int by = 0;
+  // four rows per pass, every gather load of the pass issued before the first sigmoid: a thread inside the box
+  // has up to 16 independent L2 requests in flight instead of waiting out one round trip per row
+  for (int y = y0 + rl; y < y1; y += 4 * rpi, op += 4 * ostep) {
+    float v[4][4];
+    bool in[4];
 #pragma unroll
-      for (int j = 1; j < kMaxK; ++j)
-        if (j < a.k && y >= gy[j]) by = j;
-      const float* srow = sbase + (long long)(by * a.k) * a.s_ch + (long long)y * a.s_row;
-      if (inx[0]) o.x = sigmoid_fast(__ldg(srow + xoff[0]));
-      if (inx[1]) o.y = sigmoid_fast(__ldg(srow + xoff[1]));
-      if (inx[2]) o.z = sigmoid_fast(__ldg(srow + xoff[2]));
-      if (inx[3]) o.w = sigmoid_fast(__ldg(srow + xoff[3]));
+    for (int u = 0; u < 4; ++u) {
+      const int yy = y + u * rpi;
+      in[u] = any_x && yy < y1 && yy >= y_lo && yy < y_hi;
+      if (in[u]) {
+        int by = 0;
+#pragma unroll
+        for (int j = 1; j < kMaxK; ++j)
+          if (j < a.k && yy >= gy[j]) by = j;
+        const float* srow = sbase + (long long)(by * a.k) * a.s_ch + (long long)yy * a.s_row;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[u][t] = inx[t] ? __ldg(srow + xoff[t]) : 0.f;
+      }
     }
-    if (kStream) __stcs(op, o);
-    else *op = o;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (y + u * rpi >= y1) break;
+      float4 o = half4;
+      if (in[u]) {
+        if (inx[0]) o.x = sigmoid_fast(v[u][0]);
+        if (inx[1]) o.y = sigmoid_fast(v[u][1]);
+        if (inx[2]) o.z = sigmoid_fast(v[u][2]);
+        if (inx[3]) o.w = sigmoid_fast(v[u][3]);
+      }
+      if (kStream) __stcs(op + u * ostep, o);
+      else op[u * ostep] = o;
+    }
+  }
+}
+
+// grid = (slabs, max_det, B): one CTA per possible work item (large batches: B > kMaskMaxB)
+template <bool kStream>
+__global__ void __launch_bounds__(512) mask_kernel(MaskArgs a, int rpi) {
+  const int d = blockIdx.y, b = blockIdx.z;
+  if (d >= __ldg(a.det_count + b)) return;
+  mask_slab<kStream>(a, rpi, blockIdx.x, d, b);
+}
+
+// Work-list form (option mask_work_list, off by default): a fixed grid of CTAs walks the EXISTING (slab,
+// detection) items only -- at batch 64 the (slabs, max_det, B) grid above is 19,200 CTAs of which ~4,000 have work.
+// Measured: the empty CTAs are NOT what the kernel waits for (90 us with them, 104 us with the work list: fewer,
+// longer-lived CTAs hide the gather latency worse).  Every CTA
+// scans det_count once (warp shuffles, B <= kMaskMaxB), then maps item w -> (image, detection) by a binary
+// search of the prefix in shared memory; consecutive CTAs write consecutive slabs of the same map.
+constexpr int kMaskMaxB = 2048;
+template <bool kStream>
+__global__ void __launch_bounds__(512) mask_list_kernel(MaskArgs a, int rpi, int nslab) {
+  __shared__ int pre[kMaskMaxB + 1];
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int run = 0;
+    if (lane == 0) pre[0] = 0;
+    for (int b0 = 0; b0 < a.B; b0 += 32) {
+      int c = b0 + lane < a.B ? min(__ldg(a.det_count + b0 + lane), a.max_det) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (b0 + lane < a.B) pre[b0 + lane + 1] = run + incl;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  __syncthreads();
+  const int total = pre[a.B] * nslab;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const int slab = w % nslab, i = w / nslab;
+    int lo = 0, hi = a.B;                       // largest b with pre[b] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (pre[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    mask_slab<kStream>(a, rpi, slab, i - pre[lo], lo);
   }
 }
 
 int g_mask_stream = 1;
+int g_mask_list = 0;      // 1: work-list kernel, 0 (default; measured 13 % faster at batch 64): one CTA per possible (slab, detection, image)
 
 // ------------------------------------------------------------------------------------------
 // Box-cropped form of the same maps: the reference's consumer only ever reads
@@ -651,6 +715,7 @@ __global__ void __launch_bounds__(256) crop_mask_kernel(MaskArgs a, const long l
 }  // namespace
 
 void masks_set_streaming(int on) { g_mask_stream = on; }
+void masks_set_work_list(int on) { g_mask_list = on; }
 
 int launch_decode(const DecodeArgs& a, cudaStream_t st) {
   DY_CHECK(a.num_class >= 1 && a.num_class <= kMaxClasses, "num_class");
@@ -700,9 +765,24 @@ int launch_masks(const MaskArgs& a, cudaStream_t st) {
   DY_CHECK(qpr <= 512, "score map too wide (S <= 2048)");
   int rpi = (256 + qpr / 2) / qpr;       // ~256 threads per CTA, a whole number of rows per pass
   if (rpi < 1) rpi = 1;
-  dim3 grid((a.S + kMaskRowsPerCta - 1) / kMaskRowsPerCta, a.max_det, a.B);
-  if (g_mask_stream) mask_kernel<true><<<grid, qpr * rpi, 0, st>>>(a, rpi);
-  else mask_kernel<false><<<grid, qpr * rpi, 0, st>>>(a, rpi);
+  const int nslab = (a.S + kMaskRowsPerCta - 1) / kMaskRowsPerCta;
+  if (a.B <= kMaskMaxB && g_mask_list) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      DY_CUDA(cudaGetDevice(&dev));
+      DY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const long long items = (long long)nslab * a.max_det * a.B;
+    const int per_sm = 2048 / (qpr * rpi) > 8 ? 8 : 2048 / (qpr * rpi);      // resident CTAs per SM
+    const int grid = (int)(items < (long long)sms * per_sm ? items : (long long)sms * per_sm);
+    if (g_mask_stream) mask_list_kernel<true><<<grid, qpr * rpi, 0, st>>>(a, rpi, nslab);
+    else mask_list_kernel<false><<<grid, qpr * rpi, 0, st>>>(a, rpi, nslab);
+  } else {
+    dim3 grid(nslab, a.max_det, a.B);
+    if (g_mask_stream) mask_kernel<true><<<grid, qpr * rpi, 0, st>>>(a, rpi);
+    else mask_kernel<false><<<grid, qpr * rpi, 0, st>>>(a, rpi);
+  }
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

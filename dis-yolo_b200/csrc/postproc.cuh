@@ -73,6 +73,7 @@ int launch_masks(const MaskArgs& a, cudaStream_t st);
 // box-cropped maps: off[B*max_det+1] = exclusive scan of the crop areas (floats), then the packed crops
 int launch_crop_offsets(const MaskArgs& a, long long* off, cudaStream_t st);
 int launch_masks_cropped(const MaskArgs& a, const long long* off, float* out, cudaStream_t st);
+void masks_set_work_list(int on);   // 1: fixed grid walking the existing (slab, detection) items; 0 (default): one CTA per possible item
 void masks_set_streaming(int on);   // 1 (default): st.global.cs streaming stores, 0: plain stores
 
 }  // namespace dy

@@ -347,6 +347,8 @@ uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
  *   "wgrad_fuse_kw" 0 one CTA per tap / 1 (default) fused kernel rows where the N tile is kept / 2 always
  *   "wgrad_lbo_a", "wgrad_sbo_a", "wgrad_lbo_b", "wgrad_sbo_b"  bring-up: UMMA descriptor field overrides
  *   "mask_streaming_stores"     1 (default) st.global.cs in the mask-assembly kernel, 0 plain stores
+ *   "mask_work_list"            1 mask assembly walks the existing detections with a fixed grid, 0 (default) one CTA per
+ *                               possible (slab, detection, image)
  * Unknown names return DY_STATUS_NOTFOUND. */
 int dy_set_option(const char* name, int32_t value);
 

@@ -14,9 +14,19 @@ torch.cuda.synchronize()
 dets = int(out['det_count'].sum().item())
 yol = [eng.yolo(s, B) for s in range(3)]
 mp = eng.mask_pos(B)
-for mode in (1, 0, 1, 0):
-    set_option('mask_streaming_stores', mode)
-    for layout, m in (('nhwc', mp), ('planar', mp.permute(0, 3, 1, 2).contiguous())):
-        r = eng.postproc_profile(yol, m, win, 0.25, out['masks'], layout=layout, reps=20)
-        print('streaming=%d layout=%-6s dets=%d  %s  mask %.0f GB/s' % (mode, layout, dets, {k: round(v * 1e3, 1) for k, v in r.items()},
-                                                                     dets * 288 * 288 * 4 / (r['masks'] * 1e-3) / 1e9))
+pl = mp.permute(0, 3, 1, 2).contiguous()
+fill = torch.empty_like(out['masks'][:, :max(1, dets // B)])
+for _ in range(3):
+    fill.fill_(0.5)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    fill.fill_(0.5)
+e1.record(); torch.cuda.synchronize()
+print('fill_ of %d MB: %.1f us' % (fill.numel() * 4 // 2**20, e0.elapsed_time(e1) / 20 * 1e3))
+for stream, wl in ((1, 1), (1, 0), (0, 1), (0, 0), (1, 1), (1, 0)):
+    set_option('mask_streaming_stores', stream)
+    set_option('mask_work_list', wl)
+    r = eng.postproc_profile(yol, pl, win, 0.25, out['masks'], layout='planar', reps=20)
+    print('streaming=%d work_list=%d dets=%d  %s  mask %.0f GB/s' % (stream, wl, dets, {k: round(v * 1e3, 1) for k, v in r.items()},
+                                                                    dets * 288 * 288 * 4 / (r['masks'] * 1e-3) / 1e9))
