@@ -19,6 +19,16 @@
 #include "imgproc.cuh"
 #include "augment.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX ranges around the phases of the hot path (host-side markers: free unless a profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 namespace dy {
 
 static thread_local std::string g_last_error;
@@ -740,6 +750,7 @@ static int plan_layer(dy_net* net, int n) {
 }
 
 static int run_network_bf16(dy_net* net, const float* images, int B, cudaStream_t st, bool fused) {
+  NvtxRange nvtx_("dy:network(82 convs)");
   auto& L = net->L;
   note_launch();
   DY_TRY(launch_conv1(images, L[1].d_w_f32, L[1].d_scale, L[1].d_shift, net->cfg.alpha, B, net->S, net->S, L[1].s2d,
@@ -796,6 +807,7 @@ static int run_network(dy_net* net, const float* images, int B, cudaStream_t st,
 static int run_detect(dy_net* net, const float* y8, const float* y16, const float* y32, int B, const float* windows,
                       float thresh, float* dense_box, int* dense_cls, float* dense_score, float* det_raw,
                       float* det_box, int* det_count, cudaStream_t st) {
+  NvtxRange nvtx_("dy:decode+nms+topk");
   DecodeArgs da;
   memset(&da, 0, sizeof(da));
   da.yolo[0] = y8; da.yolo[1] = y16; da.yolo[2] = y32;
@@ -851,6 +863,7 @@ static MaskArgs mask_args(dy_net* net, const float* score, int layout, int B, co
 
 static int run_masks(dy_net* net, const float* score, int layout, int B, const int* det_count, float* masks,
                      cudaStream_t st) {
+  NvtxRange nvtx_("dy:mask_assembly");
   const MaskArgs ma = mask_args(net, score, layout, B, det_count, masks);
   note_launch();
   return launch_masks(ma, st);
@@ -1197,6 +1210,7 @@ static int forward_impl(dy_net* net, const float* images_dev, int32_t B, const f
 
 int dy_forward(dy_net* net, const float* images_dev, int32_t B, const float* windows_dev, float det_thresh,
                float* det_raw_dev, float* det_box_dev, int32_t* det_count_dev, float* masks_dev, void* stream) {
+  NvtxRange nvtx_("dy_forward");
   DY_CHECK(net && images_dev && windows_dev, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   DY_TRY(user_begin(net, st));
@@ -1294,6 +1308,7 @@ int dy_forward_host_begin(dy_net* net, const float* images_host, int32_t B, cons
 
 int dy_forward_host_begin_u8(dy_net* net, const uint8_t* images_host, int32_t B, const float* windows_host,
                              float det_thresh, int32_t mask_mode, int32_t* ticket) {
+  NvtxRange nvtx_("dy_forward_host_begin");
   return host_begin(net, images_host, true, B, windows_host, det_thresh, mask_mode, ticket);
 }
 
@@ -1319,6 +1334,7 @@ static int host_end_small(dy_net* net, dy_net::HostSlot& sl, float* det_raw_host
 
 int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
                         int32_t* det_count_host, float* masks_host) {
+  NvtxRange nvtx_("dy_forward_host_end");
   DY_CHECK(net && det_box_host && det_count_host, "null argument");
   DY_CHECK(ticket >= 0 && ticket < dy_net::kHostSlots, "bad ticket");
   auto& sl = net->slot[ticket];
@@ -1347,6 +1363,7 @@ int dy_forward_host_end(dy_net* net, int32_t ticket, float* det_raw_host, float*
 int dy_forward_host_end_cropped(dy_net* net, int32_t ticket, float* det_raw_host, float* det_box_host,
                                 int32_t* det_count_host, int64_t* crop_offsets_host, float* crops_host,
                                 int64_t crops_capacity) {
+  NvtxRange nvtx_("dy_forward_host_end_cropped");
   DY_CHECK(net && det_box_host && det_count_host && crop_offsets_host && crops_host, "null argument");
   DY_CHECK(ticket >= 0 && ticket < dy_net::kHostSlots, "bad ticket");
   auto& sl = net->slot[ticket];
@@ -2458,6 +2475,7 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
                      const float* yolo1_dev, const float* true_boxes_dev, const uint8_t* true_masks_dev,
                      const int32_t* perm_prop_dev, const int32_t* perm_gt_dev, float det_thresh, float* losses_host,
                      void* stream) {
+  NvtxRange nvtx_("dy_train_forward");
   DY_CHECK(net && images_dev && yolo3_dev && yolo2_dev && yolo1_dev && true_boxes_dev && true_masks_dev &&
                perm_prop_dev && perm_gt_dev && losses_host, "null argument");
   DY_CHECK(net->train_ready, "dy_train_init has not been called");
@@ -2528,6 +2546,7 @@ int dy_train_forward(dy_net* net, const float* images_dev, int32_t B, const floa
 }
 
 int dy_train_backward(dy_net* net, int32_t B, int32_t layer_hi, int32_t layer_lo, float* grad_flat_dev, void* stream) {
+  NvtxRange nvtx_("dy_train_backward");
   DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
   DY_CHECK(layer_lo >= 1 && layer_hi <= 82 && layer_lo <= layer_hi, "layer range");
   DY_TRY(user_begin(net, (cudaStream_t)stream));
@@ -2540,6 +2559,7 @@ int dy_train_backward(dy_net* net, int32_t B, int32_t layer_hi, int32_t layer_lo
 }
 
 int dy_train_apply(dy_net* net, const float* grad_flat_dev, float lr, float grad_scale, void* stream) {
+  NvtxRange nvtx_("dy_train_apply");
   DY_CHECK(net && net->train_ready && grad_flat_dev, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   DY_TRY(user_begin(net, st));
