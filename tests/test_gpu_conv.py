@@ -151,3 +151,36 @@ def test_conv_bf16_forced_modes(case, resident, halo, staged, tma, dual):
     e = rel_err(got, want)
     assert e < 5e-3, 'resident=%d halo=%d staged=%d tma=%d rel err %.3g' % (resident, halo, staged, tma, e)
     assert float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 0.25))) < 1e-2
+
+
+@pytest.mark.parametrize('halo,split,slab', [(0, 0, -1), (1, 1, -1), (0, 1, 32), (1, 0, 32)])
+@pytest.mark.parametrize('case', [CASES[0], CASES[3], CASES[5], CASES[7], CASES[8], CASES[10],
+                                  (3, 19, 17, 128, 256, 3, 1, True, True),      # odd tile count, residual
+                                  (1, 8, 8, 256, 128, 1, 1, True, False)],      # a single (half-empty) pair tile
+                         ids=lambda c: 'B%d_%dx%d_%d-%d_k%ds%d' % c[:7])
+def test_conv_bf16_cta_pairs(case, halo, split, slab):
+    """CTA-pair plans (2-CTA clusters, tcgen05.mma.cta_group::2 with M = 256, each CTA staging half of the weight
+    tile) forced on small shapes -- odd numbers of 128-row tiles (the second CTA of the last pair works on rows
+    beyond the tensor), residuals, stride 2, with and without the shared halo box / the column-split epilogue /
+    32-column staging slabs -- against the oracle, and bit for bit against the single-CTA plan with the same K order."""
+    import torch
+    from disyolo_b200.engine import conv_layer, set_option
+    x, w, scale, shift, r = _make(case, 17)
+    xc = torch.from_numpy(x).cuda()
+    rc = torch.from_numpy(r).cuda() if r is not None else None
+    want = _oracle(bf16_round(x), bf16_round(w), case[6], scale, shift, case[7],
+                   bf16_round(r) if r is not None else None)
+    opts = dict(tc_cta2=1, tc_halo=halo, tc_split_n=split, tc_slab=slab)
+    try:
+        for k, v in opts.items():
+            set_option(k, v)
+        got = conv_layer(xc, w, case[6], scale, shift, case[7], 0.1, rc, 'bf16').cpu().numpy()
+        set_option('tc_cta2', 0)
+        single = conv_layer(xc, w, case[6], scale, shift, case[7], 0.1, rc, 'bf16').cpu().numpy()
+    finally:
+        for k in opts:
+            set_option(k, -1)
+    e = rel_err(got, want)
+    assert e < 5e-3, 'cta2 halo=%d split=%d slab=%d rel err %.3g' % (halo, split, slab, e)
+    assert float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 0.25))) < 1e-2
+    assert np.array_equal(got, single), 'CTA-pair plan differs from the single-CTA plan (same K order)'

@@ -148,3 +148,31 @@ def test_detect_stress_many_boxes():
     for d in sel:
         assert np.max(np.abs(got[0, d] - wm[d])) < 1e-6
     e.close()
+
+
+def test_nms_multi_batch_with_massive_ties():
+    """The batched NMS beyond one shared-memory batch (2048 candidates per class): thousands of candidates that
+    share a handful of score values (the radix select has to descend into the candidate-index bits of the key),
+    more selections than fit one batch's survivors, every class; keep sets and order bit-exact against the oracle."""
+    import disyolo_b200 as dy
+    e = dy.Engine(image_size=576, max_batch=2, precision='fp32', device=0, max_detection=400)
+    rng = np.random.default_rng(31)
+    N = 18000
+    box = np.zeros((2, N, 4), np.float32)
+    cy, cx = rng.random((2, N)).astype(np.float32), rng.random((2, N)).astype(np.float32)
+    h, w = (0.01 + 0.03 * rng.random((2, N))).astype(np.float32), (0.01 + 0.03 * rng.random((2, N))).astype(np.float32)
+    h[0] *= 4.0                                      # image 0: large boxes -> most candidates are suppressed, every
+    w[0] *= 4.0                                      # class walks through several 2048-candidate batches
+    box[..., 0], box[..., 1], box[..., 2], box[..., 3] = cy - h, cx - w, cy + h, cx + w
+    box = np.clip(box, 0.0, 1.0)
+    cls = rng.integers(0, 3, (2, N)).astype(np.int32)
+    score = rng.choice(np.array([0.9, 0.6, 0.6000001, 0.3], np.float32), (2, N)).astype(np.float32)
+    score[1] = 0.5                                   # image 1: ONE score value for all 18,000 candidates
+    idx, cnt, raw = [t.cpu().numpy() for t in e.nms(box, cls, score, 0.25)]
+    for b in range(2):
+        rows, kept = O.select_detections(box[b], cls[b], score[b], 0.25, max_detection=400)
+        n = len(kept)
+        assert cnt[b] == n and n >= 150
+        assert idx[b, :n].tolist() == kept.tolist(), 'image %d: keep set / order differs' % b
+        assert np.array_equal(raw[b, :n], rows)
+    e.close()
