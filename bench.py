@@ -279,7 +279,7 @@ def run_ours(args):
     eng.forward(img, win, THRESH, out=out)
     torch.cuda.synchronize()
     est = max(time.perf_counter() - tw0, 1e-3)
-    steady_steps = int(min(400, max(0, 1.5 / est)))
+    steady_steps = 0 if args.no_steady else int(min(400, max(0, 1.5 / est)))
     if dist is not None:
         t = torch.tensor([steady_steps], dtype=torch.int32, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -674,6 +674,7 @@ def stress_leg(local, peaks, B=4, size=1152, max_det=1000, thresh=0.05):
                decode_ms=pp['decode'], nms_ms=pp['nms'], finalize_ms=pp['finalize'], masks_ms=pp['masks'],
                mask_bytes=mask_bytes, mask_gbs=mask_bytes / (pp['masks'] / 1e3) / 1e9,
                mask_frac_of_hbm=mask_bytes / (pp['masks'] / 1e3) / 1e9 / peaks['hbm_gbs'],
+               hbm_peak_note='MEASURED_PEAKS hbm_gbs is a read+write copy figure; a store-dominated kernel can exceed it',
                decode_bytes=B * eng.num_candidates * 32,
                decode_frac_of_hbm=B * eng.num_candidates * 32 / (pp['decode'] / 1e3) / 1e9 / peaks['hbm_gbs'])
     eng.close()
@@ -731,6 +732,7 @@ def main():
                          'THIS build (profiles/); omitted -> roofline.traffic is null (never a stale constant)')
     ap.add_argument('--no-numa', action='store_true', help='do not bind the process to the GPU NUMA node')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step leg (BASELINE configs[3])')
+    ap.add_argument('--no-steady', action='store_true', help='skip the steady-state warm-up (profiler runs)')
     ap.add_argument('--no-stress', action='store_true', help='skip the 1152^2 stress leg (BASELINE configs[4])')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
