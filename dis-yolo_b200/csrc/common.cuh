@@ -121,7 +121,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
+#ifdef DY_NO_WAIT_HINT
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#else
+      // suspend-time hint (ns, as cutlass::arch::ClusterBarrier::wait passes it): the waiting thread sleeps in
+      // hardware until the phase flips instead of re-issuing the probe every ~50 cycles
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, 0x989680;\n\t"
+#endif
       "selp.u32 %0, 1, 0, P;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)

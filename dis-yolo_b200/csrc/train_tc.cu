@@ -58,7 +58,10 @@ __device__ __forceinline__ bool p1_pixel(uint32_t r, uint32_t Hp, uint32_t Wp, i
   return *x < W && *y < H;
 }
 
-// per-channel reductions: fp32 partial sums per thread are flushed to double every 8 row groups
+// per-channel reductions: fp32 partial sums per thread are flushed to double every 8 row groups.
+// BWD: g = dy * leaky'(z*a+b);  s1 = sum g;  s2 = sum g*xhat = invstd * (sum g*z - mean * sum g) -- the loop only
+// accumulates sum g and sum g*z (two per-channel constants fewer in registers), the affine part is applied once
+// per block in double.  Pad pixels carry dy = 0 and z = 0: the flat row space needs no pixel arithmetic.
 template <bool BWD>
 __global__ void __launch_bounds__(kT, 2)
 p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ z,
@@ -72,12 +75,10 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
   double d1[8], d2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) d1[j] = d2[j] = 0.0;
-  float fa[8], fb[8], fm[8], fi[8];
+  float fa[8], fb[8];
   if (BWD) {
     load8f(a + v * 8, fa);
     load8f(b + v * 8, fb);
-    load8f(mean + v * 8, fm);
-    load8f(invstd + v * 8, fi);
   }
   uint32_t r = blockIdx.x * (uint32_t)R + rl;
   while (r < rows) {
@@ -108,13 +109,13 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
             float g = fu[j];               // rows beyond the end and pad pixels carry dy = 0
             if (act && !(fmaf(fz[j], fa[j], fb[j]) > 0.f)) g *= alpha;
             p1[j] += g;
-            p2[j] += g * ((fz[j] - fm[j]) * fi[j]);
+            p2[j] = fmaf(g, fz[j], p2[j]);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             p1[j] += fu[j];
-            p2[j] += fu[j] * fu[j];
+            p2[j] = fmaf(fu[j], fu[j], p2[j]);
           }
         }
       }
@@ -131,13 +132,17 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
     sm[(8 + j) * kT + threadIdx.x] = d2[j];
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < 16 * cv; o += kT) {
+  for (int o = threadIdx.x; o < 8 * cv; o += kT) {
     const int j = o / cv, x = o - j * cv;
-    double t = 0.0;
-    for (int q = 0; q < R; ++q) t += sm[j * kT + q * cv + x];
-    const int ch = x * 8 + (j & 7);
-    if (j < 8) atomicAdd(o1 + ch, t);
-    else if (o2) atomicAdd(o2 + ch, t);
+    double t1 = 0.0, t2 = 0.0;
+    for (int q = 0; q < R; ++q) {
+      t1 += sm[j * kT + q * cv + x];
+      t2 += sm[(8 + j) * kT + q * cv + x];
+    }
+    const int ch = x * 8 + j;
+    if (BWD) t2 = (double)__ldg(invstd + ch) * (t2 - (double)__ldg(mean + ch) * t1);
+    atomicAdd(o1 + ch, t1);
+    if (o2) atomicAdd(o2 + ch, t2);
   }
 }
 
@@ -158,39 +163,39 @@ struct BnFinalize {
   float eps;
 };
 
-__global__ void __launch_bounds__(kT)
+// Both elementwise kernels walk the tensor by IMAGE ROW: a row (n, y) of the P1 layout is W*C contiguous valid
+// elements, so a block streams it with thread t owning the 16-byte channel vector t % (C/8) of the pixels
+// t / (C/8) + k*(256 / (C/8)) -- no per-vector pixel arithmetic (one division per image row), no validity tests
+// beyond x < W.  (The first version walked flat pixel rows and divided twice per 16-byte vector: 2 TB/s.)
+__global__ void __launch_bounds__(kT, 3)
 bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ a, const float* __restrict__ b,
-                 BnFinalize fin, const __nv_bfloat16* __restrict__ residual, uint32_t rows, int H, int W, int C,
+                 BnFinalize fin, const __nv_bfloat16* __restrict__ residual, int B, int H, int W, int C,
                  float alpha, int act, __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up,
                  __nv_bfloat16* __restrict__ out_s2d) {
   const int cv = C >> 3;
-  const uint32_t Hp = H + 1, Wp = W + 1;
-  const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
-  const uint32_t G = gridDim.x * (uint32_t)R;
+  const int Hp = H + 1, Wp = W + 1;
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv, P = kT / cv;
   float fa[8], fb[8];
   if (fin.sum != nullptr) {
-    // the double-precision finalize is done once per block (row-0 threads, one vector column each) and
-    // shared through smem: FP64 sqrt / div are too slow to repeat in every thread
+    // batch-moment finalize in double, ONE channel per thread (FP64 division / sqrt are long dependent chains:
+    // eight channels per thread on eight threads cost every block ~10 us), shared through smem
     __shared__ float s_a[8 * kT], s_b[8 * kT];
-    if (rl == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = v * 8 + j;
-        const double m = fin.sum[c] / (double)fin.M;
-        double var = fin.sumsq[c] / (double)fin.M - m * m;
-        if (var < 0.0) var = 0.0;
-        const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
-        const float aa = fin.gamma[c] * is;
-        const float bb = fin.beta[c] - (float)m * aa;
-        s_a[c] = aa;
-        s_b[c] = bb;
-        if (blockIdx.x == 0) {
-          fin.a_out[c] = aa;
-          fin.b_out[c] = bb;
-          fin.mean_out[c] = (float)m;
-          fin.var_out[c] = (float)var;
-          fin.invstd_out[c] = is;
-        }
+    const double invM = 1.0 / (double)fin.M;
+    for (int c = threadIdx.x; c < C; c += kT) {
+      const double m = fin.sum[c] * invM;
+      double var = fin.sumsq[c] * invM - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
+      const float aa = fin.gamma[c] * is;
+      const float bb = fin.beta[c] - (float)m * aa;
+      s_a[c] = aa;
+      s_b[c] = bb;
+      if (blockIdx.x == 0) {
+        fin.a_out[c] = aa;
+        fin.b_out[c] = bb;
+        fin.mean_out[c] = (float)m;
+        fin.var_out[c] = (float)var;
+        fin.invstd_out[c] = is;
       }
     }
     __syncthreads();
@@ -203,122 +208,136 @@ bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ 
     load8f(a + v * 8, fa);
     load8f(b + v * 8, fb);
   }
-  for (uint32_t r = blockIdx.x * (uint32_t)R + rl; r < rows; r += kUnroll * G) {
-    uint4 qz[kUnroll], qr[kUnroll];
-    int pn[kUnroll], py[kUnroll], px[kUnroll];
-    bool ok[kUnroll];
+  const int NH = B * H;
+  for (int ry = blockIdx.x; ry < NH; ry += gridDim.x) {
+    const int n = ry / H, y = ry - n * H;
+    const size_t rowpix = ((size_t)n * Hp + y) * Wp;
+    for (int x0 = pl; x0 < W; x0 += kUnroll * P) {
+      uint4 qz[kUnroll], qr[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const uint32_t rr = r + k * G;
-      ok[k] = rr < rows && p1_pixel(rr, Hp, Wp, H, W, &pn[k], &py[k], &px[k]);
-      qr[k] = make_uint4(0, 0, 0, 0);
-      if (ok[k]) {
-        qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)rr * C) + v);
-        if (residual) qr[k] = __ldg(reinterpret_cast<const uint4*>(residual + (size_t)rr * C) + v);
+      for (int k = 0; k < kUnroll; ++k) {
+        const int x = x0 + k * P;
+        qr[k] = make_uint4(0, 0, 0, 0);
+        if (x < W) {
+          qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (rowpix + x) * C) + v);
+          if (residual) qr[k] = __ldg(reinterpret_cast<const uint4*>(residual + (rowpix + x) * C) + v);
+        }
       }
-    }
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      if (!ok[k]) continue;
-      const uint32_t rr = r + k * G;
-      float fz[8], fr[8];
-      unpack8(qz[k], fz);
-      unpack8(qr[k], fr);
+      for (int k = 0; k < kUnroll; ++k) {
+        const int x = x0 + k * P;
+        if (x >= W) continue;
+        float fz[8], fr[8];
+        unpack8(qz[k], fz);
+        unpack8(qr[k], fr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(fz[j], fa[j], fb[j]);
-        if (act) t = fmaxf(alpha * t, t);
-        fz[j] = t + fr[j];
-      }
-      const uint4 q = pack8(fz);
-      if (out_same) reinterpret_cast<uint4*>(out_same + (size_t)rr * C)[v] = q;
-      if (out_up) {
-        const size_t Wu = 2 * W + 1, Hu = 2 * H + 1;
-        const size_t ru = ((size_t)pn[k] * Hu + 2 * py[k]) * Wu + 2 * px[k];
-        reinterpret_cast<uint4*>(out_up + ru * C)[v] = q;
-        reinterpret_cast<uint4*>(out_up + (ru + 1) * C)[v] = q;
-        reinterpret_cast<uint4*>(out_up + (ru + Wu) * C)[v] = q;
-        reinterpret_cast<uint4*>(out_up + (ru + Wu + 1) * C)[v] = q;
-      }
-      if (out_s2d) {      // space-to-depth copy for a stride-2 consumer: [N, H/2+1, W/2+1, 4C], block (y&1)*2+(x&1)
-        const size_t Hq = H / 2 + 1, Wq = W / 2 + 1;
-        const size_t rs = ((size_t)pn[k] * Hq + (py[k] >> 1)) * Wq + (px[k] >> 1);
-        reinterpret_cast<uint4*>(out_s2d + rs * 4 * C + (((py[k] & 1) << 1) | (px[k] & 1)) * C)[v] = q;
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(fz[j], fa[j], fb[j]);
+          if (act) t = fmaxf(alpha * t, t);
+          fz[j] = t + fr[j];
+        }
+        const uint4 q = pack8(fz);
+        if (out_same) reinterpret_cast<uint4*>(out_same + (rowpix + x) * C)[v] = q;
+        if (out_up) {
+          const size_t Wu = 2 * W + 1, Hu = 2 * H + 1;
+          const size_t ru = ((size_t)n * Hu + 2 * y) * Wu + 2 * x;
+          reinterpret_cast<uint4*>(out_up + ru * C)[v] = q;
+          reinterpret_cast<uint4*>(out_up + (ru + 1) * C)[v] = q;
+          reinterpret_cast<uint4*>(out_up + (ru + Wu) * C)[v] = q;
+          reinterpret_cast<uint4*>(out_up + (ru + Wu + 1) * C)[v] = q;
+        }
+        if (out_s2d) {      // space-to-depth copy for a stride-2 consumer: [N, H/2+1, W/2+1, 4C], block (y&1)*2+(x&1)
+          const size_t Hq = H / 2 + 1, Wq = W / 2 + 1;
+          const size_t rs = ((size_t)n * Hq + (y >> 1)) * Wq + (x >> 1);
+          reinterpret_cast<uint4*>(out_s2d + rs * 4 * C + (((y & 1) << 1) | (x & 1)) * C)[v] = q;
+        }
       }
     }
   }
 }
 
-__global__ void __launch_bounds__(kT)
+// dz = g*k0 - k1 - xhat*k2 (mode 0) with xhat = (z - mean)*invstd, folded to  dz = g*k0 + c1 + z*c2
+// (c2 = -invstd*k2, c1 = mean*invstd*k2 - k1: three per-channel constants instead of five), or g*a (mode 1).
+// Writes EVERY pixel of the flat row space [0, rows_out): zeros at pad pixels and in the tail (dz is a scratch
+// shared by layers of different geometry).
+__global__ void __launch_bounds__(kT, 3)
 bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                        const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                        const double* __restrict__ s1, const double* __restrict__ s2, float alpha, int act, int mode,
-                       uint32_t rows, uint32_t rows_out, long long mvalid, int H, int W, int C,
+                       uint32_t rows, uint32_t rows_out, long long mvalid, int B, int H, int W, int C,
                        __nv_bfloat16* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int cv = C >> 3;
-  const uint32_t Hp = H + 1, Wp = W + 1;
-  const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
-  const uint32_t G = gridDim.x * (uint32_t)R;
+  const int Hp = H + 1, Wp = W + 1;
+  const int v = threadIdx.x % cv, pl = threadIdx.x / cv, P = kT / cv;
   const float invM = 1.f / (float)mvalid;
-  if (dgamma != nullptr && blockIdx.x == 0 && rl == 0) {      // d gamma = sum g*xhat, d beta = sum g (copy_stats)
+  if (dgamma != nullptr && blockIdx.x == 0 && pl == 0) {      // d gamma = sum g*xhat, d beta = sum g (copy_stats)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       dgamma[v * 8 + j] = (float)s2[v * 8 + j];
       dbeta[v * 8 + j] = (float)s1[v * 8 + j];
     }
   }
-  // per-channel constants of this thread's 8 channels: dz = g*k0 - k1 - xhat*k2 (mode 0) or g*k0 (mode 1)
-  float fa[8], fb[8], k0[8], k1[8], k2[8], fm[8], fi[8];
+  float fa[8], fb[8], k0[8], c1[8], c2[8];
   load8f(a + v * 8, fa);
   load8f(b + v * 8, fb);
   if (mode == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { k0[j] = fa[j]; k1[j] = k2[j] = fm[j] = fi[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { k0[j] = fa[j]; c1[j] = c2[j] = 0.f; }
   } else {
-    float fg[8];
+    float fg[8], fm[8], fi[8];
     load8f(mean + v * 8, fm);
     load8f(invstd + v * 8, fi);
     load8f(gamma + v * 8, fg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       k0[j] = fg[j] * fi[j];
-      k1[j] = k0[j] * ((float)s1[v * 8 + j] * invM);
-      k2[j] = k0[j] * ((float)s2[v * 8 + j] * invM);
+      const float k1 = k0[j] * ((float)s1[v * 8 + j] * invM);
+      const float k2 = k0[j] * ((float)s2[v * 8 + j] * invM);
+      c2[j] = -fi[j] * k2;
+      c1[j] = fm[j] * fi[j] * k2 - k1;
     }
   }
-  for (uint32_t r = blockIdx.x * (uint32_t)R + rl; r < rows_out; r += kUnroll * G) {
-    uint4 qg[kUnroll], qz[kUnroll];
-    bool ok[kUnroll];
+  const int NHp = B * Hp;
+  for (int fr = blockIdx.x; fr < NHp; fr += gridDim.x) {
+    const int n = fr / Hp, y = fr - n * Hp;
+    const size_t rowpix = (size_t)fr * Wp;
+    const bool vrow = y < H;
+    for (int x0 = pl; x0 < Wp; x0 += kUnroll * P) {
+      uint4 qg[kUnroll], qz[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const uint32_t rr = r + k * G;
-      int n, y, x;
-      ok[k] = rr < rows && p1_pixel(rr, Hp, Wp, H, W, &n, &y, &x);
-      if (ok[k]) {
-        qg[k] = __ldg(reinterpret_cast<const uint4*>(dy + (size_t)rr * C) + v);
-        qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (size_t)rr * C) + v);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-      const uint32_t rr = r + k * G;
-      if (rr >= rows_out) continue;
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (ok[k]) {
-        float fg[8], fz[8];
-        unpack8(qg[k], fg);
-        unpack8(qz[k], fz);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float g = fg[j];
-          if (act && !(fmaf(fz[j], fa[j], fb[j]) > 0.f)) g *= alpha;
-          fg[j] = mode == 1 ? g * k0[j] : g * k0[j] - k1[j] - ((fz[j] - fm[j]) * fi[j]) * k2[j];
+      for (int k = 0; k < kUnroll; ++k) {
+        const int x = x0 + k * P;
+        if (vrow && x < W) {
+          qg[k] = __ldg(reinterpret_cast<const uint4*>(dy + (rowpix + x) * C) + v);
+          qz[k] = __ldg(reinterpret_cast<const uint4*>(z + (rowpix + x) * C) + v);
         }
-        q = pack8(fg);
       }
-      reinterpret_cast<uint4*>(dz + (size_t)rr * C)[v] = q;
+#pragma unroll
+      for (int k = 0; k < kUnroll; ++k) {
+        const int x = x0 + k * P;
+        if (x >= Wp) continue;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (vrow && x < W) {
+          float fg[8], fz[8];
+          unpack8(qg[k], fg);
+          unpack8(qz[k], fz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g = fg[j];
+            if (act && !(fmaf(fz[j], fa[j], fb[j]) > 0.f)) g *= alpha;
+            fg[j] = fmaf(fz[j], c2[j], fmaf(g, k0[j], c1[j]));
+          }
+          q = pack8(fg);
+        }
+        reinterpret_cast<uint4*>(dz + (rowpix + x) * C)[v] = q;
+      }
     }
+  }
+  if (blockIdx.x == 0) {      // tail rows [rows, rows_out)
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < (rows_out - rows) * (uint32_t)cv; i += kT)
+      reinterpret_cast<uint4*>(dz + (size_t)rows * C)[i] = zero;
   }
 }
 
@@ -766,6 +785,13 @@ static int row_grid(long long rows, int C) {
   return (int)g;
 }
 
+// image-row kernels: one block per image row, at most 8 resident waves
+static int image_row_grid(long long image_rows) {
+  long long g = image_rows;
+  if (g > 148 * 8) g = 148 * 8;
+  return g < 1 ? 1 : (int)g;
+}
+
 // reductions end with 2*C double atomics per block: cap the grid so that a launch issues at most ~256K of
 // them (a wide, low-resolution layer would otherwise spend its time serialising atomics in L2)
 static int reduce_grid(long long rows, int C) {
@@ -800,8 +826,8 @@ int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, con
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
   BnFinalize fin;
   memset(&fin, 0, sizeof(fin));
-  bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, a, b, fin, residual, (uint32_t)rows, H, W, C, alpha, act,
-                                                     out_same, out_up, out_s2d);
+  bn_act_p1_kernel<<<image_row_grid((long long)B * H), kT, 0, st>>>(z, a, b, fin, residual, B, H, W, C, alpha, act,
+                                                                    out_same, out_up, out_s2d);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -814,8 +840,8 @@ int launch_bn_finalize_act_p1(const __nv_bfloat16* z, const double* sum, const d
   const long long rows = (long long)B * (H + 1) * (W + 1);
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
   BnFinalize fin{sum, sumsq, gamma, beta, a, b, mean, var, invstd, M, eps};
-  bn_act_p1_kernel<<<row_grid(rows, C), kT, 0, st>>>(z, nullptr, nullptr, fin, residual, (uint32_t)rows, H, W, C, alpha,
-                                                     act, out_same, out_up, out_s2d);
+  bn_act_p1_kernel<<<image_row_grid((long long)B * H), kT, 0, st>>>(z, nullptr, nullptr, fin, residual, B, H, W, C,
+                                                                    alpha, act, out_same, out_up, out_s2d);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
@@ -830,9 +856,9 @@ int launch_bn_bwd_apply_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, cons
   const long long rows = (long long)B * (H + 1) * (W + 1);
   const long long ro = round_up64(rows);
   DY_CHECK(kT % (C / 8) == 0 && C <= 8 * kT && ro < (1ll << 31), "channel count / rows");
-  bn_bwd_apply_p1_kernel<<<row_grid(ro, C), kT, 0, st>>>(dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act, mode,
-                                                         (uint32_t)rows, (uint32_t)ro, (long long)B * H * W, H, W, C,
-                                                         dz, dgamma, dbeta);
+  bn_bwd_apply_p1_kernel<<<image_row_grid((long long)B * (H + 1)), kT, 0, st>>>(
+      dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act, mode, (uint32_t)rows, (uint32_t)ro, (long long)B * H * W, B, H,
+      W, C, dz, dgamma, dbeta);
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }
