@@ -982,6 +982,7 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_kchunk") g_opt_kchunk = value;
   else if (n == "tc_slab") g_opt_slab = value;
   else if (n == "tc_pdl") conv_tc_set_pdl(value < 0 ? 1 : value);
+  else if (n == "train_pdl") train_set_pdl(value < 0 ? 1 : value);
   else if (n == "tc_dual_producer") g_opt_dual_producer = value;
   else if (n == "tc_max_stages") g_opt_max_stages = value;
   else if (n == "tc_skip_epilogue") g_opt_skip_epi = value;

@@ -9,6 +9,7 @@ namespace dy {
 namespace {
 
 constexpr int kT = 256;
+int g_train_pdl = 1;      // 1: the BN / elementwise / wgrad kernels are launched with programmatic stream serialization
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -68,6 +69,8 @@ p1_reduce_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __res
                  const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ mean,
                  const float* __restrict__ invstd, float alpha, int act, uint32_t rows, int C,
                  double* __restrict__ o1, double* __restrict__ o2) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   __shared__ double sm[16 * kT];
   const int cv = C >> 3;
   const int v = threadIdx.x % cv, rl = threadIdx.x / cv, R = kT / cv;
@@ -172,6 +175,8 @@ bn_act_p1_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ 
                  BnFinalize fin, const __nv_bfloat16* __restrict__ residual, int B, int H, int W, int C,
                  float alpha, int act, __nv_bfloat16* __restrict__ out_same, __nv_bfloat16* __restrict__ out_up,
                  __nv_bfloat16* __restrict__ out_s2d) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   const int cv = C >> 3;
   const int Hp = H + 1, Wp = W + 1;
   const int v = threadIdx.x % cv, pl = threadIdx.x / cv, P = kT / cv;
@@ -267,6 +272,8 @@ bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
                        const double* __restrict__ s1, const double* __restrict__ s2, float alpha, int act, int mode,
                        uint32_t rows, uint32_t rows_out, long long mvalid, int B, int H, int W, int C,
                        __nv_bfloat16* __restrict__ dz, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   const int cv = C >> 3;
   const int Hp = H + 1, Wp = W + 1;
   const int v = threadIdx.x % cv, pl = threadIdx.x / cv, P = kT / cv;
@@ -346,6 +353,8 @@ bn_bwd_apply_p1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 __global__ void __launch_bounds__(kT)
 f32_to_p1_kernel(const float* __restrict__ src, long long rows, long long rows_out, int H, int W, int C, int Cg,
                  __nv_bfloat16* __restrict__ dst, float* __restrict__ colsum) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   __shared__ float part[64];
   const int cv = Cg >> 3, Hp = H + 1, Wp = W + 1;
   const long long total = rows_out * cv;
@@ -381,6 +390,8 @@ f32_to_p1_kernel(const float* __restrict__ src, long long rows, long long rows_o
 __global__ void __launch_bounds__(kT)
 pool2x2_p1_kernel(const __nv_bfloat16* __restrict__ src, long long rows, long long rows_out, int h, int w, int C,
                   __nv_bfloat16* __restrict__ dst) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   const int cv = C >> 3, Hp = h + 1, Wp = w + 1;
   const long long total = rows_out * cv;
   const long long Wu = 2 * w + 1, Hu = 2 * h + 1;
@@ -406,6 +417,8 @@ pool2x2_p1_kernel(const __nv_bfloat16* __restrict__ src, long long rows, long lo
 
 __global__ void add_p1_kernel(__nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ src, long long nvec,
                               int copy) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const uint4 s = __ldg(reinterpret_cast<const uint4*>(src) + i);
@@ -594,6 +607,8 @@ __global__ void __launch_bounds__(kT, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapX0, const __grid_constant__ CUtensorMap mapX1,
                 const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ WgradParams p, int dbg_lbo_a,
                 int dbg_sbo_a, int dbg_lbo_b, int dbg_sbo_b) {
+  pdl_launch_dependents();      // the next kernel of the step may be scheduled while this one drains ...
+  pdl_wait();                   // ... and this one starts its work only when its predecessor has completed
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kWgradMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kWgradMaxStages];
@@ -770,6 +785,7 @@ int g_wgrad_fuse = 1;
 }  // namespace
 
 void wgrad_set_fuse(int on) { g_wgrad_fuse = on; }
+void train_set_pdl(int on) { g_train_pdl = on; }
 
 void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b) {
   g_wdbg[0] = lbo_a; g_wdbg[1] = sbo_a; g_wdbg[2] = lbo_b; g_wdbg[3] = sbo_b;
@@ -803,9 +819,8 @@ static int reduce_grid(long long rows, int C) {
 
 int launch_bn_stats_p1(const __nv_bfloat16* z, long long rows, int C, double* sum, double* sumsq, cudaStream_t st) {
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
-  p1_reduce_kernel<false><<<reduce_grid(rows, C), kT, 0, st>>>(z, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0,
-                                                            (uint32_t)rows, C, sum, sumsq);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(p1_reduce_kernel<false>, dim3(reduce_grid(rows, C)), dim3(kT), 0, st, g_train_pdl != 0, z, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, 0.f, 0, (uint32_t)rows, C, sum, sumsq));
   return DY_OK;
 }
 
@@ -813,9 +828,8 @@ int launch_bn_bwd_reduce_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, con
                             const float* mean, const float* invstd, float alpha, int act, long long rows, int C,
                             double* s1, double* s2, cudaStream_t st) {
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
-  p1_reduce_kernel<true><<<reduce_grid(rows, C), kT, 0, st>>>(dy, z, a, b, mean, invstd, alpha, act, (uint32_t)rows, C,
-                                                           s1, s2);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(p1_reduce_kernel<true>, dim3(reduce_grid(rows, C)), dim3(kT), 0, st, g_train_pdl != 0, dy, z, a, b, mean,
+                            invstd, alpha, act, (uint32_t)rows, C, s1, s2));
   return DY_OK;
 }
 
@@ -826,9 +840,8 @@ int launch_bn_act_p1(const __nv_bfloat16* z, const float* a, const float* b, con
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
   BnFinalize fin;
   memset(&fin, 0, sizeof(fin));
-  bn_act_p1_kernel<<<image_row_grid((long long)B * H), kT, 0, st>>>(z, a, b, fin, residual, B, H, W, C, alpha, act,
-                                                                    out_same, out_up, out_s2d);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(bn_act_p1_kernel, dim3(image_row_grid((long long)B * H)), dim3(kT), 0, st, g_train_pdl != 0, z, a, b, fin,
+                            residual, B, H, W, C, alpha, act, out_same, out_up, out_s2d));
   return DY_OK;
 }
 
@@ -840,9 +853,8 @@ int launch_bn_finalize_act_p1(const __nv_bfloat16* z, const double* sum, const d
   const long long rows = (long long)B * (H + 1) * (W + 1);
   DY_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && C <= 8 * kT && rows < (1ll << 31), "channel count / rows");
   BnFinalize fin{sum, sumsq, gamma, beta, a, b, mean, var, invstd, M, eps};
-  bn_act_p1_kernel<<<image_row_grid((long long)B * H), kT, 0, st>>>(z, nullptr, nullptr, fin, residual, B, H, W, C,
-                                                                    alpha, act, out_same, out_up, out_s2d);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(bn_act_p1_kernel, dim3(image_row_grid((long long)B * H)), dim3(kT), 0, st, g_train_pdl != 0, z, nullptr,
+                            nullptr, fin, residual, B, H, W, C, alpha, act, out_same, out_up, out_s2d));
   return DY_OK;
 }
 
@@ -856,10 +868,9 @@ int launch_bn_bwd_apply_p1(const __nv_bfloat16* dy, const __nv_bfloat16* z, cons
   const long long rows = (long long)B * (H + 1) * (W + 1);
   const long long ro = round_up64(rows);
   DY_CHECK(kT % (C / 8) == 0 && C <= 8 * kT && ro < (1ll << 31), "channel count / rows");
-  bn_bwd_apply_p1_kernel<<<image_row_grid((long long)B * (H + 1)), kT, 0, st>>>(
-      dy, z, a, b, mean, invstd, gamma, s1, s2, alpha, act, mode, (uint32_t)rows, (uint32_t)ro, (long long)B * H * W, B, H,
-      W, C, dz, dgamma, dbeta);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(bn_bwd_apply_p1_kernel, dim3(image_row_grid((long long)B * (H + 1))), dim3(kT), 0, st, g_train_pdl != 0, dy,
+                            z, a, b, mean, invstd, gamma, s1, s2, alpha, act, mode, (uint32_t)rows, (uint32_t)ro,
+                            (long long)B * H * W, B, H, W, C, dz, dgamma, dbeta));
   return DY_OK;
 }
 
@@ -869,8 +880,8 @@ int launch_f32_to_p1(const float* src, int B, int H, int W, int C, __nv_bfloat16
   const long long rows = (long long)B * (H + 1) * (W + 1);
   const long long ro = round_up64(rows);
   if (colsum) DY_CUDA(cudaMemsetAsync(colsum, 0, (size_t)C * 4, st));
-  f32_to_p1_kernel<<<grid_for(ro * (Cg / 8)), kT, 0, st>>>(src, rows, ro, H, W, C, Cg, dst, colsum);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(f32_to_p1_kernel, dim3(grid_for(ro * (Cg / 8))), dim3(kT), 0, st, g_train_pdl != 0, src, rows, ro, H, W, C,
+                            Cg, dst, colsum));
   return DY_OK;
 }
 
@@ -878,22 +889,20 @@ int launch_pool2x2_p1(const __nv_bfloat16* src, int B, int h, int w, int C, __nv
   DY_CHECK(C % 8 == 0, "channel count");
   const long long rows = (long long)B * (h + 1) * (w + 1);
   const long long ro = round_up64(rows);
-  pool2x2_p1_kernel<<<grid_for(ro * (C / 8)), kT, 0, st>>>(src, rows, ro, h, w, C, dst);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(pool2x2_p1_kernel, dim3(grid_for(ro * (C / 8))), dim3(kT), 0, st, g_train_pdl != 0, src, rows, ro, h, w, C,
+                            dst));
   return DY_OK;
 }
 
 int launch_add_p1(__nv_bfloat16* dst, const __nv_bfloat16* src, long long n, cudaStream_t st) {
   DY_CHECK(n % 8 == 0, "element count");
-  add_p1_kernel<<<grid_for(n / 8), kT, 0, st>>>(dst, src, n / 8, 0);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(add_p1_kernel, dim3(grid_for(n / 8)), dim3(kT), 0, st, g_train_pdl != 0, dst, src, n / 8, 0));
   return DY_OK;
 }
 
 int launch_copy_p1(__nv_bfloat16* dst, const __nv_bfloat16* src, long long n, cudaStream_t st) {
   DY_CHECK(n % 8 == 0, "element count");
-  add_p1_kernel<<<grid_for(n / 8), kT, 0, st>>>(dst, src, n / 8, 1);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(add_p1_kernel, dim3(grid_for(n / 8)), dim3(kT), 0, st, g_train_pdl != 0, dst, src, n / 8, 1));
   return DY_OK;
 }
 
@@ -1013,9 +1022,8 @@ int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream
     DY_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
     attr = true;
   }
-  wgrad_tc_kernel<<<units * p.ksplit, kT, smem, st>>>(plan.x[0], plan.x[1], plan.z, p, g_wdbg[0], g_wdbg[1],
-                                                      g_wdbg[2], g_wdbg[3]);
-  DY_CUDA(cudaGetLastError());
+  DY_CUDA(launch_kernel_pdl(wgrad_tc_kernel, dim3(units * p.ksplit), dim3(kT), smem, st, g_train_pdl != 0, plan.x[0], plan.x[1], plan.z,
+                            p, g_wdbg[0], g_wdbg[1], g_wdbg[2], g_wdbg[3]));
   return DY_OK;
 }
 

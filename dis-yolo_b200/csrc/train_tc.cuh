@@ -109,6 +109,7 @@ int build_wgrad_plan(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, i
 int run_wgrad_plan(WgradPlan& plan, int B, int H, int W, int num_sms, cudaStream_t st);
 // measurement / bring-up aid: descriptor field overrides (0 = computed value)
 void wgrad_set_debug(int lbo_a, int sbo_a, int lbo_b, int sbo_b);
+void train_set_pdl(int on);    // A/B aid: 0 = plain stream order for the BN / elementwise / wgrad kernels, 1 (default) = PDL
 void wgrad_set_fuse(int on);   // A/B aid: 0 = one CTA per tap (no sharing), 1 (default) = fused kernel rows
 
 }  // namespace dy

@@ -336,6 +336,7 @@ uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
  *   "tc_staged", "tc_tma_epi"   epilogue through shared memory / through TMA stores + TMA residual loads
  *   "tc_dual_issue" two MMA-issuer threads with split stage rings (thin tiles)
  *   "tc_pdl"           0: conv launches in plain stream order; 1 (default): programmatic dependent launch
+ *   "train_pdl"        the same switch for the BN / elementwise / wgrad kernels of the training step
  *   "tc_dual_producer" with dual issue: 0 one TMA producer thread feeds both half rings, 1 (default) one each
  *   "tc_max_stages"    cap of the shared-memory pipeline depth (2..16)
  *   "tc_skip_epilogue"          measurement only: epilogues drain the accumulator and do nothing else
