@@ -258,6 +258,32 @@ def test_cuda_graph_replay_matches_eager():
     eng.close()
 
 
+def test_cuda_graph_replay_with_cta_pair_plans():
+    """The same with the plans of a batch-64 engine at 576 x 576 -- 2-CTA cluster launches (cta_group::2) carrying
+    the programmatic-dependent-launch attribute, the fused tail -- captured and replayed at batch 8."""
+    import torch
+    import disyolo_b200 as dy
+    B, size = 8, 576
+    eng = dy.Engine(image_size=size, max_batch=64, precision='bf16')
+    eng.load_weights(O.make_weights('lively', 0))
+    img, win = _inputs(B, size, 23)
+    img_d, win_d = torch.from_numpy(img).cuda(), torch.from_numpy(win).cuda()
+    out = eng.forward(img_d, win_d, 0.25)
+    torch.cuda.synchronize()
+    want = {k: v.clone() for k, v in out.items()}
+    g = eng.capture_graph(img_d, win_d, 0.25, out)
+    for _ in range(2):
+        for v in out.values():
+            v.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out['det_raw'], want['det_raw']) and torch.equal(out['det_count'], want['det_count'])
+        for b in range(B):
+            n = int(want['det_count'][b])
+            assert torch.equal(out['masks'][b, :n], want['masks'][b, :n])
+    eng.close()
+
+
 def test_first_forward_of_fresh_engines_is_reproducible():
     """Regression: the very first forward of a fresh engine (cold instruction / L2 caches, different
     warp timing) must give bit-identical head maps and score maps to later forwards and to other
