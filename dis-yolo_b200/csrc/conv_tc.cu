@@ -116,7 +116,8 @@ __device__ __forceinline__ void write_out16(const ConvParams& p, const OutDesc& 
   }
 }
 
-constexpr int kNumThreads = 384;     // 12 warps: producer, MMA, TMEM-alloc, spare, 2 x 4 epilogue warps
+// 4 role warps (producer, MMA, TMEM-alloc / second producer, second MMA issuer) + NWG epilogue warpgroups of 4 warps
+constexpr int conv_threads(int nwg) { return 128 * (1 + nwg); }
 
 // folded BN scale/shift (+ leaky) on one 16-column accumulator chunk.  Packed fp32x2 arithmetic
 // (FFMA2 / FMUL2, sm_100): each lane of a pair is an ordinary IEEE round-to-nearest fma / mul, so the
@@ -263,8 +264,11 @@ __device__ __forceinline__ void store_vec(const ConvParams& p, const OutDesc& o,
 // tile; the even CTA's MMA thread issues tcgen05.mma.cta_group::2 (M = 256) for both, each CTA's epilogue drains its
 // own 128 accumulator rows from its own TMEM.  Per SM this halves the weight bytes that cross L2 -> shared memory
 // and that the tensor core reads back, and doubles the pipeline depth a given amount of shared memory buys.
-template <int KCHUNK, bool FUSE, bool CTA2>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// NWG: epilogue warpgroups.  2 (384 threads, 160 registers) everywhere except the thin tiles (<= 64 columns): their
+// MMAs take 300-800 cycles per tile, which two warpgroups of latency-bound tcgen05.ld -> BN -> pack -> st.shared
+// chains cannot keep up with; there a THIRD warpgroup (512 threads, 128 registers) takes every third tile.
+template <int KCHUNK, bool FUSE, bool CTA2, int NWG>
+__global__ void __launch_bounds__(conv_threads(NWG), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapR,
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ ConvParams p) {
@@ -275,15 +279,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tfull_bar[4];
-  __shared__ __align__(8) uint64_t tempty_bar[4];
+  __shared__ __align__(8) uint64_t tfull_bar[6];
+  __shared__ __align__(8) uint64_t tempty_bar[6];
   __shared__ __align__(8) uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_scale[2][256];                 // per epilogue warpgroup
-  __shared__ __align__(16) float s_shift[2][256];
-  __shared__ long long s_dst[2][2][kBlockM];                      // [warpgroup][output][row] element offset / -1
-  __shared__ __align__(8) uint64_t res_full[2][2];                // [warpgroup][staging buffer] residual landed
-  __shared__ __align__(8) uint64_t fuse_bar[2][2];                // [warpgroup][accumulator] fused-tail MMA complete
+  __shared__ __align__(16) float s_scale[NWG][256];               // per epilogue warpgroup
+  __shared__ __align__(16) float s_shift[NWG][256];
+  __shared__ long long s_dst[NWG][2][kBlockM];                    // [warpgroup][output][row] element offset / -1
+  __shared__ __align__(8) uint64_t res_full[NWG][2];              // [warpgroup][staging buffer] residual landed
+  __shared__ __align__(8) uint64_t fuse_bar[NWG][2];              // [warpgroup][accumulator] fused-tail MMA complete
   __shared__ __align__(16) float s_fbias[16];
   __shared__ uint32_t tap_a16[kMaxSeg][3];                        // A start offset inside the stage, >>4
   __shared__ uint32_t tap_b16[kMaxSeg][3];                        // B start (absolute if resident, else in-stage), >>4
@@ -312,7 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int num_tiles = (CTA2 ? (p.n_tiles_m + 1) >> 1 : p.n_tiles_m) * p.n_tiles_n;
   const bool has_res = p.residual != nullptr;
   // fused tail: its weights [fuse_n x 64] bf16 (SWIZZLE_128B rows) sit behind the epilogue staging buffers
-  const uint32_t fuse_off = epi_off + 2u * 2u * (uint32_t)kBlockM * 64u * 2u;
+  const uint32_t fuse_off = epi_off + (uint32_t)NWG * 2u * (uint32_t)kBlockM * 64u * 2u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -326,15 +330,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 6; ++i) {
       mbar_init(&tfull_bar[i], 1);
       // one arrive per epilogue warp that drains the accumulator (a CTA pair: the warps of BOTH CTAs arrive on the
       // leader's barrier, where the MMA thread waits)
       mbar_init(&tempty_bar[i], (p.split_n ? 8 : 4) * (CTA2 ? 2 : 1));
     }
     mbar_init(&bres_bar, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i >> 1][i & 1], 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&fuse_bar[i >> 1][i & 1], 1);
+    for (int i = 0; i < 2 * NWG; ++i) mbar_init(&res_full[i >> 1][i & 1], 1);
+    for (int i = 0; i < 2 * NWG; ++i) mbar_init(&fuse_bar[i >> 1][i & 1], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -461,12 +465,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc_fence_after();
       }
       uint32_t stage = 0, phase = 0;
-      const int acc_sh = p.num_acc == 4 ? 2 : 1;
       int it = issuer;
       for (int tile = tile0 + issuer * tstride; tile < num_tiles; tile += it_step * tstride, it += it_step) {
-        const int acc = it & (p.num_acc - 1);           // num_acc is 2 or 4: parity(acc) == parity(it) == issuer
+        // accumulator stage of tile `it`: it % num_acc, used for the (it / num_acc)-th time.  num_acc is even with two
+        // issuers (issuer = parity of it = parity of acc) and a multiple of the number of epilogue warpgroups when
+        // they take alternate tiles, so every accumulator always meets the same issuer and the same warpgroup (an
+        // mbarrier only tells consecutive phases apart).
+        const int acc = it % p.num_acc;
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        mbar_wait(&tempty_bar[acc], ((uint32_t)(it >> acc_sh) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[acc], ((uint32_t)(it / p.num_acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         uint32_t acc_flag = 0u;
         for (int s = 0; s < p.num_seg; ++s) {
@@ -538,13 +545,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // split_n: BOTH warpgroups drain EVERY tile, half of its columns each -- the accumulator is handed back to
     // the MMA issuer after half the tcgen05.ld / residual round trips (a 256-column tile only has two TMEM
     // stages, so the drain time of one tile bounds the start of the tile after next)
-    const int t_first = p.split_n ? 0 : wg, t_step = p.split_n ? 1 : 2;
+    const int t_first = p.split_n ? 0 : wg, t_step = p.split_n ? 1 : NWG;     // (split_n: NWG == 2, checked on the host)
     const int cbase = p.split_n ? wg * (p.block_n >> 1) : 0;       // first column of this warpgroup inside the tile
     const int ncols = p.split_n ? (p.block_n >> 1) : p.block_n;    // columns this warpgroup drains
     int it = t_first;
-    for (int tile = tile0 + t_first * tstride; tile < num_tiles; tile += t_step * tstride, it += t_step) {
-      const int acc = it & (p.num_acc - 1);             // (no split: this warpgroup owns the accumulators of its tile parity)
-      const uint32_t acc_phase = (uint32_t)(it >> (p.num_acc == 4 ? 2 : 1)) & 1u;
+    uint32_t my_tiles = 0u;                             // tiles this warpgroup has processed (parity of its tables)
+    for (int tile = tile0 + t_first * tstride; tile < num_tiles; tile += t_step * tstride, it += t_step, ++my_tiles) {
+      const int acc = it % p.num_acc;                   // (no split: this warpgroup owns the accumulators it % NWG == wg)
+      const uint32_t acc_phase = (uint32_t)(it / p.num_acc) & 1u;
       const int m0 = (tile / p.n_tiles_n) * kTileM + m_off;
       const int n0 = (tile % p.n_tiles_n) * p.block_n;
       const long long m = (long long)m0 + q * 32 + lane;
@@ -623,7 +631,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // is no warpgroup barrier between two tiles; within a tile every slab has one, so nobody can be
         // two tiles ahead).
         // (the TMA path needs no table for out[0], so s_dst[wg][0..1] serve as the two parities)
-        long long* dst2 = s_dst[wg][(p.split_n ? it : (it >> 1)) & 1];
+        long long* dst2 = s_dst[wg][my_tiles & 1];
         if (dual) dst2[row] = dest_offset(p, p.out[1], px, m);
         if (elected && has_res && !res_primed) {
           // very first slab of this warpgroup: nothing has used the buffers yet
@@ -895,9 +903,10 @@ static size_t resident_bytes_of(int kchunk, const ConvParams& p) {
 
 static size_t epilogue_bytes_of(const ConvParams& p) {
   if (!p.slab) return 0;
-  if (p.tma_epi)                                                        // 2 warpgroups x 2 swizzled buffers
-    return 2 * 2 * (size_t)kBlockM * p.slab * 2 + (p.fuse_n ? (size_t)p.fuse_n * 128 : 0);   // (+ fused-tail weights)
-  return 2 * (size_t)kBlockM * ((size_t)p.slab * 2 + 16);
+  const size_t nwg = p.num_epi_wg == 3 ? 3 : 2;
+  if (p.tma_epi)                                                        // warpgroups x 2 swizzled buffers
+    return nwg * 2 * (size_t)kBlockM * p.slab * 2 + (p.fuse_n ? (size_t)p.fuse_n * 128 : 0);   // (+ fused-tail weights)
+  return nwg * (size_t)kBlockM * ((size_t)p.slab * 2 + 16);
 }
 
 int make_tmap_image_f32(CUtensorMap* out, const float* base, int N, int H, int W, int box_w_elems, int box_rows) {
@@ -928,7 +937,8 @@ size_t conv_tc_smem_bytes(int kchunk, const ConvParams& p) {
 }
 
 int conv_tc_pick_stages(int kchunk, const ConvParams& p) {
-  const size_t budget = 214 * 1024 - epilogue_bytes_of(p);
+  // (the three-warpgroup instantiation has 4 KB more static shared memory: per-warpgroup BN / offset tables)
+  const size_t budget = 214 * 1024 - epilogue_bytes_of(p) - (p.num_epi_wg == 3 ? 4096 : 0);
   const size_t res = resident_bytes_of(kchunk, p);
   if (res + 2 * stage_bytes_of(kchunk, p) > budget) return 0;
   int s = (int)((budget - res) / stage_bytes_of(kchunk, p));
@@ -946,8 +956,12 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
   DY_CHECK(kchunk == 64 || kchunk == 32, "kchunk");
   DY_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n");
   DY_CHECK(p.num_stages >= 2 && p.num_stages <= kMaxStages, "stages");
-  DY_CHECK(p.num_acc == 2 || p.num_acc == 4, "num_acc");
-  DY_CHECK(p.tmem_cols >= p.num_acc * p.block_n + (p.fuse_n ? 64 : 0) && p.tmem_cols <= 512, "tmem_cols");
+  DY_CHECK(p.num_acc == 2 || p.num_acc == 3 || p.num_acc == 4 || p.num_acc == 6, "num_acc");
+  const int nwg = p.num_epi_wg == 3 ? 3 : 2;
+  DY_CHECK(p.tmem_cols >= p.num_acc * p.block_n + (p.fuse_n ? nwg * 32 : 0) && p.tmem_cols <= 512, "tmem_cols");
+  DY_CHECK(nwg == 2 || (!p.cta2 && !p.split_n && p.block_n <= 64), "three epilogue warpgroups: thin single-CTA tiles only");
+  DY_CHECK(p.split_n || p.num_acc % nwg == 0, "every accumulator must always meet the same epilogue warpgroup");
+  DY_CHECK(!p.dual_issue || p.num_acc % 2 == 0, "every accumulator must always meet the same MMA issuer");
   DY_CHECK(!p.fuse_n || (p.fuse_n == 16 && p.tma_epi && p.slab == 64 && p.block_n == 64 && p.cout == 64 &&
                          p.n_tiles_n == 1 && p.residual == nullptr && p.out[1].mode == OUT_NONE &&
                          p.fuse_cout >= 1 && p.fuse_cout <= 16 && p.fuse_w && p.fuse_bias && p.fuse_out),
@@ -958,7 +972,7 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
   DY_CHECK(!p.split_n || (p.slab != 0 && !p.dual_issue && !p.fuse_n && p.num_acc == 2 && (p.block_n / 2) % p.slab == 0),
            "split-N epilogue needs a staged epilogue, one MMA issuer and a whole number of slabs per half tile");
   const size_t smem = conv_tc_smem_bytes(kchunk, p);
-  DY_CHECK(smem <= (size_t)kConvTcMaxSmem, "pipeline does not fit in shared memory");
+  DY_CHECK(smem <= (size_t)kConvTcMaxSmem - (p.num_epi_wg == 3 ? 4096 : 0), "pipeline does not fit in shared memory");
   const int tiles = p.n_tiles_m * p.n_tiles_n;
   int grid = tiles < num_sms ? tiles : num_sms;
   if (p.b_resident) {
@@ -973,14 +987,14 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
              "CTA-pair plan: 64-wide K chunks, streamed weights, one issuer, TMA staged epilogue");
     static bool attr2 = false;
     if (!attr2) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
       attr2 = true;
     }
     const int pair_tiles = ((p.n_tiles_m + 1) / 2) * p.n_tiles_n;
     int g2 = 2 * pair_tiles < num_sms ? 2 * pair_tiles : (num_sms & ~1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(g2);
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(conv_threads(2));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -992,32 +1006,33 @@ int launch_conv_tc(int kchunk, const CUtensorMap& a0, const CUtensorMap& a1, con
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
-    DY_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, true>, a0, a1, b, r, o, p));
+    DY_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false, true, 2>, a0, a1, b, r, o, p));
     DY_CUDA(cudaGetLastError());
     return DY_OK;
   }
+  // instantiations: (K chunk, fused tail, CTA pair, epilogue warpgroups)
+#define DY_LAUNCH_CONV(KC, FU, NW)                                                                                     \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KC, FU, false, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                   kConvTcMaxSmem - (NW == 3 ? 4096 : 0)));                                            \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<KC, FU, false, NW>, dim3(grid), dim3(conv_threads(NW)), smem, stream, pdl, \
+                              a0, a1, b, r, o, p));                                                                    \
+  } while (0)
   if (p.fuse_n) {
-    static bool attr32f = false;
-    if (!attr32f) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
-      attr32f = true;
-    }
-    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, true, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
+    if (nwg == 3) DY_LAUNCH_CONV(32, true, 3);
+    else DY_LAUNCH_CONV(32, true, 2);
   } else if (kchunk == 64) {
-    static bool attr64 = false;
-    if (!attr64) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
-      attr64 = true;
-    }
-    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<64, false, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
+    if (nwg == 3) DY_LAUNCH_CONV(64, false, 3);
+    else DY_LAUNCH_CONV(64, false, 2);
   } else {
-    static bool attr32 = false;
-    if (!attr32) {
-      DY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcMaxSmem));
-      attr32 = true;
-    }
-    DY_CUDA(launch_kernel_pdl(conv_tc_kernel<32, false, false>, dim3(grid), dim3(kNumThreads), smem, stream, pdl, a0, a1, b, r, o, p));
+    if (nwg == 3) DY_LAUNCH_CONV(32, false, 3);
+    else DY_LAUNCH_CONV(32, false, 2);
   }
+#undef DY_LAUNCH_CONV
   DY_CUDA(cudaGetLastError());
   return DY_OK;
 }

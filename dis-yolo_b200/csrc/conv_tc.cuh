@@ -78,6 +78,7 @@ struct ConvParams {
   int debug_skip;  // measurement aid: 1 = epilogue only drains the accumulator barrier (no math, no stores)
   int cta2;        // 1: CTA-pair plan -- 2-CTA clusters, tcgen05.mma.cta_group::2 with M = 256, each CTA stages half of the
                    // weight tile (64-wide K chunks, streamed weights, TMA staged epilogue)
+  int num_epi_wg;  // epilogue warpgroups: 2, or 3 for thin single-CTA tiles (<= 64 columns; 512-thread instantiation)
   int split_n;     // staged epilogue only: 1 = both epilogue warpgroups drain every tile, half of its columns each
                    // (0: they take alternate tiles)
   int tma_epi;     // staged epilogue only: out[0] (P1 layout) leaves through TMA stores, the residual

@@ -164,6 +164,7 @@ static int g_opt_split_n = -1;      // 0: epilogue warpgroups take alternate til
 static int g_opt_kchunk = -1;       // 32: 32-wide K chunks (SWIZZLE_64B) even where 64 divides the channel counts (A/B)
 static int g_opt_slab = -1;         // 32: 32-column staging slabs in the TMA epilogue (A/B)
 static int g_opt_cta2 = -1;         // 0: never plan CTA pairs (cta_group::2), 1: wherever legal, -1: planner's choice
+static int g_opt_epi_wg = -1;       // 2 / 3 epilogue warpgroups (3: thin single-CTA tiles only); -1: planner's choice
 static int g_opt_fuse_tail = -1;    // 0: convolutional82 as its own launch, otherwise fused into convolutional81's epilogue
 static int g_wg_dbg[4] = {0, 0, 0, 0};   // bring-up aid: wgrad UMMA descriptor overrides (0 = computed)
 
@@ -348,6 +349,13 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   if (p.tma_epi && cta2 && !halo && d.k == 3 && g_opt_slab < 0) p.slab = 32;
   DY_CHECK(nchunks * kchunk == K, "K chunking mismatch");
   p.fuse_n = d.fuse_n;      // (sizes the epilogue staging area)
+  // thin tiles: a third epilogue warpgroup (the 512-thread instantiation); decided before the stage count because
+  // it adds a third pair of staging buffers (tiles of <= 64 columns never use the column-split epilogue)
+  const bool wg3_ok = !cta2 && p.block_n <= 64;
+  bool wg3 = false;      // (measured, scripts/ab_opts.py tc_epi_wg=3: only conv3 / 6 / 8 gain 5 %, the 3x3 thin layers lose 5-15 %)
+  if (g_opt_epi_wg == 2) wg3 = false;
+  if (g_opt_epi_wg == 3) wg3 = wg3_ok;
+  p.num_epi_wg = wg3 ? 3 : 2;
   p.num_stages = conv_tc_pick_stages(kchunk, p);
   // deeper rings than 8 stages measured slower on every layer (profiles/r2_ab_opts.txt): default cap 8
   const int stage_cap = g_opt_max_stages >= 2 ? g_opt_max_stages : 8;
@@ -365,6 +373,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
   // four TMEM accumulator stages (two per issuer) when they fit: otherwise each issuer would be
   // serialised with its own epilogue warpgroup
   p.num_acc = (dual_issue && 4 * p.block_n <= 512) ? 4 : 2;
+  if (p.num_epi_wg == 3) p.num_acc = dual_issue ? 6 : 3;      // (block_n <= 64: at most 384 columns)
   // wide tiles (two TMEM stages only): both epilogue warpgroups drain every tile, half of its columns each, so the
   // accumulator returns to the MMA issuer after half the tcgen05.ld / residual round trips
   const bool split_ok = !dual_issue && p.slab != 0 && !d.fuse_n && p.num_acc == 2 && (p.block_n / 2) % p.slab == 0;
@@ -379,7 +388,7 @@ static int build_tc_plan(const TcConvDesc& d, int num_sms, TcPlan* plan) {
     p.fuse_w = d.fuse_w; p.fuse_bias = d.fuse_bias; p.fuse_out = d.fuse_out;
   }
   tc = 32;
-  while (tc < p.num_acc * p.block_n + (p.fuse_n ? 64 : 0)) tc <<= 1;
+  while (tc < p.num_acc * p.block_n + (p.fuse_n ? p.num_epi_wg * 32 : 0)) tc <<= 1;
   DY_CHECK(tc <= 512, "TMEM columns");
   p.tmem_cols = tc;
   const int a0_cols = (d.s == 2) ? 4 * d.cin0 : d.cin0;
@@ -979,6 +988,7 @@ int dy_set_option(const char* name, int32_t value) {
   else if (n == "tc_fuse_tail") g_opt_fuse_tail = value;
   else if (n == "tc_split_n") g_opt_split_n = value;
   else if (n == "tc_cta2") g_opt_cta2 = value;
+  else if (n == "tc_epi_wg") g_opt_epi_wg = value;
   else if (n == "tc_kchunk") g_opt_kchunk = value;
   else if (n == "tc_slab") g_opt_slab = value;
   else if (n == "tc_pdl") conv_tc_set_pdl(value < 0 ? 1 : value);

@@ -343,6 +343,7 @@ uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
  *   "conv1_tc"      0: the stem on CUDA cores instead of the tcgen05 im2col kernel
  *   "tc_split_n"    0: the two epilogue warpgroups take alternate tiles; 1: both drain every tile, half of its columns
  *                   each, wherever legal; -1 (default): planner's choice (tiles of 128+ columns)
+ *   "tc_epi_wg"     2 / 3 epilogue warpgroups (3 = the 512-thread instantiation, thin single-CTA tiles only; -1 planner)
  *   "tc_kchunk"     32: 32-wide K chunks everywhere (A/B);  "tc_slab"  32: 32-column TMA-epilogue staging slabs (A/B)
  *   "tc_fuse_tail"  0: convolutional82 as its own launch in dy_forward (default: fused into convolutional81)
  *   "wgrad_fuse_kw" 0 one CTA per tap / 1 (default) fused kernel rows where the N tile is kept / 2 always
