@@ -1,14 +1,17 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution kernel (see conv_tc.cuh for the scheme).
 //
-// CTA = 256 threads, 1 CTA per SM, persistent over output tiles (128 pixels x block_n channels):
-//   warp 0      TMA producer   (one elected lane): A tile [128 x KCHUNK] + B tile [block_n x KCHUNK]
-//                              per pipeline stage, 128B/64B hardware swizzle
-//   warp 1      MMA issuer     (one elected lane): tcgen05.mma kind::f16, M=128, N=block_n, K=16,
-//                              fp32 accumulators in TMEM, double buffered across tiles
-//   warp 2      TMEM allocator
-//   warps 4..7  epilogue: tcgen05.ld -> folded BN scale/shift -> leaky -> (+residual) -> bf16/fp32
-//                              stores in up to two destination layouts (same / space-to-depth /
-//                              2x-upsampled / fp32 head layouts); pad pixels are never written.
+// CTA = 384 threads (512 in the three-warpgroup instantiation), 1 CTA per SM, persistent over output tiles
+// (128 pixels x block_n channels; a CTA PAIR works on 256 pixels x block_n channels, see conv_tc_kernel):
+//   warp 0      TMA producer   (one elected lane): A box [128 or 136 x KCHUNK] + the weight chunk(s) [block_n x KCHUNK]
+//                              of a pipeline stage, 128B/64B hardware swizzle
+//   warp 1      MMA issuer     (one elected lane): tcgen05.mma kind::f16, M=128 (cta_group::2: 256), N=block_n, K=16,
+//                              fp32 accumulators in TMEM, 2-6 stages across tiles
+//   warp 2      TMEM allocator; second TMA producer when two MMA issuers split the stage ring (thin tiles)
+//   warp 3      second MMA issuer (thin tiles)
+//   warps 4..   epilogue warpgroups: tcgen05.ld -> folded BN scale/shift -> leaky -> (+residual) -> bf16/fp32
+//                              through swizzled staging buffers and TMA stores (or direct / cooperative stores) in up
+//                              to two destination layouts (same / space-to-depth / 2x-upsampled / fp32 head
+//                              layouts); pad pixels are never written.
 #include "conv_tc.cuh"
 
 namespace dy {
