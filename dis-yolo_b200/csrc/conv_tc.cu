@@ -126,13 +126,21 @@ constexpr int conv_threads(int nwg) { return 128 * (1 + nwg); }
 // (FFMA2 / FMUL2, sm_100): each lane of a pair is an ordinary IEEE round-to-nearest fma / mul, so the
 // results are bit-identical to the scalar form at half the issue slots -- the epilogue warps (2 per SM
 // sub-partition) are issue/latency bound on the thin layers.
-__device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r)[16], const float* s_scale,
-                                         const float* s_shift, int c0, float (&v)[16]) {
+// 16-byte shared-memory read through a 32-bit shared-window address (a generic pointer to a __shared__ array costs a
+// window-base computation per use once the register allocator starts rematerialising it)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+__device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r)[16], uint32_t s_scale,
+                                         uint32_t s_shift, int c0, float (&v)[16]) {
 #ifdef DY_SCALAR_EPILOGUE      // A/B build (scripts/build_variant.sh): the scalar form
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
-    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * j4);
-    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * j4);
+    const float4 sc = lds128(s_scale + (uint32_t)(c0 + 4 * j4) * 4u);
+    const float4 sh = lds128(s_shift + (uint32_t)(c0 + 4 * j4) * 4u);
     v[4 * j4 + 0] = fmaf(__uint_as_float(r[4 * j4 + 0]), sc.x, sh.x);
     v[4 * j4 + 1] = fmaf(__uint_as_float(r[4 * j4 + 1]), sc.y, sh.y);
     v[4 * j4 + 2] = fmaf(__uint_as_float(r[4 * j4 + 2]), sc.z, sh.z);
@@ -144,16 +152,19 @@ __device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r
   }
   return;
 #endif
-  const float2 al = make_float2(p.alpha, p.alpha);
+  // leaky: max(alpha*x, x); a linear layer uses alpha' = 1 (max(x, x) = x) -- no branch in the per-chunk code (the
+  // ncu source page showed ~100 issued instructions per 16-column chunk, a third of them control / address overhead)
+  const float alf = p.act ? p.alpha : 1.f;
+  const float2 al = make_float2(alf, alf);
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
-    const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * j4);   // smem broadcast
-    const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * j4);
+    const float4 sc = lds128(s_scale + (uint32_t)(c0 + 4 * j4) * 4u);   // smem broadcast
+    const float4 sh = lds128(s_shift + (uint32_t)(c0 + 4 * j4) * 4u);
     float2 a = __ffma2_rn(make_float2(__uint_as_float(r[4 * j4 + 0]), __uint_as_float(r[4 * j4 + 1])),
                           make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
     float2 b = __ffma2_rn(make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])),
                           make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
-    if (p.act) {
+    {
       const float2 ta = __fmul2_rn(a, al), tb = __fmul2_rn(b, al);
       a.x = fmaxf(ta.x, a.x); a.y = fmaxf(ta.y, a.y);
       b.x = fmaxf(tb.x, b.x); b.y = fmaxf(tb.y, b.y);
@@ -171,8 +182,8 @@ __device__ __forceinline__ void load_res16(const __nv_bfloat16* rp, uint4& a, ui
 
 // direct path: the row's owner thread adds its residual and writes its own pixels
 __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const PixelInfo& px, long long m,
-                                                      int gcol, const uint32_t (&r)[16], const float* s_scale,
-                                                      const float* s_shift, int c0, bool has_res, const uint4& ra,
+                                                      int gcol, const uint32_t (&r)[16], uint32_t s_scale,
+                                                      uint32_t s_shift, int c0, bool has_res, const uint4& ra,
                                                       const uint4& rb) {
   float v[16];
   bn_act16(p, r, s_scale, s_shift, c0, v);
@@ -185,7 +196,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const ConvParams& p, const
 
 // staged path, phase 1: (+ residual already sitting in the staging row) -> bf16 -> staging row
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const uint32_t (&r)[16],
-                                                      const float* s_scale, const float* s_shift, int c0,
+                                                      uint32_t s_scale, uint32_t s_shift, int c0,
                                                       bool has_res, uint8_t* srow /* row base + 2*col */) {
   float v[16];
   bn_act16(p, r, s_scale, s_shift, c0, v);
@@ -207,7 +218,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 // (+ residual already in place) -> bf16 in place; pad pixels / rows beyond M become zeros because
 // the TMA store writes every row of the box
 __device__ __forceinline__ void epilogue_chunk_swz(const ConvParams& p, const uint32_t (&r)[16],
-                                                   const float* s_scale, const float* s_shift, int c0,
+                                                   uint32_t s_scale, uint32_t s_shift, int c0,
                                                    bool has_res, bool valid, uint8_t* srow, int ch0, int rsw) {
   float v[16];
   bn_act16(p, r, s_scale, s_shift, c0, v);
@@ -521,6 +532,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int Hp = p.H + 1, Wp = p.W + 1;
     float* my_scale = s_scale[wg];
     float* my_shift = s_shift[wg];
+    const uint32_t scale_a = smem_u32(my_scale), shift_a = smem_u32(my_shift);      // 32-bit shared-window addresses
     int cached_n0 = -1;
     uint32_t res_par = 0u;                              // bit b = parity of res_full[wg][b]; persists across tiles
     uint32_t sc = 0u;                                   // slabs processed by this warpgroup so far (buffer = sc & 1)
@@ -600,7 +612,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
             if (do_res) load_res16(res_row + c0 + 16, ra1, rb1);
           }
-          if (px.valid) epilogue_chunk_direct(p, px, m, n0 + c0, r0, my_scale, my_shift, c0, has_res, ra0, rb0);
+          if (px.valid) epilogue_chunk_direct(p, px, m, n0 + c0, r0, scale_a, shift_a, c0, has_res, ra0, rb0);
           if (more1) {
             tmem_ld_wait();
             if (c0 + 32 < p.block_n) {
@@ -608,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
               if (do_res) load_res16(res_row + c0 + 32, ra0, rb0);
             }
             if (px.valid)
-              epilogue_chunk_direct(p, px, m, n0 + c0 + 16, r1, my_scale, my_shift, c0 + 16, has_res, ra1, rb1);
+              epilogue_chunk_direct(p, px, m, n0 + c0 + 16, r1, scale_a, shift_a, c0 + 16, has_res, ra1, rb1);
           }
         }
       } else if (p.tma_epi) {
@@ -661,13 +673,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tmem_ld_wait();
             const bool more1 = c0 + 16 < p.slab;
             if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
+#ifdef DY_DEBUG_SKIP
             if (p.debug_skip != 2)
-              epilogue_chunk_swz(p, r0, my_scale, my_shift, cbase + slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
+#endif
+              epilogue_chunk_swz(p, r0, scale_a, shift_a, cbase + slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
             if (more1) {
               tmem_ld_wait();
               if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
+#ifdef DY_DEBUG_SKIP
               if (p.debug_skip != 2)
-                epilogue_chunk_swz(p, r1, my_scale, my_shift, cbase + slab0 + c0 + 16, has_res, px.valid, srow,
+#endif
+                epilogue_chunk_swz(p, r1, scale_a, shift_a, cbase + slab0 + c0 + 16, has_res, px.valid, srow,
                                    (c0 + 16) >> 3, rsw);
             }
           }
@@ -799,11 +815,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tmem_ld_wait();
             const bool more1 = c0 + 16 < p.slab;
             if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
-            epilogue_chunk_staged(p, r0, my_scale, my_shift, cbase + slab0 + c0, has_res, srow + c0 * 2);
+            epilogue_chunk_staged(p, r0, scale_a, shift_a, cbase + slab0 + c0, has_res, srow + c0 * 2);
             if (more1) {
               tmem_ld_wait();
               if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
-              epilogue_chunk_staged(p, r1, my_scale, my_shift, cbase + slab0 + c0 + 16, has_res, srow + (c0 + 16) * 2);
+              epilogue_chunk_staged(p, r1, scale_a, shift_a, cbase + slab0 + c0 + 16, has_res, srow + (c0 + 16) * 2);
             }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
