@@ -134,6 +134,15 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void bn_act16(const ConvParams& p, const uint32_t (&r)[16], uint32_t s_scale,
                                          uint32_t s_shift, int c0, float (&v)[16]) {
 #ifdef DY_SCALAR_EPILOGUE      // A/B build (scripts/build_variant.sh): the scalar form
@@ -219,13 +228,13 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 // the TMA store writes every row of the box
 __device__ __forceinline__ void epilogue_chunk_swz(const ConvParams& p, const uint32_t (&r)[16],
                                                    uint32_t s_scale, uint32_t s_shift, int c0,
-                                                   bool has_res, bool valid, uint8_t* srow, int ch0, int rsw) {
+                                                   bool has_res, bool valid, uint32_t srow_a, int ch0, int rsw) {
   float v[16];
   bn_act16(p, r, s_scale, s_shift, c0, v);
-  uint4* qa = reinterpret_cast<uint4*>(srow + ((ch0 ^ rsw) << 4));
-  uint4* qb = reinterpret_cast<uint4*>(srow + (((ch0 + 1) ^ rsw) << 4));
+  // (32-bit shared-window addresses; ch0 is even, so chunk ch0+1 of the swizzled row is the neighbour 16 bytes: ^ 16)
+  const uint32_t qa = srow_a + (uint32_t)((ch0 ^ rsw) << 4), qb = qa ^ 16u;
   if (has_res) {
-    const uint4 ra = *qa, rb = *qb;
+    const uint4 ra = lds128u(qa), rb = lds128u(qb);
     add_res16(v, ra, rb);
   }
   uint4 a = make_uint4(0, 0, 0, 0), b = a;
@@ -235,8 +244,8 @@ __device__ __forceinline__ void epilogue_chunk_swz(const ConvParams& p, const ui
     b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
     b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
   }
-  *qa = a;
-  *qb = b;
+  sts128u(qa, a);
+  sts128u(qb, b);
 }
 
 // destination element offset of a pixel's row in an output form (without the channel), or -1
@@ -667,7 +676,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             if (elected) bulk_wait_read<1>();                // the store two slabs ago has read this buffer
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           }
-          uint8_t* srow = stg + (size_t)row * epi_pitch;
+          const uint32_t srow = smem_u32(stg) + (uint32_t)row * epi_pitch;
           tmem_ld16(taddr + (uint32_t)slab0, r0);
           for (int c0 = 0; c0 < p.slab; c0 += 32) {
             tmem_ld_wait();
