@@ -428,8 +428,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int ring = p.dual_issue ? (it & 1) : 0;
         int stage = ring ? rstage[1] : rstage[0];
         uint32_t phase = ring ? rphase[1] : rphase[0];
-        const int m0 = (tile / p.n_tiles_n) * kTileM + m_off;
-        const int n0 = (tile % p.n_tiles_n) * p.block_n;
+        const int mt = p.n_tiles_n == 1 ? tile : tile / p.n_tiles_n;      // (integer divisions cost ~20 issue slots each)
+        const int m0 = mt * kTileM + m_off;
+        const int n0 = (tile - mt * p.n_tiles_n) * p.block_n;
         const int nb0 = n0 + (CTA2 ? (int)cta_rank * b_rows : 0);   // first weight row this CTA stages
         if (has_res) {
           // pull the residual tile towards L2 now; the epilogue reads it a few microseconds later
@@ -489,14 +490,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
       uint32_t stage = 0, phase = 0;
       int it = issuer;
+      int acc = issuer;                                  // = it % num_acc, used for the (it / num_acc)-th time (aph = its parity)
+      uint32_t aph = 0u;
       for (int tile = tile0 + issuer * tstride; tile < num_tiles; tile += it_step * tstride, it += it_step) {
         // accumulator stage of tile `it`: it % num_acc, used for the (it / num_acc)-th time.  num_acc is even with two
         // issuers (issuer = parity of it = parity of acc) and a multiple of the number of epilogue warpgroups when
         // they take alternate tiles, so every accumulator always meets the same issuer and the same warpgroup (an
         // mbarrier only tells consecutive phases apart).
-        const int acc = it % p.num_acc;
+        // (acc / aph are advanced at the end of the iteration: no division in the loop)
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-        mbar_wait(&tempty_bar[acc], ((uint32_t)(it / p.num_acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[acc], aph ^ 1u);          // epilogue has drained this accumulator
         tc_fence_after();
         uint32_t acc_flag = 0u;
         for (int s = 0; s < p.num_seg; ++s) {
@@ -530,6 +533,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
         if constexpr (CTA2) umma_commit_cta2(&tfull_bar[acc]);    // (both CTAs' epilogues)
         else umma_commit(&tfull_bar[acc]);              // accumulator complete -> epilogue
+        acc += it_step;                                 // it_step <= num_acc: one wrap at most
+        if (acc >= p.num_acc) {
+          acc -= p.num_acc;
+          aph ^= 1u;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -574,22 +582,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int ncols = p.split_n ? (p.block_n >> 1) : p.block_n;    // columns this warpgroup drains
     int it = t_first;
     uint32_t my_tiles = 0u;                             // tiles this warpgroup has processed (parity of its tables)
+    // The per-tile code of a thin layer is instruction-issue bound (ncu: five integer divisions of ~20 issue slots
+    // each per tile and warp): accumulator index / phase and -- when this warpgroup's row offset advances by a
+    // constant, i.e. with one N tile -- the pixel coordinates of the thread's row are advanced incrementally.
+    int acc = t_first % p.num_acc;                      // = it % num_acc (no split: the accumulators with it % NWG == wg)
+    uint32_t acc_phase = 0u;                            // = (it / num_acc) & 1
+    const bool inc_px = p.n_tiles_n == 1;
+    int cx = 0, cy = 0, cn = 0, dx = 0, dy = 0, dn = 0;  // coordinates of this thread's row / their per-iteration step
+    if (inc_px) {
+      const uint32_t mu = (uint32_t)((tile0 + t_first * tstride) * kTileM + m_off + q * 32 + lane);
+      uint32_t t = mu / (uint32_t)Wp;
+      cx = (int)(mu - t * (uint32_t)Wp);
+      cn = (int)(t / (uint32_t)Hp);
+      cy = (int)(t - (uint32_t)cn * (uint32_t)Hp);
+      const uint32_t du = (uint32_t)(t_step * tstride * kTileM);
+      t = du / (uint32_t)Wp;
+      dx = (int)(du - t * (uint32_t)Wp);
+      dn = (int)(t / (uint32_t)Hp);
+      dy = (int)(t - (uint32_t)dn * (uint32_t)Hp);
+    }
     for (int tile = tile0 + t_first * tstride; tile < num_tiles; tile += t_step * tstride, it += t_step, ++my_tiles) {
-      const int acc = it % p.num_acc;                   // (no split: this warpgroup owns the accumulators it % NWG == wg)
-      const uint32_t acc_phase = (uint32_t)(it / p.num_acc) & 1u;
-      const int m0 = (tile / p.n_tiles_n) * kTileM + m_off;
-      const int n0 = (tile % p.n_tiles_n) * p.block_n;
+      const int mt = inc_px ? tile : tile / p.n_tiles_n;
+      const int m0 = mt * kTileM + m_off;
+      const int n0 = (tile - mt * p.n_tiles_n) * p.block_n;
       const long long m = (long long)m0 + q * 32 + lane;
       PixelInfo px;
-      {
-        // 32-bit unsigned arithmetic (M < 2^31 is checked on the host): two cheap divisions per tile
+      if (inc_px) {
+        px.x = cx; px.y = cy; px.n = cn;
+        cx += dx;
+        if (cx >= Wp) { cx -= Wp; ++cy; }
+        cy += dy;
+        if (cy >= Hp) { cy -= Hp; ++cn; }
+        cn += dn;
+      } else {
+        // 32-bit unsigned arithmetic (M < 2^31 is checked on the host)
         const uint32_t mu = (uint32_t)m;
         const uint32_t t = mu / (uint32_t)Wp;
         px.x = (int)(mu - t * (uint32_t)Wp);
         px.n = (int)(t / (uint32_t)Hp);
         px.y = (int)(t - (uint32_t)px.n * (uint32_t)Hp);
-        px.valid = (m < p.M) && (px.x < p.W) && (px.y < p.H);
       }
+      px.valid = (m < p.M) && (px.x < p.W) && (px.y < p.H);
       if (n0 != cached_n0) {
         // (re)stage this N tile's folded BN scale/shift; 128 threads of the warpgroup only
         asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
@@ -646,7 +679,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int row = q * 32 + lane;
         const int rsw = (p.slab == 64) ? (row & 7) : ((row >> 1) & 3);      // this row's swizzle XOR
         const int vpr = p.slab >> 3, vsh = (p.slab == 64) ? 3 : 2;
-        const int nslab = ncols / p.slab;
+        const int nslab = ncols >> (p.slab == 64 ? 6 : 5);   // slab is 64 or 32
         const int nb = n0 + cbase;                           // first global column of this warpgroup
         const bool elected = wg_tid == 0;
         const bool dual = p.out[1].mode != OUT_NONE;
@@ -734,8 +767,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int ntile = tile + t_step * tstride;
                 if (ntile < num_tiles) {
                   have = true;
-                  nm0 = (ntile / p.n_tiles_n) * kTileM + m_off;
-                  nn0 = (ntile % p.n_tiles_n) * p.block_n + cbase;
+                  const int nmt = inc_px ? ntile : ntile / p.n_tiles_n;
+                  nm0 = nmt * kTileM + m_off;
+                  nn0 = (ntile - nmt * p.n_tiles_n) * p.block_n + cbase;
                 }
               }
               if (have) {
@@ -853,6 +887,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           if constexpr (CTA2) mbar_arrive_leader(&tempty_bar[acc]);
           else mbar_arrive(&tempty_bar[acc]);
         }
+      }
+      acc += t_step;                                    // t_step <= num_acc: one wrap at most
+      if (acc >= p.num_acc) {
+        acc -= p.num_acc;
+        acc_phase ^= 1u;
       }
     }
     if constexpr (FUSE) {
