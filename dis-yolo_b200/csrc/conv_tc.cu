@@ -567,11 +567,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       tmem_ld_wait();
       tc_fence_before();
       if (f_px.valid) {
+        // (one pointer walking the channel planes, biases read as float4: the rolled form recomputed a 64-bit
+        // address, compared and loaded a bias per channel -- ~140 issued instructions per tile and warp)
         float* d = p.fuse_out + (((long long)f_px.n * p.fuse_cout) * p.H + f_px.y) * p.W + f_px.x;
         const long long plane = (long long)p.H * p.W;
+        const int nout = p.fuse_cout;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < p.fuse_cout) __stcs(d + j * plane, __uint_as_float(fr[j]) + s_fbias[j]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (4 * j4 >= nout) break;
+          const float4 bq = *reinterpret_cast<const float4*>(&s_fbias[4 * j4]);
+          const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (4 * j4 + e < nout) __stcs(d, __uint_as_float(fr[4 * j4 + e]) + bb[e]);
+            d += plane;
+          }
+        }
       }
     };
     // split_n: BOTH warpgroups drain EVERY tile, half of its columns each -- the accumulator is handed back to
