@@ -14,6 +14,8 @@
 //                              layouts); pad pixels are never written.
 #include "conv_tc.cuh"
 
+#include <type_traits>
+
 namespace dy {
 
 namespace {
@@ -226,14 +228,15 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvParams& p, const
 // TMA staged path, phase 1: 16 columns = two 16-byte chunks (index ch0, ch0+1) of a swizzled row;
 // (+ residual already in place) -> bf16 in place; pad pixels / rows beyond M become zeros because
 // the TMA store writes every row of the box
+template <bool RES>
 __device__ __forceinline__ void epilogue_chunk_swz(const ConvParams& p, const uint32_t (&r)[16],
                                                    uint32_t s_scale, uint32_t s_shift, int c0,
-                                                   bool has_res, bool valid, uint32_t srow_a, int ch0, int rsw) {
+                                                   bool valid, uint32_t srow_a, int ch0, int rsw) {
   float v[16];
   bn_act16(p, r, s_scale, s_shift, c0, v);
   // (32-bit shared-window addresses; ch0 is even, so chunk ch0+1 of the swizzled row is the neighbour 16 bytes: ^ 16)
   const uint32_t qa = srow_a + (uint32_t)((ch0 ^ rsw) << 4), qb = qa ^ 16u;
-  if (has_res) {
+  if constexpr (RES) {
     const uint4 ra = lds128u(qa), rb = lds128u(qb);
     add_res16(v, ra, rb);
   }
@@ -721,24 +724,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
           }
           const uint32_t srow = smem_u32(stg) + (uint32_t)row * epi_pitch;
-          tmem_ld16(taddr + (uint32_t)slab0, r0);
-          for (int c0 = 0; c0 < p.slab; c0 += 32) {
-            tmem_ld_wait();
-            const bool more1 = c0 + 16 < p.slab;
-            if (more1) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 16), r1);
-#ifdef DY_DEBUG_SKIP
-            if (p.debug_skip != 2)
-#endif
-              epilogue_chunk_swz(p, r0, scale_a, shift_a, cbase + slab0 + c0, has_res, px.valid, srow, c0 >> 3, rsw);
-            if (more1) {
+          // the chunk sequence of one slab, unswitched on (residual?, 2 or 4 chunks): no loop control, no per-chunk
+          // tests of tile-invariant conditions in the issue-bound part of the epilogue
+          auto run_slab = [&](auto res_tag, auto nch_tag) {
+            constexpr bool RES = decltype(res_tag)::value;
+            constexpr int NCH = decltype(nch_tag)::value;
+            tmem_ld16(taddr + (uint32_t)slab0, r0);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ch += 2) {
               tmem_ld_wait();
-              if (c0 + 32 < p.slab) tmem_ld16(taddr + (uint32_t)(slab0 + c0 + 32), r0);
-#ifdef DY_DEBUG_SKIP
-              if (p.debug_skip != 2)
-#endif
-                epilogue_chunk_swz(p, r1, scale_a, shift_a, cbase + slab0 + c0 + 16, has_res, px.valid, srow,
-                                   (c0 + 16) >> 3, rsw);
+              tmem_ld16(taddr + (uint32_t)(slab0 + 16 * (ch + 1)), r1);
+              epilogue_chunk_swz<RES>(p, r0, scale_a, shift_a, cbase + slab0 + 16 * ch, px.valid, srow, 2 * ch, rsw);
+              tmem_ld_wait();
+              if (ch + 2 < NCH) tmem_ld16(taddr + (uint32_t)(slab0 + 16 * (ch + 2)), r0);
+              epilogue_chunk_swz<RES>(p, r1, scale_a, shift_a, cbase + slab0 + 16 * (ch + 1), px.valid, srow, 2 * ch + 2, rsw);
             }
+          };
+#ifdef DY_DEBUG_SKIP
+          if (p.debug_skip == 2) {
+            for (int c0 = 0; c0 < p.slab; c0 += 16) { tmem_ld16(taddr + (uint32_t)(slab0 + c0), r0); tmem_ld_wait(); }
+          } else
+#endif
+          if (p.slab == 64) {
+            if (has_res) run_slab(std::true_type{}, std::integral_constant<int, 4>{});
+            else run_slab(std::false_type{}, std::integral_constant<int, 4>{});
+          } else {
+            if (has_res) run_slab(std::true_type{}, std::integral_constant<int, 2>{});
+            else run_slab(std::false_type{}, std::integral_constant<int, 2>{});
           }
           if (sidx + 1 == nslab) {
             // every tcgen05.ld of this tile has completed: hand the accumulator back to the MMA issuer
