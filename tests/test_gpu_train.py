@@ -557,3 +557,31 @@ def test_fully_unlocked_net_trains_on_the_tensor_core_engine():
     print('stage-2 loss history', hist)
     assert np.all(np.isfinite(hist)) and hist[-1] < hist[0]
     eng.close()
+
+
+def test_losses_with_degenerate_ground_truth_box():
+    """overlaps_graph without epsilon (yolo3_net_pos.py:954-975): image 1's ground truth is ONE zero-area box, so every
+    RoI / ground-truth IoU is 0 or 0/0 and the image contributes no positive RoI to loss_mask; the eight scalars
+    still match the float64 oracle (the label tensors are whatever they are: both sides read the same arrays)."""
+    import disyolo_b200 as dy
+    W, img, labels, tb, tm, pp, pg, thresh = _setup()
+    B, size = img.shape[0], img.shape[1]
+    tb = tb.copy()
+    tb[1] = 0.0
+    tb[1, 0, 0, 0, 0] = [0.4, 0.6, 0.0, 0.0, 1.0]          # xc, yc, w = h = 0: kept (non-zero row), zero area
+    eng = dy.Engine(image_size=size, max_batch=B, precision='fp32')
+    eng.load_weights(W)
+    eng.train_init()
+    perms = [(pp[b].tolist(), pg[b].tolist()) for b in range(B)]
+    T.NP_DT = np.float64
+    try:
+        losses = eng.train_forward(img, labels, tb[:, 0, 0, 0], tm, pp, pg, thresh)
+        ol, og, Wn, adam, aux = T.train_step(img, W, O.default_lock_flags(), labels, tb, tm, perms, det_thresh=thresh,
+                                             lr=1e-4, adam=None, step=1)
+    finally:
+        T.NP_DT = np.float32
+    want = np.array([ol[k] for k in ('total', 'obj', 'noobj', 'cls', 'xy', 'wh', 'mask', 'l2')])
+    print('degenerate-gt losses', losses, 'oracle', want)
+    assert np.all(np.isfinite(losses))
+    assert np.allclose(losses, want, rtol=1e-4, atol=1e-5)
+    eng.close()

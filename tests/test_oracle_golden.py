@@ -215,3 +215,25 @@ def test_product_and_oracle_lively_weights_are_bit_identical():
         assert sorted(a) == sorted(b)
         for k in a:
             assert a[k].dtype == b[k].dtype == np.float32 and np.array_equal(a[k], b[k]), k
+
+
+def test_overlaps_graph_degenerate_boxes():
+    """overlaps_graph (yolo3_net_pos.py:954-975) has no epsilon: two zero-area boxes give 0/0 = NaN, which can never
+    satisfy `IoU >= 0.5`, so such a RoI is not a positive (the device kernel maps NaN to -1 in the same place,
+    csrc/train.cu mask_roi_kernel); a zero-area box against a proper one is a plain 0."""
+    from oracle import dis_oracle_train as T
+    deg = np.array([[0.3, 0.3, 0.3, 0.3]], np.float32)
+    box = np.array([[0.1, 0.1, 0.5, 0.5], [0.3, 0.3, 0.3, 0.3]], np.float32)
+    ov = T.overlaps(deg, box)
+    assert ov.shape == (1, 2) and ov[0, 0] == 0.0 and np.isnan(ov[0, 1])
+    # through mask_rois: the only proposal and the only ground-truth box are the same zero-area box -> no positive RoI
+    det = np.zeros((30, 6), np.float32)
+    det[0, :4] = deg[0]
+    tb = np.zeros((20, 5), np.float32)
+    tb[0] = [0.3, 0.3, 0.0, 0.0, 1.0]            # xc, yc, w, h, class: kept (non-zero row), zero area
+    rois, assign, keep = T.mask_rois(det, tb, list(range(30)), list(range(20)))
+    assert len(rois) == 0 and keep.tolist() == [0]
+    # ... while a proper ground-truth box is its own positive (IoU 1 with itself)
+    tb[0] = [0.3, 0.3, 0.2, 0.2, 1.0]
+    rois, assign, keep = T.mask_rois(det, tb, list(range(30)), list(range(20)))
+    assert len(rois) == 1 and assign.tolist() == [0]
