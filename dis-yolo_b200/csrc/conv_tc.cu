@@ -424,6 +424,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
       const int ring_sz = p.dual_issue ? p.num_stages / 2 : p.num_stages;
       const int it_step = split ? 2 : 1;
+      // 32-bit shared-window addresses of the barrier arrays and of the stage ring (see common.cuh)
+      const uint32_t full_a = opaque_u32(smem_u32(full_bar)), empty_a = opaque_u32(smem_u32(empty_bar));
+      const uint32_t stage_a = opaque_u32(smem_base + stages_off);
       int rstage[2] = {0, 0};
       uint32_t rphase[2] = {0u, 0u};
       int it = my_ring;
@@ -446,22 +449,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const uint32_t tx = a_tx + (p.b_resident ? 0u : (uint32_t)sg.ntap * b_bytes);
           for (int c = 0; c < sg.nchunk; ++c) {
             const int gs = ring * ring_sz + stage;                   // global stage slot
-            mbar_wait(&empty_bar[gs], phase ^ 1u);
-            uint8_t* sa = smem_gen + stages_off + (size_t)gs * stage_bytes;
+            mbar_wait_a(empty_a + 8u * (uint32_t)gs, phase ^ 1u);
+            const uint32_t sa = stage_a + (uint32_t)gs * stage_bytes, fb = full_a + 8u * (uint32_t)gs;
             if constexpr (CTA2) {
               // the leader's barrier counts the bytes of both CTAs (complete_tx may precede expect_tx within a phase)
-              if (cta_rank == 0) mbar_expect_tx(&full_bar[gs], 2u * tx);
-              tma_load_2d_cta2(sa, am, &full_bar[gs], sg.col0 + c * KCHUNK, m0 + sg.shift);
+              if (cta_rank == 0) mbar_expect_tx_a(fb, 2u * tx);
+              tma_load_2d_cta2_a(sa, am, fb, sg.col0 + c * KCHUNK, m0 + sg.shift);
               for (int t = 0; t < sg.ntap; ++t)
-                tma_load_2d_cta2(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[gs],
-                                 (sg.tap_b0[t] + c) * KCHUNK, nb0);
+                tma_load_2d_cta2_a(sa + a_bytes + (uint32_t)t * b_bytes, &mapB, fb, (sg.tap_b0[t] + c) * KCHUNK, nb0);
             } else {
-              mbar_expect_tx(&full_bar[gs], tx);
-              tma_load_2d(sa, am, &full_bar[gs], sg.col0 + c * KCHUNK, m0 + sg.shift);
+              mbar_expect_tx_a(fb, tx);
+              tma_load_2d_a(sa, am, fb, sg.col0 + c * KCHUNK, m0 + sg.shift);
               if (!p.b_resident) {
                 for (int t = 0; t < sg.ntap; ++t)
-                  tma_load_2d(sa + a_bytes + (size_t)t * b_bytes, &mapB, &full_bar[gs],
-                              (sg.tap_b0[t] + c) * KCHUNK, nb0);
+                  tma_load_2d_a(sa + a_bytes + (uint32_t)t * b_bytes, &mapB, fb, (sg.tap_b0[t] + c) * KCHUNK, nb0);
               }
             }
             if (++stage == ring_sz) {
@@ -485,6 +486,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       // descriptor bits that never change: LBO=1, SBO, version, layout
       const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46) | ((uint64_t)kLayout << 61);
       const uint32_t S = (uint32_t)(p.dual_issue ? p.num_stages / 2 : p.num_stages);   // this issuer's ring
+      const uint32_t full_a = opaque_u32(smem_u32(full_bar)), empty_a = opaque_u32(smem_u32(empty_bar));
       const uint32_t ring_base = (uint32_t)issuer * S;
       const uint32_t b16 = b_bytes >> 4;
       if (p.b_resident) {
@@ -509,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
           const int nchunk = p.seg[s].nchunk, ntap = p.seg[s].ntap;
           for (int c = 0; c < nchunk; ++c) {
             const uint32_t gs = ring_base + stage;
-            mbar_wait(&full_bar[gs], phase);            // TMA bytes have landed
+            mbar_wait_a(full_a + 8u * gs, phase);       // TMA bytes have landed
             tc_fence_after();
             // (a clustered CTA's shared-window addresses carry its rank above bit 18: keep the descriptor's 14 bits)
             const uint32_t sa16 = ((smem_base + stages_off + gs * stage_bytes) & 0x3FFFFu) >> 4;
@@ -526,8 +528,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 acc_flag = 1u;
               }
             }
-            if constexpr (CTA2) umma_commit_cta2(&empty_bar[gs]);   // (both CTAs' slots)
-            else umma_commit(&empty_bar[gs]);           // frees the smem slot when the MMAs retire
+            if constexpr (CTA2) umma_commit_cta2_a(empty_a + 8u * gs);   // (both CTAs' slots)
+            else umma_commit_a(empty_a + 8u * gs);      // frees the smem slot when the MMAs retire
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;
