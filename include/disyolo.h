@@ -341,6 +341,9 @@ uint32_t dy_crc32c(const void* data, uint64_t n, uint32_t crc);
  *   "tc_max_stages"    cap of the shared-memory pipeline depth (2..16)
  *   "tc_skip_epilogue"          measurement only: epilogues drain the accumulator and do nothing else
  *   "conv1_tc"      0: the stem on CUDA cores instead of the tcgen05 im2col kernel
+ *   "tc_cta2"       0: never plan CTA pairs (2-CTA clusters, tcgen05.mma.cta_group::2 with M = 256, each CTA staging half
+ *                   of the weight tile); 1: wherever legal; -1 (default): every 3x3 / plain 1x1 layer with >= 128 output
+ *                   channels and at least one wave of tiles
  *   "tc_split_n"    0: the two epilogue warpgroups take alternate tiles; 1: both drain every tile, half of its columns
  *                   each, wherever legal; -1 (default): planner's choice (tiles of 128+ columns)
  *   "tc_epi_wg"     2 / 3 epilogue warpgroups (3 = the 512-thread instantiation, thin single-CTA tiles only; -1 planner)

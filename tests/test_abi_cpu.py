@@ -118,3 +118,44 @@ def test_yolonet_surface_without_gpu(built_lib):
         from disyolo_b200 import _lib
         with pytest.raises(_lib.DisYoloError):
             m.YOLONet(False)
+
+
+def test_every_set_option_name_is_documented_in_the_header():
+    """dy_set_option switches (csrc/net.cu) <-> the list in include/disyolo.h: a switch nobody can look up is a trap."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, 'dis-yolo_b200', 'csrc', 'net.cu')).read()
+    body = src[src.index('int dy_set_option('):]
+    body = body[:body.index('\n}\n')]
+    names = set(re.findall(r'n == "([a-z0-9_]+)"', body))
+    assert len(names) >= 20, names
+    hdr = open(os.path.join(root, 'include', 'disyolo.h')).read()
+    doc = hdr[hdr.index('Tuning / test / measurement overrides'):hdr.index('int dy_set_option(')]
+    missing = sorted(n for n in names if '"%s"' % n not in doc)
+    assert not missing, 'undocumented dy_set_option names: %s' % missing
+
+
+def test_committed_traffic_figure_matches_the_committed_launch_list():
+    """bench.py reports roofline.traffic from profiles/traffic.json; it must be what the committed ncu launch list of
+    the bench command says (scripts/traffic_from_launches.py), not a stale constant."""
+    import csv
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tj = json.load(open(os.path.join(root, 'profiles', 'traffic.json')))
+    rows = list(csv.reader(open(os.path.join(root, 'profiles', 'r2_launches.csv'), errors='replace')))
+    hi = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+    hdr = rows[hi]
+    ki, mi, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot, launches = 0.0, 0
+    for r in rows[hi + 1:]:
+        if len(r) <= vi or 'conv_tc_kernel' not in r[ki]:
+            continue
+        if r[mi] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            tot += float(r[vi].replace(',', '')) * scale.get(r[ui], 1.0)
+        if r[mi] == 'gpu__time_duration.sum':
+            launches += 1
+    assert launches == 2 * tj['conv_tc_launches_per_step'] == 160
+    assert abs(tot / 2 - tj['conv_tc_dram_bytes_per_step']) < 1e-6 * tot
